@@ -1,0 +1,182 @@
+"""Seeded synthetic inputs at the boundary of the mask-proposal scoring path.
+
+The reference consumes SAM output (``masks bool[N,H,W]``, ``boxes int64[N,4]`` XYWH,
+Hybridgl_main.py:85-90), a raw RGB frame (``image['sam_img']``, data/dataset_refer_bert.py:113),
+CLIP text embeddings (Hybridgl_main.py:150-166), a GEM heat-map (Hybridgl_main.py:200-201) and a
+ground-truth mask (data/dataset_refer_bert.py:116-121).  None of the producers (SAM / GEM / spaCy /
+RefCOCO) is available offline, so this module draws tensors of the same shape, dtype and statistics
+(SURVEY.md section 8(d) and Appendix D).  Pure numpy, no device code: the same generator feeds the
+CUDA path, the oracle and the golden-vector script.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional
+
+import numpy as np
+
+DIRFLAGS = ("none", "left", "right", "middle", "up", "down")          # utils.py:102-133
+RELAFLAGS = ("none", "left", "right", "up", "down", "big", "small", "within")  # utils.py:240-268
+
+
+@dataclasses.dataclass
+class Expression:
+    """Per-expression host-side inputs (what spaCy + encode_text + GEM hand to the path)."""
+    sentence_feat: np.ndarray            # f32 [De]   encode_text(sentence)            Hybridgl_main.py:150
+    noun_feat: np.ndarray                # f32 [De]   encode_text(noun_phrase)         Hybridgl_main.py:151
+    other_feats: np.ndarray              # f32 [K,De] encode_text('a photo of '+noun)  Hybridgl_main.py:159-161 (K may be 0)
+    dirflag: str                         # extract_dir_phrase                          Hybridgl_main.py:143
+    relaflag: str                        # extract_rela_word                           Hybridgl_main.py:177
+    heatmap: np.ndarray                  # f32 [H,W]  GEM map after T.Resize           Hybridgl_main.py:200-201
+
+
+@dataclasses.dataclass
+class Item:
+    """One image with its proposals and expressions (one DataLoader item of the reference)."""
+    image: np.ndarray                    # u8 [H,W,3] RGB
+    masks: np.ndarray                    # bool [N,H,W]
+    boxes: np.ndarray                    # int64 [N,4] XYWH
+    target: np.ndarray                   # u8 [H,W] {0,1}
+    expressions: List[Expression]
+    features: Optional[np.ndarray] = None  # f32 [N,De] hybrid CLIP features (stand-in for CLIPViTFM.forward)
+
+    @property
+    def n_masks(self) -> int:
+        return int(self.masks.shape[0])
+
+
+def _smooth_noise(rng: np.random.Generator, h: int, w: int, c: int, cells: int = 12) -> np.ndarray:
+    """Low-pass noise: bilinear upsample of a coarse random lattice (keeps blur != identity)."""
+    gy, gx = cells + 2, cells + 2
+    lat = rng.random((gy, gx, c), dtype=np.float32)
+    ys = np.linspace(0, gy - 1.001, h, dtype=np.float32)
+    xs = np.linspace(0, gx - 1.001, w, dtype=np.float32)
+    y0 = ys.astype(np.int64); x0 = xs.astype(np.int64)
+    fy = (ys - y0)[:, None, None]; fx = (xs - x0)[None, :, None]
+    a = lat[y0][:, x0]; b = lat[y0][:, x0 + 1]; cc = lat[y0 + 1][:, x0]; d = lat[y0 + 1][:, x0 + 1]
+    return (a * (1 - fy) * (1 - fx) + b * (1 - fy) * fx + cc * fy * (1 - fx) + d * fy * fx).astype(np.float32)
+
+
+def make_image(rng: np.random.Generator, h: int, w: int) -> np.ndarray:
+    base = _smooth_noise(rng, h, w, 3)
+    tex = rng.random((h, w, 3), dtype=np.float32)
+    img = 0.75 * base + 0.25 * tex
+    return np.clip(img * 255.0 + 0.5, 0, 255).astype(np.uint8)
+
+
+def make_masks(rng: np.random.Generator, n: int, h: int, w: int,
+               min_area: int = 800, max_frac: float = 0.6) -> np.ndarray:
+    """SAM-style blobs: rotated ellipses, area log-uniform in [min_area, max_frac*H*W]
+    (SAM is run with min_mask_region_area=800, Hybridgl_main.py:74)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    out = np.zeros((n, h, w), dtype=bool)
+    min_area = max(4, min(min_area, h * w // 8))
+    lo, hi = np.log(float(min_area)), np.log(max_frac * h * w)
+    for i in range(n):
+        for _ in range(16):
+            area = float(np.exp(rng.uniform(lo, hi)))
+            ratio = float(np.exp(rng.uniform(-0.9, 0.9)))
+            ra = np.sqrt(area / np.pi * ratio); rb = np.sqrt(area / np.pi / ratio)
+            cy = rng.uniform(0.1 * h, 0.9 * h); cx = rng.uniform(0.1 * w, 0.9 * w)
+            th = rng.uniform(0, np.pi)
+            dx, dy = xx - cx, yy - cy
+            u = dx * np.cos(th) + dy * np.sin(th); v = -dx * np.sin(th) + dy * np.cos(th)
+            m = (u / ra) ** 2 + (v / rb) ** 2 <= 1.0
+            if m.sum() >= min(min_area, h * w // 8) and not m.all():
+                out[i] = m
+                break
+        else:  # degenerate tiny frames in unit tests
+            out[i, h // 4: h // 2 + 1, w // 4: w // 2 + 1] = True
+    return out
+
+
+def masks_to_boxes(masks: np.ndarray) -> np.ndarray:
+    """XYWH boxes exactly as SAM derives them: inclusive XYXY edges, w = x1 - x0, h = y1 - y0
+    (segment_anything/utils/amg.py batched_mask_to_box + box_xyxy_to_xywh)."""
+    n = masks.shape[0]
+    boxes = np.zeros((n, 4), dtype=np.int64)
+    for i in range(n):
+        ys, xs = np.nonzero(masks[i])
+        if ys.size == 0:
+            continue
+        x0, x1, y0, y1 = xs.min(), xs.max(), ys.min(), ys.max()
+        boxes[i] = (x0, y0, x1 - x0, y1 - y0)
+    return boxes
+
+
+def make_target(rng: np.random.Generator, masks: np.ndarray) -> np.ndarray:
+    """Ground truth = one proposal shifted by a few pixels so that IoU is neither 0 nor 1."""
+    k = int(rng.integers(0, masks.shape[0]))
+    dy, dx = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    t = np.roll(np.roll(masks[k], dy, axis=0), dx, axis=1)
+    return t.astype(np.uint8)
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even f32 -> bf16 -> f32 (the build's 'bf16 inputs' contract)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+
+
+def make_expression(rng: np.random.Generator, h: int, w: int, de: int,
+                    n_other: Optional[int] = None, dirflag: Optional[str] = None,
+                    relaflag: Optional[str] = None, hm_grid=(28, 37), bf16: bool = True,
+                    anchor: Optional[np.ndarray] = None) -> Expression:
+    if n_other is None:
+        n_other = int(rng.integers(0, 4))
+    if dirflag is None:
+        dirflag = DIRFLAGS[int(rng.integers(0, len(DIRFLAGS)))]
+    if relaflag is None:
+        relaflag = RELAFLAGS[int(rng.integers(0, len(RELAFLAGS)))]
+    sent = rng.standard_normal(de).astype(np.float32)
+    noun = (0.6 * sent + 0.8 * rng.standard_normal(de)).astype(np.float32)
+    if anchor is not None:  # make the expression "refer to" one proposal so that scores are peaked
+        sent = sent + 1.5 * anchor; noun = noun + 1.5 * anchor
+    other = rng.standard_normal((n_other, de)).astype(np.float32)
+    coarse = rng.random((hm_grid[0], hm_grid[1]), dtype=np.float32)
+    ys = np.clip((np.arange(h) + 0.5) * hm_grid[0] / h - 0.5, 0, hm_grid[0] - 1)
+    xs = np.clip((np.arange(w) + 0.5) * hm_grid[1] / w - 0.5, 0, hm_grid[1] - 1)
+    y0 = np.floor(ys).astype(np.int64); x0 = np.floor(xs).astype(np.int64)
+    y1 = np.minimum(y0 + 1, hm_grid[0] - 1); x1 = np.minimum(x0 + 1, hm_grid[1] - 1)
+    fy = (ys - y0).astype(np.float32)[:, None]; fx = (xs - x0).astype(np.float32)[None, :]
+    hm = (coarse[y0][:, x0] * (1 - fy) * (1 - fx) + coarse[y0][:, x1] * (1 - fy) * fx
+          + coarse[y1][:, x0] * fy * (1 - fx) + coarse[y1][:, x1] * fy * fx).astype(np.float32)
+    if bf16:
+        sent, noun, other = bf16_round(sent), bf16_round(noun), bf16_round(other)
+    return Expression(sent, noun, other.reshape(n_other, de), dirflag, relaflag, hm)
+
+
+def make_item(seed: int, h: int = 480, w: int = 640, n_masks: int = 64, n_expr: int = 1,
+              de: int = 512, with_features: bool = True, bf16: bool = True,
+              n_other: Optional[int] = None, dirflag: Optional[str] = None,
+              relaflag: Optional[str] = None) -> Item:
+    rng = np.random.default_rng(seed)
+    image = make_image(rng, h, w)
+    masks = make_masks(rng, n_masks, h, w)
+    boxes = masks_to_boxes(masks)
+    target = make_target(rng, masks)
+    feats = None
+    if with_features:
+        feats = rng.standard_normal((n_masks, de)).astype(np.float32)
+        if bf16:
+            feats = bf16_round(feats)
+    exprs = []
+    for _ in range(n_expr):
+        anchor = None
+        if feats is not None:
+            anchor = feats[int(rng.integers(0, n_masks))] * 0.25
+        exprs.append(make_expression(rng, h, w, de, n_other=n_other, dirflag=dirflag,
+                                     relaflag=relaflag, bf16=bf16, anchor=anchor))
+    return Item(image, masks, boxes, target, exprs, feats)
+
+
+# BASELINE.json configs -> concrete shapes
+CONFIGS = {
+    1: dict(h=480, w=640, n_masks=64, n_expr=1, S=224, g=14, Dv=768, De=512, heads=12, layers=12, fusion_mode="G2L"),
+    2: dict(h=480, w=640, n_masks=100, n_expr=3, S=224, g=14, Dv=768, De=512, heads=12, layers=12, fusion_mode="G2L&L2G"),
+    3: dict(h=480, w=640, n_masks=150, n_expr=2, S=224, g=14, Dv=768, De=512, heads=12, layers=12, fusion_mode="L2G", n_other=3),
+    4: dict(h=480, w=640, n_masks=200, n_expr=3, S=336, g=24, Dv=1024, De=768, heads=16, layers=24, fusion_mode="G2L&L2G"),
+    5: dict(h=600, w=800, n_masks=200, n_expr=5, S=224, g=14, Dv=768, De=512, heads=12, layers=12, fusion_mode="G2L"),
+}

@@ -1,0 +1,112 @@
+"""Pin the numpy oracle against outputs of the reference itself (tests/golden/*.npz, produced by
+tests/golden/gen_golden.py from /root/reference).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import unpack_masks
+from hybridgl_b200 import synth
+from oracle import hybridgl_oracle as O
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_prep_matches_reference(golden, tag):
+    g = golden("prep")
+    seed, h, w, S, n = g[f"{tag}_meta"].tolist()
+    it = synth.make_item(seed, h, w, n, 0, with_features=False)
+    blur = O.gaussian_blur_u8(it.image)
+    if f"{tag}_image" in g:
+        assert np.array_equal(g[f"{tag}_image"], it.image)
+        assert np.array_equal(unpack_masks(g[f"{tag}_masks"], w), it.masks)
+        assert np.array_equal(g[f"{tag}_blur"], blur)          # cv2.GaussianBlur restated bit-exactly
+        loc, glo = O.prep(it.image, blur, it.masks, S)
+        if tag == "b":   # odd tiny frame: ATen takes a differently-contracted scalar path here (<= 3 ulp off)
+            np.testing.assert_allclose(loc, g[f"{tag}_local"], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(glo, g[f"{tag}_global"], rtol=0, atol=1e-6)
+        else:
+            assert np.array_equal(loc, g[f"{tag}_local"])       # bit-exact (FMA order restated)
+            assert np.array_equal(glo, g[f"{tag}_global"])
+    else:
+        assert g[f"{tag}_image_sum"].tolist() == [int(it.image.astype(np.int64).sum()), int(it.masks.sum())]
+        assert np.array_equal(g[f"{tag}_blur"], blur[::8, ::8])
+        loc, glo = O.prep(it.image, blur, it.masks, S)
+        assert np.array_equal(loc[:, :, ::7, ::5], g[f"{tag}_local"])
+        assert np.array_equal(glo[:, :, ::7, ::5], g[f"{tag}_global"])
+        np.testing.assert_allclose([loc.astype(np.float64).sum(), glo.astype(np.float64).sum()], g[f"{tag}_sums"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f"])
+def test_grid_matches_reference(golden, tag):
+    g = golden("grid")
+    seed, h, w, gs, n = g[f"{tag}_meta"].tolist()
+    masks = unpack_masks(g[f"{tag}_masks"], w)
+    aa = O.mask_to_grid(masks, gs, antialias=True)
+    na = O.mask_to_grid(masks, gs, antialias=False)
+    # small outputs take a differently-contracted ATen loop (<= 2 ulp); taps and zero pattern are exact
+    np.testing.assert_allclose(na, g[f"{tag}_noaa"], rtol=0, atol=2.4e-7)
+    assert np.array_equal(na != 0, g[f"{tag}_noaa"] != 0)
+    np.testing.assert_allclose(aa, g[f"{tag}_aa"], rtol=0, atol=1.2e-7)   # <= 1 ulp: ATen vectorises the tap sum
+    assert np.array_equal(aa != 0, g[f"{tag}_aa"] != 0)                   # the zero pattern drives the attention mask
+    if f"{tag}_attn_row0" in g:
+        am = O.make_attn_mask(g[f"{tag}_aa"], heads=3)
+        assert np.array_equal(am[:, 0, :], g[f"{tag}_attn_row0"])
+        assert not am[:, 1:, :].any()
+
+
+def test_dir_mask_and_relation(golden):
+    g = golden("misc")
+    for key in g.files:
+        if key.startswith("dir_"):
+            _, d, hw = key.split("_")
+            h, w = map(int, hw.split("x"))
+            assert np.array_equal(O.gen_dir_mask(d, h, w), g[key]), key
+    for bi, bj, si, sj, word, ref in zip(g["rel_bi"], g["rel_bj"], g["rel_si"], g["rel_sj"], g["rel_word"], g["rel_out"]):
+        got = O.relation_boxes(bi, bj, si, sj, str(word))
+        np.testing.assert_allclose(got, ref, rtol=2e-7, atol=0)
+
+
+def _case(g, ci):
+    p = f"c{ci:02d}_"
+    seed, h, w, n, n_other = g[p + "meta"].tolist()
+    d = {k[len(p):]: g[k] for k in g.files if k.startswith(p)}
+    d.update(h=h, w=w, n=n, n_other=n_other, rela=str(d["flags"][0]), dirf=str(d["flags"][1]))
+    d["masks"] = unpack_masks(d["masks"], w); d["target"] = unpack_masks(d["target"], w)
+    return d
+
+
+def test_scoring_matches_reference(golden):
+    g = golden("scoring")
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        it = synth.make_item(int(c["meta"][0]), c["h"], c["w"], c["n"], 1, de=512, n_other=c["n_other"],
+                             dirflag=c["dirf"], relaflag=c["rela"])
+        heat = c["heat_resized"] if "heat_resized" in c else O.resize_bilinear_aa(c["heat_raw"], c["h"], c["w"])[0]
+        cond = O.condition_heatmap(heat, c["dirf"])
+        sg = O.gem_pool(cond, c["masks"], O.black_for(c["rela"]))
+        np.testing.assert_allclose(sg, c["score_gem"], rtol=2e-4, atol=2e-5)
+        r = O.score_and_select(c["features"], c["sentence"], c["noun"], c["others"], c["boxes"], c["rela"],
+                               score_gem=sg, logit_scale_exp=float(c["logit_scale_exp"]))
+        np.testing.assert_allclose(r["score_clip"], c["score_clip"], rtol=1e-4, atol=1e-4)
+        if c["n_other"]:
+            np.testing.assert_allclose(r["score_neg"], c["score_neg"], rtol=1e-4, atol=1e-4)
+        else:
+            assert np.isnan(c["score_neg"]).all() and np.isnan(r["score_neg"]).all()   # Appendix B-5
+        assert r["idx_hybrid"] == int(c["idx_hybrid"]), ci
+        assert np.array_equal(r["top_idx"], c["top_idx"]), ci
+        np.testing.assert_allclose(r["blended"], c["blended"], rtol=2e-4, atol=2e-5)
+        assert r["idx_final"] == int(c["idx_final"]), ci
+        i0, u0, iou0 = O.compute_iou(c["masks"][r["idx_hybrid"]], c["target"])
+        i1, u1, iou1 = O.compute_iou(c["masks"][r["idx_final"]], c["target"])
+        assert [i0, u0, i1, u1] == c["IU"].tolist()
+        np.testing.assert_allclose([iou0, iou1], c["iou"], rtol=1e-6)
+
+
+def test_heatmap_resize_aa_matches_reference(golden):
+    g = golden("scoring")
+    seen = 0
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        if "heat_resized" in c:
+            got = O.resize_bilinear_aa(c["heat_raw"], c["h"], c["w"])[0]
+            np.testing.assert_allclose(got, c["heat_resized"], rtol=0, atol=2e-7)
+            seen += 1
+    assert seen >= 10
