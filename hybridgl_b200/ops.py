@@ -1,0 +1,258 @@
+"""Thin tensor-level wrappers over the C ABI (include/hgl.h).
+
+Every function takes CUDA tensors, checks dtype / contiguity / device, passes raw pointers and the
+current CUDA stream to libhgl.so, and returns freshly allocated (or caller-supplied) CUDA tensors.
+PyTorch is used for device memory and streams only -- no arithmetic of the path happens in torch.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DIR_CODES, HGL_BF16, HGL_BG_BLACK, HGL_BG_BLUR, HGL_F32, REL_CODES, check  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t
+
+
+def _mask_bytes(masks: torch.Tensor, name: str = "masks") -> torch.Tensor:
+    _req(masks, (torch.bool, torch.uint8), name, 3)
+    return masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+
+
+def _dt(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return HGL_F32
+    if dtype == torch.bfloat16:
+        return HGL_BF16
+    raise TypeError(f"unsupported dtype {dtype} (float32 or bfloat16)")
+
+
+def _offsets(off: Optional[torch.Tensor], B: int, name: str) -> Optional[torch.Tensor]:
+    if off is None:
+        if B != 1:
+            raise ValueError(f"{name} is required when the batch holds more than one image")
+        return None
+    _req(off, torch.int32, name, 1)
+    if off.numel() != B + 1:
+        raise ValueError(f"{name}: expected {B + 1} entries, got {off.numel()}")
+    return off
+
+
+def device_ok() -> None:
+    check(_lib.load().hgl_check_device(), "hgl_check_device")
+
+
+# ---- (a1) ---------------------------------------------------------------------------------------------
+def gaussian_blur15(image: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cv2.GaussianBlur(img,(15,15),0) (Hybridgl_main.py:99).  image u8 [B,H,W,3] or [H,W,3]."""
+    squeeze = image.dim() == 3
+    img = image[None] if squeeze else image
+    _req(img, torch.uint8, "image", 4)
+    B, H, W, C = img.shape
+    if C != 3:
+        raise ValueError("image must be HWC with 3 channels")
+    if out is None:
+        out = torch.empty_like(img)
+    check(_lib.load().hgl_gaussian_blur15(img.data_ptr(), out.data_ptr(), B, H, W, _stream()), "hgl_gaussian_blur15")
+    return out[0] if squeeze else out
+
+
+def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks: torch.Tensor, size: int,
+                        mask_off: Optional[torch.Tensor] = None, background: str = "blur",
+                        dtype: torch.dtype = torch.float32,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S]."""
+    img = image[None] if image.dim() == 3 else image
+    _req(img, torch.uint8, "image", 4)
+    B, H, W, _ = img.shape
+    m = _mask_bytes(masks)
+    M = m.shape[0]
+    if tuple(m.shape[1:]) != (H, W):
+        raise ValueError(f"masks {tuple(m.shape)} do not match the frame {H}x{W}")
+    bg = {"blur": HGL_BG_BLUR, "black": HGL_BG_BLACK}[background]
+    bl = None
+    if bg == HGL_BG_BLUR:
+        if blur is None:
+            blur = gaussian_blur15(img)
+        bl = blur[None] if blur.dim() == 3 else blur
+        _req(bl, torch.uint8, "blur", 4)
+        if bl.shape != img.shape:
+            raise ValueError("blur must have the shape of image")
+    off = _offsets(mask_off, B, "mask_off")
+    if out is None:
+        local = torch.empty((M, 3, size, size), dtype=dtype, device=img.device)
+        glob = torch.empty_like(local)
+    else:
+        local, glob = out
+    check(_lib.load().hgl_prep(img.data_ptr(), _ptr(bl), m.data_ptr(), _ptr(off), B, M, H, W, size, bg, _dt(dtype),
+                               local.data_ptr(), glob.data_ptr(), _stream()), "hgl_prep")
+    return local, glob
+
+
+# ---- (a2)-(a4) ----------------------------------------------------------------------------------------
+def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area: bool = False):
+    """TF.resize(pred_masks.float(), (g, g)) model/backbone.py:160 -> f32 [M,g,g] (and int32 areas [M])."""
+    m = _mask_bytes(masks)
+    M, H, W = m.shape
+    grid = torch.empty((M, g, g), dtype=torch.float32, device=m.device)
+    area = torch.empty((M,), dtype=torch.int32, device=m.device) if want_area else None
+    check(_lib.load().hgl_mask_grid(m.data_ptr(), M, H, W, g, int(bool(antialias)), grid.data_ptr(), _ptr(area), _stream()),
+          "hgl_mask_grid")
+    return (grid, area) if want_area else grid
+
+
+def make_attn_mask(grid: torch.Tensor, heads: int) -> torch.Tensor:
+    """CLIPViTFM.make_attn_mask model/backbone.py:108-115 -> bool [M*heads, L+1, L+1] (True = blocked)."""
+    _req(grid, torch.float32, "grid")
+    M = grid.shape[0]
+    L = grid[0].numel()
+    out = torch.empty((M * heads, L + 1, L + 1), dtype=torch.uint8, device=grid.device)
+    check(_lib.load().hgl_attn_mask(grid.data_ptr(), M, L, heads, out.data_ptr(), _stream()), "hgl_attn_mask")
+    return out.view(torch.bool)
+
+
+def attn_key_bias(grid: torch.Tensor) -> torch.Tensor:
+    """Compact form of the same mask: additive bias [M, L+1] for the CLS query row (0 or -inf)."""
+    _req(grid, torch.float32, "grid")
+    M = grid.shape[0]
+    L = grid[0].numel()
+    out = torch.empty((M, L + 1), dtype=torch.float32, device=grid.device)
+    check(_lib.load().hgl_attn_bias(grid.data_ptr(), M, L, out.data_ptr(), _stream()), "hgl_attn_bias")
+    return out
+
+
+def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Optional[torch.Tensor], a: float = 1.0,
+                    b: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a * tokenmask(src, grid) + b * add on LND streams [L+1, M, D] (model/backbone.py:235-249, 216, 290-291)."""
+    _req(src, (torch.float32, torch.bfloat16), "src", 3)
+    L1, M, D = src.shape
+    if add is not None:
+        _req(add, src.dtype, "add", 3)
+        if add.shape != src.shape:
+            raise ValueError("add must have the shape of src")
+    if grid is not None:
+        _req(grid, torch.float32, "grid")
+        if grid.shape[0] != M or grid[0].numel() != L1 - 1:
+            raise ValueError(f"grid {tuple(grid.shape)} does not match streams {tuple(src.shape)}")
+    if out is None:
+        out = torch.empty_like(src)
+    check(_lib.load().hgl_token_mask_fuse(src.data_ptr(), _ptr(add), _ptr(grid), float(a), float(b), L1, M, D, _dt(src.dtype),
+                                          out.data_ptr(), _stream()), "hgl_token_mask_fuse")
+    return out
+
+
+# ---- (a10)+(a11) --------------------------------------------------------------------------------------
+def heat_pool(heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor, masks: torch.Tensor,
+              mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
+              workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Hybridgl_main.py:204-223: conditioned GEM heat-map pooled inside / outside every mask -> score_gem f32 [E,max_n]."""
+    _req(heat, torch.float32, "heat", 3)
+    E, H, W = heat.shape
+    m = _mask_bytes(masks)
+    M = m.shape[0]
+    if tuple(m.shape[1:]) != (H, W):
+        raise ValueError("masks and heat-map frames differ")
+    _req(dirflag, torch.int32, "dirflag", 1)
+    _req(black, torch.float32, "black", 1)
+    B = 1 if mask_off is None else mask_off.numel() - 1
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    lib = _lib.load()
+    need = lib.hgl_heat_pool_workspace_bytes(B, M, E, H, W, max_n)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=heat.device)
+    out = torch.empty((E, max_n), dtype=torch.float32, device=heat.device)
+    check(lib.hgl_heat_pool(heat.data_ptr(), _ptr(eoff), dirflag.data_ptr(), black.data_ptr(), m.data_ptr(), _ptr(moff),
+                            B, M, E, H, W, max_n, out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_heat_pool")
+    return out
+
+
+# ---- (a6)-(a9),(a12) ----------------------------------------------------------------------------------
+def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, others: torch.Tensor, other_off: torch.Tensor,
+                 boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],
+                 mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None,
+                 max_n: Optional[int] = None, logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6):
+    """Hybridgl_main.py:153-196,225-227 for a batch.  Returns dict(score_clip[E,max_n], idx_hybrid[E], idx_final[E],
+    top_idx[E,3], blended[E,3])."""
+    _req(feat, (torch.float32, torch.bfloat16), "feat", 2)
+    M, De = feat.shape
+    _req(sent, torch.float32, "sent", 2)
+    _req(noun, torch.float32, "noun", 2)
+    E = sent.shape[0]
+    _req(others, torch.float32, "others", 2)
+    _req(other_off, torch.int32, "other_off", 1)
+    _req(boxes, torch.int64, "boxes", 2)
+    _req(relaflag, torch.int32, "relaflag", 1)
+    if sent.shape != (E, De) or noun.shape != (E, De) or other_off.numel() != E + 1 or boxes.shape != (M, 4):
+        raise ValueError("score_select: inconsistent shapes")
+    B = 1 if mask_off is None else mask_off.numel() - 1
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    if score_gem is not None:
+        _req(score_gem, torch.float32, "score_gem", 2)
+        if score_gem.shape != (E, max_n):
+            raise ValueError("score_gem must be [E, max_n]")
+    dev = feat.device
+    score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
+    idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
+    idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
+    top = torch.empty((E, 3), dtype=torch.int32, device=dev)
+    blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    check(_lib.load().hgl_score_select(feat.data_ptr(), _dt(feat.dtype), sent.data_ptr(), noun.data_ptr(), others.data_ptr(),
+                                       other_off.data_ptr(), boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
+                                       _ptr(moff), _ptr(eoff), B, M, E, De, max_n, float(logit_scale_exp), float(r), float(alpha),
+                                       score_clip.data_ptr(), idx_h.data_ptr(), idx_f.data_ptr(), top.data_ptr(),
+                                       blended.data_ptr(), _stream()), "hgl_score_select")
+    return dict(score_clip=score_clip, idx_hybrid=idx_h, idx_final=idx_f, top_idx=top, blended=blended)
+
+
+# ---- (a13) --------------------------------------------------------------------------------------------
+def iou_accumulate(masks: torch.Tensor, target: torch.Tensor, idx_hybrid: torch.Tensor, idx_final: torch.Tensor,
+                   cum: Optional[torch.Tensor], mask_off: Optional[torch.Tensor] = None,
+                   expr_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Compute_IoU utils.py:365-384 for both picks of every expression.  Returns iu int64 [E,4] =
+    (I_hybrid, U_hybrid, I_final, U_final) and adds the column sums into cum int64 [4]."""
+    m = _mask_bytes(masks)
+    M, H, W = m.shape
+    t = target[None] if target.dim() == 2 else target
+    t = _mask_bytes(t, "target")
+    B = t.shape[0]
+    _req(idx_hybrid, torch.int64, "idx_hybrid", 1)
+    _req(idx_final, torch.int64, "idx_final", 1)
+    E = idx_hybrid.numel()
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if cum is not None:
+        _req(cum, torch.int64, "cum", 1)
+    iu = torch.empty((E, 4), dtype=torch.int64, device=m.device)
+    check(_lib.load().hgl_iou(m.data_ptr(), t.data_ptr(), idx_hybrid.data_ptr(), idx_final.data_ptr(), _ptr(moff), _ptr(eoff),
+                              B, M, E, H, W, iu.data_ptr(), _ptr(cum), _stream()), "hgl_iou")
+    return iu

@@ -1,0 +1,137 @@
+/*
+ * libhgl -- C ABI of the B200-native HybridGL mask-proposal scoring path.
+ *
+ * The reference (fhgyuanshen/HybridGL) has no FFI / plugin interface: the path is reached through plain
+ * Python calls.  Each entry point below therefore cites the reference *code block*
+ * it replaces (file:line relative to the reference checkout); hybridgl_b200/ops.py binds them with ctypes
+ * and hybridgl_b200/{backbone,utils,pipeline}.py re-expose the reference's own call surface on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns and sizes all buffers
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued asynchronously on it
+ *   - no allocation, no synchronisation, no host<->device copy inside the library (re-entrant per stream)
+ *   - return value: 0 on success, a negative HGL_E* code otherwise; hgl_last_error() gives the text
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - dtype codes: HGL_F32 / HGL_BF16 for floating tensors; masks are 1 byte per pixel (torch.bool)
+ *   - ragged batches: masks of image b are rows mask_off[b] .. mask_off[b+1]-1 of the [M,...] tensors,
+ *     expressions of image b are rows expr_off[b] .. expr_off[b+1]-1 of the [E,...] tensors
+ */
+#ifndef HGL_H_
+#define HGL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HGL_API __attribute__((visibility("default")))
+#else
+#define HGL_API
+#endif
+
+#define HGL_OK 0
+#define HGL_EINVAL (-1)   /* bad argument (shape, dtype, null pointer, unsupported size) */
+#define HGL_ECUDA (-2)    /* CUDA runtime error at launch */
+#define HGL_EARCH (-3)    /* device is not sm_100 */
+
+#define HGL_F32 0
+#define HGL_BF16 1
+
+/* background of the global view outside the mask (utils.py:292-345 apply_visual_prompts option set) */
+#define HGL_BG_BLUR 0     /* Gaussian-blurred frame  (Hybridgl_main.py:99-113; utils.py:306-320) */
+#define HGL_BG_BLACK 1    /* zeros                   (utils.py:336-341) */
+
+/* relation words of utils.py:240-268 (extract_rela_word, utils.py:207-237) */
+enum { HGL_REL_NONE = 0, HGL_REL_LEFT, HGL_REL_RIGHT, HGL_REL_UP, HGL_REL_DOWN, HGL_REL_BIG, HGL_REL_SMALL, HGL_REL_WITHIN };
+/* direction words of utils.py:102-161 (extract_dir_phrase / gen_dir_mask) */
+enum { HGL_DIR_NONE = 0, HGL_DIR_LEFT, HGL_DIR_RIGHT, HGL_DIR_MIDDLE, HGL_DIR_UP, HGL_DIR_DOWN };
+
+HGL_API const char* hgl_last_error(void);
+HGL_API int hgl_version(void);
+/* 0 if the current device is sm_100 and the kernels are loadable, HGL_EARCH otherwise */
+HGL_API int hgl_check_device(void);
+
+/* ---- (a1) per-mask visual-prompt preprocessing ------------------------------------------------------
+ * Replaces the Python loop Hybridgl_main.py:92-125 (dups demo.py:79-112) and utils.py:292-345:
+ *   global[n] = Normalize_IN(bilinear_S( where(mask_n, image, background) / 255 ))
+ *   local[n]  = bilinear_S( where(mask_n, Normalize_IN(image/255), clip_pixel_mean) )
+ * image/blur u8 [B,H,W,3]; masks u8 [M,H,W]; mask_off int32 [B+1] (NULL => B==1, all M masks belong to image 0);
+ * local_out/global_out [M,3,S,S] of out_dtype.  blur may be NULL for HGL_BG_BLACK. */
+HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint8_t* masks, const int32_t* mask_off,
+             int B, int M, int H, int W, int S, int bg_mode, int out_dtype,
+             void* local_out, void* global_out, void* stream);
+
+/* cv2.GaussianBlur(img,(15,15),0) on uint8, BORDER_REFLECT_101, OpenCV's Q8 fixed-point taps
+ * (Hybridgl_main.py:99).  image/out u8 [B,H,W,3]. */
+HGL_API int hgl_gaussian_blur15(const uint8_t* image, uint8_t* out, int B, int H, int W, void* stream);
+
+/* ---- (a2) mask -> patch grid ------------------------------------------------------------------------
+ * Replaces TF.resize(pred_masks.float(), (g,g)) model/backbone.py:160.  antialias=1 is torchvision>=0.17
+ * behaviour (this container), antialias=0 the reference's pinned torchvision 0.15.2.
+ * masks u8 [M,H,W] -> grid f32 [M,g,g]; area int32 [M] (pixel count of every mask; may be NULL). */
+HGL_API int hgl_mask_grid(const uint8_t* masks, int M, int H, int W, int g, int antialias,
+                  float* grid, int32_t* area, void* stream);
+
+/* ---- (a3) CLS-row attention mask --------------------------------------------------------------------
+ * Replaces CLIPViTFM.make_attn_mask model/backbone.py:108-115.
+ * grid f32 [M,L] -> out u8 [M*heads, L+1, L+1], 1 = blocked: only (q=0, k>=1, grid[m,k-1]==0). */
+HGL_API int hgl_attn_mask(const float* grid, int M, int L, int heads, uint8_t* out, void* stream);
+/* Compact equivalent used by the B200 forward: additive key bias for the CLS query only,
+ * bias f32 [M, L+1] = 0 or -inf (col 0 always 0). */
+HGL_API int hgl_attn_bias(const float* grid, int M, int L, float* bias, void* stream);
+
+/* ---- (a4) token masking + stream mix ----------------------------------------------------------------
+ * Replaces the permute/view/mul/cat chains model/backbone.py:235-249, 214-216, 275-291:
+ *   out[l,m,:] = a * w(l,m) * src[l,m,:] + b * add[l,m,:],  w = 1 for l==0 (CLS) else grid[m,l-1]
+ * grid NULL => w == 1 (plain a*src + b*add);  add NULL => b term dropped.
+ * src/add/out [L+1, M, D] (LND) of dtype; grid f32 [M,L]. out may alias src or add. */
+HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* grid, float a, float b,
+                        int L1, int M, int D, int dtype, void* out, void* stream);
+
+/* ---- (a10)+(a11) heat-map conditioning and mask pooling ---------------------------------------------
+ * Replaces Hybridgl_main.py:204-223 and gen_dir_mask utils.py:135-161:
+ *   A' = minmax(A) * ramp(dirflag);  A'' = A' / mean(A');
+ *   score_gem[e,n] = (2-black_e) * sum(A''*m_n)/area(m_n) - black_e * sum(A''*(1-m_n))/area(1-m_n)
+ * heat f32 [E,H,W] (GEM map after T.Resize, Hybridgl_main.py:201); expr_off int32 [B+1] (NULL => B==1);
+ * dirflag int32 [E]; black f32 [E]; masks u8 [M,H,W]; mask_off int32 [B+1] (NULL => B==1).
+ * score_gem f32 [E, max_n] row e holds the n masks of its image (max_n = row stride).
+ * workspace: hgl_heat_pool_workspace_bytes(...) bytes, zeroing not required. */
+HGL_API int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n);
+HGL_API int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
+                  const uint8_t* masks, const int32_t* mask_off, int B, int M, int E, int H, int W,
+                  int max_n, float* score_gem, void* workspace, void* stream);
+
+/* ---- (a6)-(a9),(a12) scoring, spatial-relationship re-ranking, per-expression argmax ----------------
+ * Replaces Hybridgl_main.py:153-196 and :225-227 plus CLIPViTFM.calculate_score model/backbone.py:74-87 and
+ * relation_boxes utils.py:240-268, one launch for a whole batch of images:
+ *   text = r*sent + (1-r)*noun;  s = scale * cos(feat, text);  sneg = scale * cos(feat, mean(others))
+ *   idx_hybrid = argmax s;  p = softmax(s), q = softmax(sneg);  top = topk(p, min(3,n)), topneg = topk(q, min(6,n))
+ *   T_i = sum_j rel(box[top_i], box[J_j], p[top_i], Q[J_j])   (J,Q) = (top,p) if no other nouns else (topneg,q)
+ *   T = softmax(T);  T_i = (1-alpha)*T_i + alpha*score_gem[top_i];  idx_final = top[argmax T]
+ * feat [M,De] feat_dtype; sent/noun f32 [E,De]; others f32 [K,De] with other_off int32 [E+1];
+ * boxes int64 [M,4] XYWH; relaflag int32 [E]; score_gem f32 [E,max_n] or NULL (=> alpha term skipped);
+ * outputs: score_clip f32 [E,max_n] (pre-softmax), idx_hybrid/idx_final int64 [E] (index local to the image),
+ * top_idx int32 [E,3] (-1 padded), blended f32 [E,3]. */
+HGL_API int hgl_score_select(const void* feat, int feat_dtype, const float* sent, const float* noun, const float* others,
+                     const int32_t* other_off, const int64_t* boxes, const int32_t* relaflag, const float* score_gem,
+                     const int32_t* mask_off, const int32_t* expr_off, int B, int M, int E, int De, int max_n,
+                     double logit_scale_exp, double r, double alpha,
+                     float* score_clip, int64_t* idx_hybrid, int64_t* idx_final, int32_t* top_idx, float* blended,
+                     void* stream);
+
+/* ---- (a13) IoU accounting ---------------------------------------------------------------------------
+ * Replaces Compute_IoU utils.py:365-384 (called at Hybridgl_main.py:171,230):
+ *   for every expression e and each of the two picks: I = |pred & gt|, U = |pred | gt|
+ * masks u8 [M,H,W]; target u8 [B,H,W]; idx_hybrid/idx_final int64 [E] (image-local);
+ * iu int64 [E,4] = {I_hybrid,U_hybrid,I_final,U_final} (overwritten);
+ * cum int64 [4] += sums (caller zeroes at sweep start; these are the accumulators NCCL all-reduces). */
+HGL_API int hgl_iou(const uint8_t* masks, const uint8_t* target, const int64_t* idx_hybrid, const int64_t* idx_final,
+            const int32_t* mask_off, const int32_t* expr_off, int B, int M, int E, int H, int W,
+            int64_t* iu, int64_t* cum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGL_H_ */

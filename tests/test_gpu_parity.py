@@ -1,0 +1,288 @@
+"""GPU parity: the CUDA path (through the C ABI, hybridgl_b200/ops.py) against the numpy oracle and against the
+golden vectors produced by the reference itself.  Integer / byte / index results must be bit-exact; floating
+point tolerances are written next to each check (north star: fused scores within 1e-3 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unpack_masks
+from hybridgl_b200 import synth
+from oracle import hybridgl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from hybridgl_b200 import ops as _ops
+    _ops.device_ok()
+    return _ops
+
+
+def cu(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def bf16r(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+# ------------------------------------------------------------------------------------------------ blur
+@pytest.mark.parametrize("h,w,seed", [(480, 640, 0), (97, 131, 1), (33, 20, 2), (600, 800, 3)])
+def test_blur_bit_exact(ops, h, w, seed):
+    rng = np.random.default_rng(seed)
+    img = synth.make_image(rng, h, w) if seed % 2 == 0 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = ops.gaussian_blur15(cu(img)).cpu().numpy()
+    assert np.array_equal(got, O.gaussian_blur_u8(img))
+
+
+def test_blur_matches_reference_cv2(ops, golden):
+    g = golden("prep")
+    for tag in "ab":
+        got = ops.gaussian_blur15(cu(g[f"{tag}_image"])).cpu().numpy()
+        assert np.array_equal(got, g[f"{tag}_blur"])       # cv2.GaussianBlur output recorded from the reference run
+
+
+# ------------------------------------------------------------------------------------------------ prep
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_prep_matches_reference_golden(ops, golden, tag):
+    g = golden("prep")
+    seed, h, w, S, n = g[f"{tag}_meta"].tolist()
+    it = synth.make_item(seed, h, w, n, 0, with_features=False)
+    img = cu(it.image)
+    blur = ops.gaussian_blur15(img)
+    loc, glo = ops.prep_visual_prompts(img, blur, cu(it.masks), S)
+    loc = loc.cpu().numpy(); glo = glo.cpu().numpy()
+    rl, rg = g[f"{tag}_local"], g[f"{tag}_global"]
+    if f"{tag}_image" not in g:
+        loc = loc[:, :, ::7, ::5]; glo = glo[:, :, ::7, ::5]
+    if tag == "b":      # reference's own CPU kernel is contracted differently on this tiny odd frame (see oracle test)
+        np.testing.assert_allclose(loc, rl, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(glo, rg, rtol=0, atol=1e-6)
+    else:               # f32 output is bit-identical to the reference's
+        assert np.array_equal(loc, rl)
+        assert np.array_equal(glo, rg)
+
+
+@pytest.mark.parametrize("h,w,S,n,seed", [(480, 640, 224, 9, 5), (333, 500, 224, 5, 6), (480, 640, 336, 3, 7),
+                                          (224, 224, 224, 2, 8), (60, 90, 64, 7, 9), (427, 641, 224, 4, 10)])
+def test_prep_vs_oracle_f32_and_bf16(ops, h, w, S, n, seed):
+    it = synth.make_item(seed, h, w, n, 0, with_features=False)
+    blur = O.gaussian_blur_u8(it.image)
+    ol, og = O.prep(it.image, blur, it.masks, S)
+    loc, glo = ops.prep_visual_prompts(cu(it.image), cu(blur), cu(it.masks), S)
+    assert np.array_equal(loc.cpu().numpy(), ol)
+    assert np.array_equal(glo.cpu().numpy(), og)
+    lb, gb = ops.prep_visual_prompts(cu(it.image), cu(blur), cu(it.masks), S, dtype=torch.bfloat16)
+    assert np.array_equal(lb.float().cpu().numpy(), bf16r(ol))     # same f32 value, then round-to-nearest-even
+    assert np.array_equal(gb.float().cpu().numpy(), bf16r(og))
+
+
+def test_prep_black_background_and_edge_masks(ops):
+    it = synth.make_item(11, 120, 160, 4, 0, with_features=False)
+    it.masks[0] = False; it.masks[1] = True          # empty and full-frame proposals
+    ol, og = O.prep(it.image, None, it.masks, 64, background="black")
+    loc, glo = ops.prep_visual_prompts(cu(it.image), None, cu(it.masks), 64, background="black")
+    assert np.array_equal(loc.cpu().numpy(), ol)
+    assert np.array_equal(glo.cpu().numpy(), og)
+
+
+def test_prep_ragged_batch(ops):
+    items = [synth.make_item(20 + i, 96, 128, n, 0, with_features=False) for i, n in enumerate([5, 1, 9, 3])]
+    img = np.stack([it.image for it in items])
+    masks = np.concatenate([it.masks for it in items])
+    off = np.cumsum([0] + [it.n_masks for it in items]).astype(np.int32)
+    blur = ops.gaussian_blur15(cu(img))
+    loc, glo = ops.prep_visual_prompts(cu(img), blur, cu(masks), 32, mask_off=cu(off))
+    loc = loc.cpu().numpy(); glo = glo.cpu().numpy()
+    for i, it in enumerate(items):
+        ol, og = O.prep(it.image, O.gaussian_blur_u8(it.image), it.masks, 32)
+        assert np.array_equal(loc[off[i]:off[i + 1]], ol)
+        assert np.array_equal(glo[off[i]:off[i + 1]], og)
+
+
+def test_prep_empty_and_errors(ops):
+    from hybridgl_b200._lib import HglError
+    img = torch.zeros((16, 16, 3), dtype=torch.uint8, device=DEV)
+    loc, glo = ops.prep_visual_prompts(img, img, torch.zeros((0, 16, 16), dtype=torch.bool, device=DEV), 8)
+    assert loc.shape == (0, 3, 8, 8)
+    with pytest.raises(HglError):
+        ops.prep_visual_prompts(img, img, torch.zeros((1, 16, 16), dtype=torch.bool, device=DEV), 10)   # S % 4 != 0
+
+
+# ------------------------------------------------------------------------------------------------ grid / attn / fuse
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f"])
+def test_grid_matches_reference_golden(ops, golden, tag):
+    g = golden("grid")
+    seed, h, w, gs, n = g[f"{tag}_meta"].tolist()
+    masks = unpack_masks(g[f"{tag}_masks"], w)
+    aa, area = ops.masks_to_grid(cu(masks), gs, antialias=True, want_area=True)
+    aa = aa.cpu().numpy()
+    np.testing.assert_allclose(aa, g[f"{tag}_aa"], rtol=0, atol=1e-6)     # fp32 separable sum, vertical pass first
+    assert np.array_equal(aa != 0, g[f"{tag}_aa"] != 0)                   # zero pattern (drives the CLS attention mask)
+    assert np.array_equal(area.cpu().numpy(), masks.reshape(n, -1).sum(1))
+    na, area2 = ops.masks_to_grid(cu(masks), gs, antialias=False, want_area=True)
+    np.testing.assert_allclose(na.cpu().numpy(), g[f"{tag}_noaa"], rtol=0, atol=2.4e-7)
+    assert np.array_equal(na.cpu().numpy(), O.mask_to_grid(masks, gs, antialias=False))
+    assert np.array_equal(area2.cpu().numpy(), masks.reshape(n, -1).sum(1))
+    if f"{tag}_attn_row0" in g:
+        am = ops.make_attn_mask(cu(g[f"{tag}_aa"]), heads=3).cpu().numpy()
+        assert np.array_equal(am[:, 0, :], g[f"{tag}_attn_row0"])
+        assert not am[:, 1:, :].any()
+        bias = ops.attn_key_bias(cu(g[f"{tag}_aa"])).cpu().numpy()
+        assert np.array_equal(np.isneginf(bias), g[f"{tag}_attn_row0"][::3])
+        assert np.all((bias == 0) | np.isneginf(bias))
+
+
+@pytest.mark.parametrize("h,w,g,n,seed", [(480, 640, 14, 32, 30), (480, 640, 24, 8, 31), (600, 800, 14, 6, 32), (1080, 1920, 24, 2, 33)])
+def test_grid_vs_oracle(ops, h, w, g, n, seed):
+    masks = synth.make_masks(np.random.default_rng(seed), n, h, w)
+    ref = O.mask_to_grid(masks, g, antialias=True)
+    got = ops.masks_to_grid(cu(masks), g).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+    assert np.array_equal(got != 0, ref != 0)
+    assert np.array_equal(ops.make_attn_mask(cu(got), 2).cpu().numpy(), O.make_attn_mask(ref, 2))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_token_mask_fuse(ops, dtype):
+    rng = np.random.default_rng(40)
+    L1, M, D = 17, 5, 64
+    x = rng.standard_normal((L1, M, D)).astype(np.float32)
+    y = rng.standard_normal((L1, M, D)).astype(np.float32)
+    grid = rng.random((M, 4, 4)).astype(np.float32); grid[grid < 0.3] = 0
+    if dtype == torch.bfloat16:
+        x, y = bf16r(x), bf16r(y)
+    for (a, b, gr, add) in [(2.0, 1.0, grid, y), (1.0, 2.0, None, y), (1.0, 0.0, grid, None)]:
+        ref = O.fuse_streams(x, gr, a, y if add is not None else np.zeros_like(x), b if add is not None else 0.0)
+        got = ops.token_mask_fuse(cu(x, dtype), None if add is None else cu(y, dtype), None if gr is None else cu(gr), a, b)
+        got = got.float().cpu().numpy()
+        if dtype == torch.float32:
+            assert np.array_equal(got, ref)
+        else:
+            assert np.array_equal(got, bf16r(ref))
+
+
+# ------------------------------------------------------------------------------------------------ heat pool / scoring / IoU
+def _case(g, ci):
+    p = f"c{ci:02d}_"
+    seed, h, w, n, n_other = g[p + "meta"].tolist()
+    d = {k[len(p):]: g[k] for k in g.files if k.startswith(p)}
+    d.update(h=h, w=w, n=n, n_other=n_other, rela=str(d["flags"][0]), dirf=str(d["flags"][1]))
+    d["masks"] = unpack_masks(d["masks"], w); d["target"] = unpack_masks(d["target"], w)
+    d["heat"] = d["heat_resized"] if "heat_resized" in d else O.resize_bilinear_aa(d["heat_raw"], h, w)[0]
+    return d
+
+
+def _run_case(ops, c, feat_dtype=torch.float32):
+    from hybridgl_b200._lib import DIR_CODES, REL_CODES
+    masks = cu(c["masks"])
+    sg = ops.heat_pool(cu(c["heat"][None]), cu(np.array([DIR_CODES[c["dirf"]]], np.int32)),
+                       cu(np.array([O.black_for(c["rela"])], np.float32)), masks)
+    res = ops.score_select(cu(c["features"], feat_dtype), cu(c["sentence"][None]), cu(c["noun"][None]),
+                           cu(c["others"].reshape(-1, 512)) if c["n_other"] else torch.zeros((0, 512), device=DEV),
+                           cu(np.array([0, c["n_other"]], np.int32)), cu(c["boxes"]),
+                           cu(np.array([REL_CODES[c["rela"]]], np.int32)), sg,
+                           logit_scale_exp=float(c["logit_scale_exp"]))
+    cum = torch.zeros(4, dtype=torch.int64, device=DEV)
+    iu = ops.iou_accumulate(masks, cu(c["target"]), res["idx_hybrid"], res["idx_final"], cum)
+    return sg, res, iu, cum
+
+
+def test_scoring_matches_reference_golden(ops, golden):
+    g = golden("scoring")
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        sg, res, iu, cum = _run_case(ops, c)
+        n = c["n"]
+        np.testing.assert_allclose(sg.cpu().numpy()[0, :n], c["score_gem"], rtol=1e-3, atol=1e-4, err_msg=f"case {ci}")
+        np.testing.assert_allclose(res["score_clip"].cpu().numpy()[0, :n], c["score_clip"], rtol=1e-3, atol=1e-4)
+        k1 = min(3, n)
+        np.testing.assert_allclose(res["blended"].cpu().numpy()[0, :k1], c["blended"], rtol=1e-3, atol=1e-5, err_msg=f"case {ci}")
+        assert int(res["idx_hybrid"][0]) == int(c["idx_hybrid"]), ci          # fixtures have clear top-2 margins
+        assert np.array_equal(res["top_idx"].cpu().numpy()[0, :k1], c["top_idx"]), ci
+        assert int(res["idx_final"][0]) == int(c["idx_final"]), ci
+        assert iu.cpu().numpy()[0].tolist() == c["IU"].tolist(), ci            # integer counters: bit-exact
+        assert cum.cpu().numpy().tolist() == c["IU"].tolist(), ci
+
+
+def test_scoring_bf16_features_within_tolerance(ops, golden):
+    g = golden("scoring")
+    for ci in (0, 5, 11, 24):
+        c = _case(g, ci)       # features in the fixtures are already bf16-representable
+        _, res, _, _ = _run_case(ops, c, torch.bfloat16)
+        np.testing.assert_allclose(res["score_clip"].cpu().numpy()[0, :c["n"]], c["score_clip"], rtol=1e-3, atol=1e-4)
+        assert int(res["idx_final"][0]) == int(c["idx_final"])
+
+
+def test_batched_ragged_pipeline_vs_oracle(ops):
+    """Several images with different mask / expression counts in ONE launch of each kernel."""
+    from hybridgl_b200._lib import DIR_CODES, REL_CODES
+    h, w, de = 120, 160, 64
+    spec = [(7, 2), (3, 1), (12, 3), (1, 2), (6, 5)]
+    items = [synth.make_item(300 + i, h, w, n, e, de=de) for i, (n, e) in enumerate(spec)]
+    moff = np.cumsum([0] + [n for n, _ in spec]).astype(np.int32)
+    eoff = np.cumsum([0] + [e for _, e in spec]).astype(np.int32)
+    max_n = max(n for n, _ in spec)
+    exprs = [ex for it in items for ex in it.expressions]
+    masks = np.concatenate([it.masks for it in items]); boxes = np.concatenate([it.boxes for it in items])
+    feats = np.concatenate([it.features for it in items])
+    heat = np.stack([ex.heatmap for ex in exprs])
+    ooff = np.cumsum([0] + [ex.other_feats.shape[0] for ex in exprs]).astype(np.int32)
+    others = np.concatenate([ex.other_feats for ex in exprs]) if ooff[-1] else np.zeros((0, de), np.float32)
+    dirs = np.array([DIR_CODES[ex.dirflag] for ex in exprs], np.int32)
+    rels = np.array([REL_CODES[ex.relaflag] for ex in exprs], np.int32)
+    black = np.array([O.black_for(ex.relaflag) for ex in exprs], np.float32)
+    target = np.stack([it.target for it in items])
+    dm, dmo, deo = cu(masks), cu(moff), cu(eoff)
+    sg = ops.heat_pool(cu(heat), cu(dirs), cu(black), dm, dmo, deo, max_n)
+    res = ops.score_select(cu(feats), cu(np.stack([ex.sentence_feat for ex in exprs])), cu(np.stack([ex.noun_feat for ex in exprs])),
+                           cu(others), cu(ooff), cu(boxes), cu(rels), sg, dmo, deo, max_n, logit_scale_exp=100.0)
+    cum = torch.zeros(4, dtype=torch.int64, device=DEV)
+    iu = ops.iou_accumulate(dm, cu(target), res["idx_hybrid"], res["idx_final"], cum, dmo, deo).cpu().numpy()
+    sgh = sg.cpu().numpy(); sch = res["score_clip"].cpu().numpy()
+    tot = np.zeros(4, np.int64)
+    e = 0
+    for it in items:
+        for ex in it.expressions:
+            n = it.n_masks
+            ref_sg = O.gem_pool(O.condition_heatmap(ex.heatmap, ex.dirflag), it.masks, O.black_for(ex.relaflag))
+            np.testing.assert_allclose(sgh[e, :n], ref_sg, rtol=1e-3, atol=1e-4)
+            r = O.score_and_select(it.features, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag,
+                                   score_gem=ref_sg, logit_scale_exp=100.0)
+            np.testing.assert_allclose(sch[e, :n], r["score_clip"], rtol=1e-3, atol=1e-4)
+            top2 = np.sort(r["score_clip"])[-2:] if n > 1 else None
+            if top2 is None or top2[1] - top2[0] > 1e-3 * abs(top2[1]):
+                assert int(res["idx_hybrid"][e]) == r["idx_hybrid"]
+            b2 = np.sort(r["blended"])[-2:] if len(r["blended"]) > 1 else None
+            if b2 is None or b2[1] - b2[0] > 1e-3 * max(abs(b2[1]), 1e-3):
+                assert int(res["idx_final"][e]) == r["idx_final"]
+            i0, u0, _ = O.compute_iou(it.masks[int(res["idx_hybrid"][e])], it.target)
+            i1, u1, _ = O.compute_iou(it.masks[int(res["idx_final"][e])], it.target)
+            assert iu[e].tolist() == [i0, u0, i1, u1]
+            tot += np.array([i0, u0, i1, u1])
+            e += 1
+    assert cum.cpu().numpy().tolist() == tot.tolist()
+
+
+def test_full_size_properties(ops):
+    """BASELINE config-2 shapes: size-independent properties instead of an element-wise oracle."""
+    cfg = synth.CONFIGS[2]
+    it = synth.make_item(77, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], de=cfg["De"])
+    it.masks[0] = True                                     # full-frame proposal: local == Normalize(Resize(img)) exactly
+    img = cu(it.image); masks = cu(it.masks)
+    blur = ops.gaussian_blur15(img)
+    loc, glo = ops.prep_visual_prompts(img, blur, masks, cfg["S"])
+    ol, og = O.prep(it.image, blur.cpu().numpy(), it.masks[:2], cfg["S"])
+    assert np.array_equal(loc[:2].cpu().numpy(), ol) and np.array_equal(glo[:2].cpu().numpy(), og)
+    # every output pixel is a convex combination of its taps: bounded by the normalised range of u8 pixels
+    lo = float((0 - 0.485) / 0.229) - 1e-5; hi = float((1 - 0.406) / 0.225) + 1e-5
+    assert float(loc.min()) >= lo and float(loc.max()) <= hi and float(glo.min()) >= lo and float(glo.max()) <= hi
+    grid, area = ops.masks_to_grid(masks, cfg["g"], want_area=True)
+    assert np.array_equal(area.cpu().numpy(), it.masks.reshape(it.n_masks, -1).sum(1))
+    # antialiased weights are normalised: the grid mean equals the mask's area fraction (up to fp32 rounding)
+    frac = area.double() / (cfg["h"] * cfg["w"])
+    assert torch.allclose(grid.double().mean(dim=(1, 2)), frac, atol=2e-3)
+    assert torch.all(grid[0] > 0.999999)
