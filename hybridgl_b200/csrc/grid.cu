@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256) token_mask_fuse_kernel(const void* __rest
 
 extern "C" int hgl_mask_grid(const uint8_t* masks, int M, int H, int W, int g, int antialias, float* grid, int32_t* area, void* stream) {
   using namespace hgl;
+  if (M == 0) return HGL_OK;
   HGL_REQUIRE(masks && grid, "hgl_mask_grid: null pointer");
   HGL_REQUIRE(M >= 0 && H >= 1 && W >= 1 && g >= 1 && g <= kMaxG, "hgl_mask_grid: bad shape M=%d H=%d W=%d g=%d", M, H, W, g);
   if (M == 0) return HGL_OK;

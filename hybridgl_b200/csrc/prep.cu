@@ -270,6 +270,7 @@ extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint8_t
                         int B, int M, int H, int W, int S, int bg_mode, int out_dtype,
                         void* local_out, void* global_out, void* stream) {
   using namespace hgl;
+  if (M == 0 && B >= 1) return HGL_OK;   // nothing to do (empty tensors have null data pointers)
   HGL_REQUIRE(image && masks && local_out && global_out, "hgl_prep: null pointer");
   HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK, "hgl_prep: bg_mode %d", bg_mode);
   HGL_REQUIRE(bg_mode != HGL_BG_BLUR || blur, "hgl_prep: blur frame required for HGL_BG_BLUR");
