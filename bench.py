@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the HybridGL mask-proposal scoring path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 2] [--images 16]
+
+A *step* is one pass of the hot path (blur -> prep -> mask grid -> heat-map pooling -> score/select -> IoU)
+over one batch of `--images` synthetic RefCOCO-shaped images per GPU (BASELINE.json configs[1]: 480x640,
+100 masks/image, 3 expressions/image, ViT-B/16 geometry S=224 g=14 De=512, bf16 prep outputs).  One JSON line
+on stdout (rank 0).  `value` = expressions/s with inputs resident in HBM, `e2e` = the same through
+ScoringPath.run_host with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+`--impl reference` times the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "expressions/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=int, default=2, help="BASELINE.json config index (1-based), default 2")
+    ap.add_argument("--images", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
+    return ap.parse_args()
+
+
+def workload_config(idx: int, images: int):
+    from hybridgl_b200 import synth
+    c = dict(synth.CONFIGS[idx])
+    c["images_per_gpu_per_step"] = images
+    return c
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def _oracle_one_image(args):
+    """The reference path for ONE image on one core, through the numpy oracle port (oracle/hybridgl_oracle.py)."""
+    seed, cfg, n_masks = args
+    import numpy as np
+    from hybridgl_b200 import synth
+    from oracle import hybridgl_oracle as O
+    it = synth.make_item(seed, cfg["h"], cfg["w"], n_masks, cfg["n_expr"], de=cfg["De"], n_other=2)
+    t0 = time.perf_counter()
+    blur = O.gaussian_blur_u8(it.image)
+    O.prep(it.image, blur, it.masks, cfg["S"])
+    O.mask_to_grid(it.masks, cfg["g"], antialias=True)
+    cum = np.zeros(4, np.int64)
+    for ex in it.expressions:
+        sg = O.gem_pool(O.condition_heatmap(ex.heatmap, ex.dirflag), it.masks, O.black_for(ex.relaflag))
+        r = O.score_and_select(it.features, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag, score_gem=sg)
+        i0, u0, _ = O.compute_iou(it.masks[r["idx_hybrid"]], it.target)
+        i1, u1, _ = O.compute_iou(it.masks[r["idx_final"]], it.target)
+        cum += np.array([i0, u0, i1, u1])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_sample(cfg, budget_s: float = 20.0):
+    """Rank 0, N=1: the oracle port on ONE host core over a bounded sample (whole images of the workload)."""
+    n_masks = cfg["n_masks"]
+    t_first = _oracle_one_image((9000, cfg, n_masks))
+    imgs, total = 1, t_first
+    while total + t_first < budget_s and imgs < 4:
+        total += _oracle_one_image((9000 + imgs, cfg, n_masks)); imgs += 1
+    return {"value": imgs * cfg["n_expr"] / total, "unit": METRIC, "cores": 1, "kind": "port",
+            "sample": f"{imgs} image(s) x {n_masks} masks x {cfg['n_expr']} expressions of the same workload, numpy oracle port "
+                      f"(oracle/hybridgl_oracle.py), {total:.1f} s on 1 core; the Python reference itself cannot travel to the GPU box"}
+
+
+def run_reference(args, cfg):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference is Python and does
+    not exist on the GPU box) on all host cores: one image per worker process per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    n_masks = cfg["n_masks"]
+    t_img = _oracle_one_image((8000, cfg, n_masks))
+    # keep the whole run within ~4 minutes: shrink the per-image mask count if one image per step would not fit
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    scale = 1.0
+    if t_img * 1.5 > budget:
+        scale = max(0.05, budget / (t_img * 1.5))
+        n_masks = max(4, int(cfg["n_masks"] * scale))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for w in range(args.warmup):
+            pool.map(_oracle_one_image, [(7000 + w * workers + i, cfg, n_masks) for i in range(workers)])
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_oracle_one_image, [(6000 + s * workers + i, cfg, n_masks) for i in range(workers)])
+        dt = time.perf_counter() - t0
+    # throughput in expressions/s of the FULL workload: a step with n_masks' < n_masks does n_masks'/n_masks of the work
+    eff = n_masks / cfg["n_masks"]
+    value = args.steps * workers * cfg["n_expr"] * eff / dt
+    sample = (f"{workers} images per step (one per worker process), {n_masks}/{cfg['n_masks']} masks per image"
+              f"{' (throughput scaled by that fraction; per-mask work dominates)' if eff < 1 else ''}, numpy oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
+            "cpu_baseline": {"value": value, "unit": METRIC, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    return (f"RefCOCO-shaped synthetic batch: {cfg['images_per_gpu_per_step']} images/GPU/step, {cfg['h']}x{cfg['w']}, "
+            f"{cfg['n_masks']} masks/image, {cfg['n_expr']} expressions/image, ViT-B/16 geometry (S={cfg['S']}, g={cfg['g']}, "
+            f"De={cfg['De']}), fusion_mode {cfg['fusion_mode']} (features supplied)")
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(cfg, B, prep_bytes):
+    """Per-launch algorithmic HBM bytes of each kernel (stated in DESIGN.md)."""
+    H, W, N, E, S, De = cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["S"], cfg["De"]
+    M, ET = B * N, B * E
+    return {
+        "blur": 2 * B * H * W * 3,
+        "pack": M * H * W + M * H * ((W + 31) // 32) * 4,
+        "prep": M * H * ((W + 31) // 32) * 4 + 2 * B * H * W * 3 + 2 * M * 3 * S * S * prep_bytes,
+        "grid": M * H * W + M * cfg["g"] ** 2 * 4,
+        "heat_pool": M * H * W + 2 * ET * H * W * 4 + ET * N * 4,
+        "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
+        "iou": 2 * 2 * ET * H * W,
+    }
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from hybridgl_b200 import synth
+    from hybridgl_b200.pipeline import ScoringPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.images
+    prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype)
+    # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
+    batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev)
+               for i in range(2)]
+    max_n = cfg["n_masks"]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        path.run(batches[w % 2], max_n)
+    path.cum.zero_()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    stage_events = []
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        path.events = []
+        path.run(batches[s % 2], max_n)
+        stage_events.append(path.events)
+    path.events = None
+    cum = path.cum.clone()
+    if world > 1:
+        dist.all_reduce(cum)              # the path's only collective: IoU accumulators (64 bytes)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    expr_per_step = world * B * cfg["n_expr"]
+    value = expr_per_step * args.steps / (ms_total / 1e3)
+
+    # per-kernel durations from the events recorded inside the timed region
+    dur = {}
+    for evs in stage_events:
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            dur.setdefault(n1, []).append(e0.elapsed_time(e1))
+    avg_ms = {k: sum(v) / len(v) for k, v in dur.items()}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg = algorithmic_bytes(cfg, B, 2 if prep_dtype == torch.bfloat16 else 4)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    kernels = {}
+    for k, b in alg.items():
+        if k in avg_ms and avg_ms[k] > 0:
+            ach = b / (avg_ms[k] * 1e-3) / 1e9
+            kernels[k] = {"ms": round(avg_ms[k], 4), "algorithmic_bytes": b, "achieved_gbs": round(ach, 1), "frac": round(ach / peak_hbm, 4),
+                          "share_of_step": round(avg_ms[k] / sum(avg_ms.values()), 4)}
+    top = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"kernel": f"hgl_{top}", "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak_hbm, "unit": "GB/s",
+                "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src}
+
+    # ---- e2e: the public API with pinned HOST buffers
+    e2e = None
+    if args.e2e_steps > 0:
+        host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
+        for w in range(2):
+            path.run_host(host[w % 2], max_n)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in range(args.e2e_steps):
+            out = path.run_host(host[s % 2], max_n)
+        t1.record()
+        barrier()
+        ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": expr_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": METRIC,
+               "h2d_bytes_per_step": ScoringPath.h2d_bytes(host[0]), "d2h_bytes_per_step": path.d2h_bytes(),
+               "steps": args.e2e_steps, "api": "hybridgl_b200.pipeline.ScoringPath.run_host (pinned host tensors in / out)"}
+        del out
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(cfg)
+        c = [int(v) for v in cum.tolist()]
+        line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if prep_dtype == torch.bfloat16 else "f32", "data": "synthetic",
+                "config": {"workload": workload_name(cfg), "l2": "two alternating batches, masks alone are "
+                           f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
+                           **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": ScoringPath.LAUNCHES_PER_RUN * args.steps,
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+                "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
+                        "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = workload_config(args.workload, args.images)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,8 +18,10 @@ SIGNATURES = {
     "hgl_last_error": (c_char_p, []),
     "hgl_version": (c_int, []),
     "hgl_check_device": (c_int, []),
-    "hgl_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                         c_void_p, c_void_p, c_void_p]),
+    "hgl_pack_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hgl_prep_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "hgl_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgl_gaussian_blur15": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hgl_mask_grid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hgl_attn_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -77,18 +77,41 @@ def gaussian_blur15(image: torch.Tensor, out: Optional[torch.Tensor] = None) -> 
     return out[0] if squeeze else out
 
 
+def pack_masks(masks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bool/u8 [M,H,W] -> packed int32 [M,H,ceil(W/32)] (bit i of word w = pixel 32*w+i).  The one pass over the byte masks."""
+    m = _mask_bytes(masks)
+    M, H, W = m.shape
+    if out is None:
+        out = torch.empty((M, H, (W + 31) // 32), dtype=torch.int32, device=m.device)
+    else:
+        _req(out, torch.int32, "bits", 3)
+        if tuple(out.shape) != (M, H, (W + 31) // 32):
+            raise ValueError(f"bits must be [M,H,ceil(W/32)] int32, got {tuple(out.shape)}")
+    check(_lib.load().hgl_pack_masks(m.data_ptr(), M, H, W, out.data_ptr(), _stream()), "hgl_pack_masks")
+    return out
+
+
+def _bits(masks_or_bits: torch.Tensor, W: Optional[int] = None) -> torch.Tensor:
+    """Accept either byte masks (packed on the fly) or an already packed int32 tensor."""
+    if masks_or_bits.dtype == torch.int32:
+        return _req(masks_or_bits, torch.int32, "bits", 3)
+    return pack_masks(masks_or_bits)
+
+
 def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks: torch.Tensor, size: int,
-                        mask_off: Optional[torch.Tensor] = None, background: str = "blur",
+                        mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None, background: str = "blur",
                         dtype: torch.dtype = torch.float32,
-                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S]."""
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                        workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S].
+    `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks()."""
     img = image[None] if image.dim() == 3 else image
     _req(img, torch.uint8, "image", 4)
     B, H, W, _ = img.shape
-    m = _mask_bytes(masks)
-    M = m.shape[0]
-    if tuple(m.shape[1:]) != (H, W):
-        raise ValueError(f"masks {tuple(m.shape)} do not match the frame {H}x{W}")
+    bits = _bits(masks)
+    M = bits.shape[0]
+    if tuple(bits.shape[1:]) != (H, (W + 31) // 32):
+        raise ValueError(f"masks {tuple(masks.shape)} do not match the frame {H}x{W}")
     bg = {"blur": HGL_BG_BLUR, "black": HGL_BG_BLACK}[background]
     bl = None
     if bg == HGL_BG_BLUR:
@@ -99,13 +122,23 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
         if bl.shape != img.shape:
             raise ValueError("blur must have the shape of image")
     off = _offsets(mask_off, B, "mask_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
     if out is None:
         local = torch.empty((M, 3, size, size), dtype=dtype, device=img.device)
         glob = torch.empty_like(local)
     else:
         local, glob = out
-    check(_lib.load().hgl_prep(img.data_ptr(), _ptr(bl), m.data_ptr(), _ptr(off), B, M, H, W, size, bg, _dt(dtype),
-                               local.data_ptr(), glob.data_ptr(), _stream()), "hgl_prep")
+    lib = _lib.load()
+    need = lib.hgl_prep_workspace_bytes(B, size, _dt(dtype))
+    if need < 0:
+        raise ValueError(f"prep: unsupported size {size}")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=img.device)
+    check(lib.hgl_prep(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, bg, _dt(dtype),
+                       local.data_ptr(), glob.data_ptr(), workspace.data_ptr(), _stream()), "hgl_prep")
     return local, glob
 
 

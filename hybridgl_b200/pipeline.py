@@ -1,0 +1,134 @@
+"""The mask-proposal scoring path as one batched call (the public API of this package).
+
+Mirrors, for a batch of images at once, what one iteration of the reference's evaluation loop does between
+"SAM has produced masks + boxes" (Hybridgl_main.py:86-90) and "IoU counters updated" (Hybridgl_main.py:230):
+
+    blur -> prep (local/global CLIP inputs) -> mask grid (+area) -> [hybrid CLIP features: plain PyTorch backbone,
+    or supplied by the caller] -> GEM heat-map pooling -> cosine scoring + spatial guidance + argmax -> IoU
+
+Every arithmetic step runs in libhgl.so (hand-written sm_100a kernels behind the C ABI); this file only owns
+buffers, streams and the order of launches.  Host language stays Python like the reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+# host->device inputs of one step and their dtypes (what a caller must provide per batch)
+INPUT_KEYS = ("image", "masks", "boxes", "target", "features", "sent", "noun", "others", "other_off", "heat",
+              "dirflag", "relaflag", "black", "mask_off", "expr_off")
+# device->host results of one step
+OUTPUT_KEYS = ("score_clip", "score_gem", "idx_hybrid", "idx_final", "top_idx", "blended", "iu")
+
+
+class ScoringPath:
+    """Batched scoring path.  `size` = CLIP input side (224 | 336), `grid` = patch grid side (14 | 24)."""
+
+    def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
+                 background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
+                 device: Optional[torch.device] = None):
+        ops.device_ok()
+        self.size, self.grid = size, grid
+        self.prep_dtype, self.antialias, self.background = prep_dtype, antialias, background
+        self.logit_scale_exp, self.r, self.alpha = logit_scale_exp, r, alpha
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.cum = torch.zeros(4, dtype=torch.int64, device=self.device)     # cum_I, cum_U, cum_I_final, cum_U_final
+        self._buf: Dict[str, torch.Tensor] = {}
+        self._dev_in: Dict[str, torch.Tensor] = {}
+        self._host_out: Dict[str, torch.Tensor] = {}
+        self.events = None            # optional per-stage CUDA events (bench.py)
+
+    # ------------------------------------------------------------------------------------------------
+    def _get(self, name: str, shape, dtype) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def _mark(self, name: str):
+        if self.events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.append((name, ev))
+
+    def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """One pass over a device-resident batch.  Returns device tensors (see OUTPUT_KEYS) plus the prep
+        outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M]."""
+        img, masks = batch["image"], batch["masks"]
+        B, H, W, _ = img.shape
+        M = masks.shape[0]
+        moff, eoff = batch["mask_off"], batch["expr_off"]
+        self._mark("start")
+        blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
+        self._mark("blur")
+        bits = ops.pack_masks(masks, out=self._get("bits", (M, H, (W + 31) // 32), torch.int32))
+        self._mark("pack")
+        local = self._get("local", (M, 3, self.size, self.size), self.prep_dtype)
+        glob = self._get("global", (M, 3, self.size, self.size), self.prep_dtype)
+        lib = ops._lib.load()
+        pws = self._get("prep_ws", (max(lib.hgl_prep_workspace_bytes(B, self.size, ops._dt(self.prep_dtype)), 1),), torch.uint8)
+        ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
+                                dtype=self.prep_dtype, out=(local, glob), workspace=pws)
+        self._mark("prep")
+        grid, area = ops.masks_to_grid(masks, self.grid, antialias=self.antialias, want_area=True)
+        self._mark("grid")
+        feats = batch["features"] if features is None else features
+        E = batch["sent"].shape[0]
+        need = lib.hgl_heat_pool_workspace_bytes(B, M, E, H, W, max_n)
+        ws = self._get("heat_ws", (need,), torch.uint8)
+        score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], masks, moff, eoff, max_n, workspace=ws)
+        self._mark("heat_pool")
+        res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
+                               batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)
+        self._mark("score_select")
+        iu = ops.iou_accumulate(masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
+        self._mark("iou")
+        res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits)
+        return res
+
+    # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid 1, heat_pool 3, score_select 1, iou 2
+    LAUNCHES_PER_RUN = 11
+
+    def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:
+        """End-to-end call with HOST buffers (pinned): H2D of every input, the kernels, D2H of the results,
+        then a stream synchronise.  This is what bench.py times as `e2e`."""
+        for k in INPUT_KEYS:
+            src = host_batch[k]
+            dst = self._dev_in.get(k)
+            if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                self._dev_in[k] = dst
+            dst.copy_(src, non_blocking=True)
+        res = self.run(self._dev_in, max_n)
+        out = {}
+        for k in OUTPUT_KEYS:
+            src = res[k]
+            dst = self._host_out.get(k)
+            if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                dst = torch.empty(src.shape, dtype=src.dtype).pin_memory()
+                self._host_out[k] = dst
+            dst.copy_(src, non_blocking=True)
+            out[k] = dst
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    @staticmethod
+    def h2d_bytes(host_batch: Dict[str, torch.Tensor]) -> int:
+        return sum(host_batch[k].numel() * host_batch[k].element_size() for k in INPUT_KEYS)
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._host_out.values())
+
+
+def report(cum: torch.Tensor, ious_hybrid, ious_final):
+    """The four numbers the reference appends to result_log (Hybridgl_main.py:240-247)."""
+    c = [int(v) for v in cum.tolist()]
+    o = c[0] * 100.0 / c[1] if c[1] else float("nan")
+    of = c[2] * 100.0 / c[3] if c[3] else float("nan")
+    m = float(torch.tensor(ious_hybrid, dtype=torch.float32).mean()) * 100.0 if len(ious_hybrid) else float("nan")
+    mf = float(torch.tensor(ious_final, dtype=torch.float32).mean()) * 100.0 if len(ious_final) else float("nan")
+    return dict(oIoU=o, mIoU=m, oIoU_final=of, mIoU_final=mf)

@@ -180,3 +180,64 @@ CONFIGS = {
     4: dict(h=480, w=640, n_masks=200, n_expr=3, S=336, g=24, Dv=1024, De=768, heads=16, layers=24, fusion_mode="G2L&L2G"),
     5: dict(h=600, w=800, n_masks=200, n_expr=5, S=224, g=14, Dv=768, De=512, heads=12, layers=12, fusion_mode="G2L"),
 }
+
+
+# --------------------------------------------------------------------------------------------------
+# device-side generator for benchmark-sized batches (same shapes / statistics, torch RNG on the GPU)
+# --------------------------------------------------------------------------------------------------
+def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_expr: int, de: int,
+                      device="cuda", n_other: int = 2, pinned_host: bool = False):
+    """RefCOCO-shaped batch laid out for the batched C ABI (ragged offsets, here uniform).
+    Returns a dict of tensors on `device` (or pinned host tensors when pinned_host=True)."""
+    import torch
+    gen = torch.Generator(device=device).manual_seed(seed)
+    B, N, E = n_images, n_masks, n_expr
+    M, ET = B * N, B * E
+
+    def rand(*shape):
+        return torch.rand(*shape, generator=gen, device=device)
+
+    coarse = rand(B, 3, 14, 14)
+    base = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=False)
+    img = (0.75 * base + 0.25 * rand(B, 3, h, w)).mul(255).add(0.5).clamp(0, 255).to(torch.uint8)
+    image = img.permute(0, 2, 3, 1).contiguous()                                       # [B,H,W,3] u8
+    lo, hi = float(np.log(800.0)), float(np.log(0.6 * h * w))
+    area = torch.exp(lo + (hi - lo) * rand(M))
+    ratio = torch.exp(-0.9 + 1.8 * rand(M))
+    ra = torch.sqrt(area / np.pi * ratio); rb = torch.sqrt(area / np.pi / ratio)
+    cy = (0.1 + 0.8 * rand(M)) * h; cx = (0.1 + 0.8 * rand(M)) * w
+    th = rand(M) * np.pi
+    yy = torch.arange(h, device=device, dtype=torch.float32)[None, :, None]
+    xx = torch.arange(w, device=device, dtype=torch.float32)[None, None, :]
+    masks = torch.empty((M, h, w), dtype=torch.bool, device=device)
+    for s in range(0, M, 64):                                                           # chunked: keeps temporaries small
+        sl = slice(s, min(M, s + 64))
+        dx = xx - cx[sl, None, None]; dy = yy - cy[sl, None, None]
+        c, sn = torch.cos(th[sl])[:, None, None], torch.sin(th[sl])[:, None, None]
+        u = dx * c + dy * sn; v = -dx * sn + dy * c
+        masks[sl] = (u / ra[sl, None, None]) ** 2 + (v / rb[sl, None, None]) ** 2 <= 1.0
+    masks[:, h // 2, w // 2] = True                                                      # never empty
+    ys = masks.any(dim=2); xs = masks.any(dim=1)
+    y0 = ys.float().argmax(1); y1 = h - 1 - ys.flip(1).float().argmax(1)
+    x0 = xs.float().argmax(1); x1 = w - 1 - xs.flip(1).float().argmax(1)
+    boxes = torch.stack([x0, y0, x1 - x0, y1 - y0], dim=1).to(torch.int64)              # SAM XYWH convention
+    pick = torch.randint(0, N, (B,), generator=gen, device=device) + torch.arange(B, device=device) * N
+    target = torch.roll(masks[pick], shifts=(3, -4), dims=(1, 2)).to(torch.uint8)       # [B,H,W]
+    feats = torch.randn((M, de), generator=gen, device=device).to(torch.bfloat16)
+    anchor = feats[torch.randint(0, N, (ET,), generator=gen, device=device)
+                   + torch.arange(B, device=device).repeat_interleave(E) * N].float() * 0.25
+    sent = (torch.randn((ET, de), generator=gen, device=device) + 1.5 * anchor).to(torch.bfloat16).float()
+    noun = (0.6 * sent + 0.8 * torch.randn((ET, de), generator=gen, device=device) + 1.5 * anchor).to(torch.bfloat16).float()
+    others = torch.randn((ET * n_other, de), generator=gen, device=device).to(torch.bfloat16).float()
+    other_off = (torch.arange(ET + 1, device=device) * n_other).to(torch.int32)
+    heat = torch.nn.functional.interpolate(rand(ET, 1, 28, 37), size=(h, w), mode="bilinear", align_corners=False)[:, 0].contiguous()
+    dirflag = torch.randint(0, 6, (ET,), generator=gen, device=device).to(torch.int32)
+    relaflag = torch.randint(0, 8, (ET,), generator=gen, device=device).to(torch.int32)
+    black = torch.where(relaflag == 5, 1.95, torch.where(relaflag == 6, 1.5, 1.8)).to(torch.float32)
+    out = dict(image=image, masks=masks, boxes=boxes, target=target, features=feats, sent=sent, noun=noun, others=others,
+               other_off=other_off, heat=heat, dirflag=dirflag, relaflag=relaflag, black=black,
+               mask_off=(torch.arange(B + 1, device=device) * N).to(torch.int32),
+               expr_off=(torch.arange(B + 1, device=device) * E).to(torch.int32))
+    if pinned_host:
+        out = {k: v.cpu().pin_memory() for k, v in out.items()}
+    return out

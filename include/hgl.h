@@ -53,15 +53,23 @@ HGL_API int hgl_version(void);
 /* 0 if the current device is sm_100 and the kernels are loadable, HGL_EARCH otherwise */
 HGL_API int hgl_check_device(void);
 
+/* ---- packed mask format ------------------------------------------------------------------------------
+ * bits u32 [M, H, WW], WW = ceil(W/32); bit i of word w of a row is pixel x = 32*w + i (non-zero byte -> 1).
+ * The byte masks of SAM (torch.bool [M,H,W], Hybridgl_main.py:86-87) are read exactly once, here; prep, the mask
+ * grid and the heat-map pooling all consume the 8x smaller packed tensor. */
+HGL_API int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream);
+
 /* ---- (a1) per-mask visual-prompt preprocessing ------------------------------------------------------
  * Replaces the Python loop Hybridgl_main.py:92-125 (dups demo.py:79-112) and utils.py:292-345:
  *   global[n] = Normalize_IN(bilinear_S( where(mask_n, image, background) / 255 ))
  *   local[n]  = bilinear_S( where(mask_n, Normalize_IN(image/255), clip_pixel_mean) )
- * image/blur u8 [B,H,W,3]; masks u8 [M,H,W]; mask_off int32 [B+1] (NULL => B==1, all M masks belong to image 0);
- * local_out/global_out [M,3,S,S] of out_dtype.  blur may be NULL for HGL_BG_BLACK. */
-HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint8_t* masks, const int32_t* mask_off,
-             int B, int M, int H, int W, int S, int bg_mode, int out_dtype,
-             void* local_out, void* global_out, void* stream);
+ * image/blur u8 [B,H,W,3]; bits = packed masks [M,H,WW]; mask_off int32 [B+1] (NULL => B==1, all M masks belong
+ * to image 0); max_n >= masks of any one image; local_out/global_out [M,3,S,S] of out_dtype (16-byte aligned).
+ * blur may be NULL for HGL_BG_BLACK.  workspace: hgl_prep_workspace_bytes() bytes, 256-byte aligned. */
+HGL_API int64_t hgl_prep_workspace_bytes(int B, int S, int out_dtype);
+HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off,
+             int B, int M, int max_n, int H, int W, int S, int bg_mode, int out_dtype,
+             void* local_out, void* global_out, void* workspace, void* stream);
 
 /* cv2.GaussianBlur(img,(15,15),0) on uint8, BORDER_REFLECT_101, OpenCV's Q8 fixed-point taps
  * (Hybridgl_main.py:99).  image/out u8 [B,H,W,3]. */

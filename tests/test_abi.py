@@ -42,19 +42,19 @@ def test_library_loads_and_reports_errors(lib):
     h = lib.load()
     assert h.hgl_version() >= 100
     # argument validation happens before any CUDA call, so it is testable without a device
-    rc = h.hgl_prep(None, None, None, None, 1, 1, 8, 8, 8, 0, 0, None, None, None)
+    rc = h.hgl_prep(None, None, None, None, 1, 1, 1, 8, 8, 8, 0, 0, None, None, None, None)
     assert rc == -1 and b"null pointer" in h.hgl_last_error()
     rc = h.hgl_mask_grid(1, 1, 8, 8, 99, 1, 1, None, None)
     assert rc == -1 and b"bad shape" in h.hgl_last_error()
     assert h.hgl_heat_pool_workspace_bytes(2, 10, 3, 48, 64, 8) > 0
 
 
-def test_sass_is_sm100_and_uses_bulk_copy(lib):
+def test_sass_is_sm100(lib):
     out = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout or "SM100a" in out.stdout or "sm_100" in out.stdout
-    assert "UBLKCP" in out.stdout          # the prep kernel's TMA bulk copy
+    assert "STG.E.NA" in out.stdout        # streaming (no-allocate) stores of the prep kernel
 
 
 def test_ops_fail_loudly_without_cuda(lib):

@@ -80,6 +80,27 @@ def test_prep_vs_oracle_f32_and_bf16(ops, h, w, S, n, seed):
     assert np.array_equal(gb.float().cpu().numpy(), bf16r(og))
 
 
+def _pack_ref(masks):
+    m, h, w = masks.shape
+    ww = (w + 31) // 32
+    pad = np.zeros((m, h, ww * 32), bool); pad[:, :, :w] = masks
+    return np.packbits(pad, axis=-1, bitorder="little").view("<u4").reshape(m, h, ww).astype(np.uint32)
+
+
+@pytest.mark.parametrize("h,w,S,n", [(480, 640, 224, 5), (333, 500, 224, 3), (97, 131, 32, 4), (60, 90, 64, 3), (64, 64, 128, 2), (900, 1200, 224, 2)])
+def test_packed_masks_and_prep_from_bits(ops, h, w, S, n):
+    it = synth.make_item(50 + n, h, w, n, 0, with_features=False)
+    it.masks[0, 0, :] = True; it.masks[0, -1, :] = True; it.masks[-1, :, 0] = True; it.masks[-1, :, -1] = True
+    ref = _pack_ref(it.masks)
+    masks = cu(it.masks)
+    got = ops.pack_masks(masks).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, ref)
+    blur = O.gaussian_blur_u8(it.image)
+    loc, glo = ops.prep_visual_prompts(cu(it.image), cu(blur), ops.pack_masks(masks), S)   # prep straight from packed masks
+    ol, og = O.prep(it.image, blur, it.masks, S)
+    assert np.array_equal(loc.cpu().numpy(), ol) and np.array_equal(glo.cpu().numpy(), og)
+
+
 def test_prep_black_background_and_edge_masks(ops):
     it = synth.make_item(11, 120, 160, 4, 0, with_features=False)
     it.masks[0] = False; it.masks[1] = True          # empty and full-frame proposals
@@ -95,7 +116,7 @@ def test_prep_ragged_batch(ops):
     masks = np.concatenate([it.masks for it in items])
     off = np.cumsum([0] + [it.n_masks for it in items]).astype(np.int32)
     blur = ops.gaussian_blur15(cu(img))
-    loc, glo = ops.prep_visual_prompts(cu(img), blur, cu(masks), 32, mask_off=cu(off))
+    loc, glo = ops.prep_visual_prompts(cu(img), blur, cu(masks), 32, mask_off=cu(off), max_n=9)
     loc = loc.cpu().numpy(); glo = glo.cpu().numpy()
     for i, it in enumerate(items):
         ol, og = O.prep(it.image, O.gaussian_blur_u8(it.image), it.masks, 32)
