@@ -6,20 +6,22 @@
 // The reference loops over masks in Python (~8 full-frame kernels + one D2H sync per mask).  Here (SURVEY.md
 // Appendix A-2): S_in[e,n] = masks[n,:] . A''_e, area[n] = |m_n|, S_tot[e] = sum A''_e, then a closed form.
 //
-// B200 design: the masks (M*H*W bytes) are the only large operand -> read each byte once per group of
-// expressions, straight from HBM into registers (no shared-memory staging: there is no reuse of mask bytes).
+// B200 design: works on the PACKED masks (hgl_pack_masks), 8x fewer bytes than the byte masks and mostly zero words.
 //   pass 1  heat_stats : per expression min / max / sum(A*ramp)            (E*H*W*4 bytes, tiny)
-//   pass 2  heat_pool  : a warp owns 32*PX contiguous pixels, keeps the conditioned heat values of up to EB
-//                        expressions of its image in REGISTERS and streams every mask of that image past them
-//                        (16-byte coalesced loads, predicated adds, one shuffle tree per (mask, warp));
-//                        per-CTA partials are combined in a fixed order (deterministic, no float atomics)
-//   pass 3  finalize   : sum the tile partials in order, closed form -> score_gem[E, max_n]
+//   pass 2  heat_pool  : a CTA owns (image, band of RB rows): the conditioned heat values of up to EB expressions of
+//                        that band sit in shared memory; each warp streams masks: 32 bit-words per coalesced load, one
+//                        ballot finds the non-zero words, and for each of those all 32 lanes add their pixel's heat
+//                        value when their bit is set (conflict-free LDS, lane-private accumulators, ONE shuffle tree per
+//                        (mask, band)).  Zero words -- most of a mask -- cost nothing.  Partials are written per band and
+//                        combined in a fixed order (deterministic, no float atomics).
+//   pass 3  finalize   : sum the band partials in order, closed form -> score_gem[E, max_n]
 #include "hgl_common.cuh"
 
 namespace hgl {
 
 constexpr int kStatChunks = 32;
 constexpr int kPoolWarps = 8;
+constexpr int kPoolRows = 4;      // rows per band
 
 __device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {  // ATen linspace (float): both-ends evaluation
   if (n <= 1) return a;
@@ -46,9 +48,9 @@ struct HeatWs {            // workspace carve-up (all offsets in bytes, 16-align
   size_t bytes;
 };
 
-static HeatWs carve(void* ws, int M, int E, int H, int W, int max_n, int tile_px) {
+static HeatWs carve(void* ws, int M, int E, int H, int W, int max_n) {
   HeatWs h;
-  const int tiles = (int)ceil_div64((int64_t)H * W, tile_px);
+  const int tiles = ceil_div(H, kPoolRows);   // bands
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 15) & ~size_t(15); return o; };
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
@@ -63,18 +65,22 @@ static HeatWs carve(void* ws, int M, int E, int H, int W, int max_n, int tile_px
 
 __global__ void __launch_bounds__(256) heat_stats_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag, int H, int W,
                                                          float* __restrict__ stats) {
+  // chunk = a band of rows; a thread walks columns x = tid, tid+256, ... so the ramp is evaluated once per column
   const int e = blockIdx.y, ch = blockIdx.x;
-  const size_t HW = (size_t)H * W;
-  const size_t per = (HW + kStatChunks - 1) / kStatChunks;
-  const size_t lo = (size_t)ch * per, hi = min(HW, lo + per);
-  const float* A = heat + (size_t)e * HW;
+  const int rows_per = (H + kStatChunks - 1) / kStatChunks;
+  const int r_lo = min(H, ch * rows_per), r_hi = min(H, r_lo + rows_per);   // trailing chunks may be empty
+  const float* A = heat + (size_t)e * H * W;
   const int dir = dirflag[e];
   float mn = INFINITY, mx = -INFINITY, s1 = 0.f, s0 = 0.f;
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float a = A[i];
-    const float rp = ramp_at(dir, (int)(i % W), W);
-    mn = fminf(mn, a); mx = fmaxf(mx, a);
-    s1 += a * rp; s0 += rp;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const float rp = ramp_at(dir, x, W);
+    float cs = 0.f;
+    for (int r = r_lo; r < r_hi; ++r) {
+      const float a = A[(size_t)r * W + x];
+      mn = fminf(mn, a); mx = fmaxf(mx, a);
+      cs += a;
+    }
+    s1 += cs * rp; s0 += rp * (float)(r_hi - r_lo);
   }
   __shared__ float red[4][8];
   mn = warp_min(mn); mx = warp_max(mx); s1 = warp_sum(s1); s0 = warp_sum(s0);
@@ -102,116 +108,121 @@ __device__ __forceinline__ void heat_consts(const float* stats, int e, size_t HW
   kk = (float)(1.0 / (range * mean));
 }
 
-template <int EB, int PX>
+template <int EB>
 __global__ void __launch_bounds__(kPoolWarps * 32) heat_pool_kernel(const float* __restrict__ heat, const int32_t* __restrict__ expr_off,
-                                                                    const int32_t* __restrict__ dirflag, const uint8_t* __restrict__ masks,
+                                                                    const int32_t* __restrict__ dirflag, const uint32_t* __restrict__ bits,
                                                                     const int32_t* __restrict__ mask_off, int M, int E, int H, int W, int max_n,
-                                                                    int nchunk, HeatWs ws) {
-  extern __shared__ float acc[];             // [kPoolWarps][nchunk][EB+1]  (last slot: area as int bits)
+                                                                    HeatWs ws) {
+  extern __shared__ __align__(16) float smf[];
+  // layout: cond [EB][bpx] conditioned heat of the band (zero beyond W) | wsum [EB][bwp] sum over each 32-pixel word | ramp [EB][W32]
   const size_t HW = (size_t)H * W;
-  const int tile = blockIdx.x, b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kWarpPx = 32 * PX;
-  const size_t px0 = ((size_t)tile * kPoolWarps + warp) * kWarpPx + (size_t)lane * PX;   // first pixel of this lane
+  const int WW = (W + 31) >> 5, W32 = WW * 32;
+  const int band = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int y0 = band * kPoolRows, rows = min(kPoolRows, H - y0);
+  const int bw = rows * WW;                          // words of one mask inside the band
+  const int bwp = kPoolRows * WW;                    // padded
+  const int bpx = bwp * 32;                          // padded pixels per expression plane
+  float* cond = smf;
+  float* wsum = cond + EB * bpx;
+  float* ramp = wsum + EB * bwp;
+  __shared__ float tot_s[kPoolWarps][8];
   int n_lo = 0, n_hi = M, e_lo = 0, e_hi = E;
   if (mask_off) { n_lo = mask_off[b]; n_hi = mask_off[b + 1]; }
   if (expr_off) { e_lo = expr_off[b]; e_hi = expr_off[b + 1]; }
   const int n_cnt = n_hi - n_lo;
-  const bool vec_ok = (HW % PX == 0) && ((reinterpret_cast<uintptr_t>(masks) & (PX - 1)) == 0);
+  constexpr int kMaxLoads = 4;                       // band words per lane (bw <= 128)
+  const int nloads = (bw + 31) >> 5;
 
-  for (int eg = e_lo; eg < e_hi; eg += EB) {       // groups of EB expressions (one pass over the masks per group)
+  for (int eg = e_lo; eg < e_hi; eg += EB) {       // groups of EB expressions (one pass over the packed masks per group)
     const int ne = min(EB, e_hi - eg);
-    float cond[EB][PX];
-    float tot[EB];
+    __syncthreads();
+    for (int t = tid; t < EB * W32; t += blockDim.x) {
+      const int j = t / W32, x = t - j * W32;
+      ramp[t] = (j < ne && x < W) ? ramp_at(dirflag[eg + j], x, W) : 0.f;
+    }
+    __syncthreads();
+    // conditioned heat of the band: A'' = (A - mn) * kk * ramp(x); one warp-task per (expression, word)
 #pragma unroll
     for (int j = 0; j < EB; ++j) {
-      tot[j] = 0.f;
       float mn = 0.f, kk = 0.f;
-      int dir = 0;
-      if (j < ne) { heat_consts(ws.stats, eg + j, HW, mn, kk); dir = dirflag[eg + j]; }
-#pragma unroll
-      for (int q = 0; q < PX; ++q) {
-        const size_t pidx = px0 + q;
+      if (j < ne) heat_consts(ws.stats, eg + j, HW, mn, kk);
+      float tot = 0.f;
+      for (int wd = warp; wd < bwp; wd += kPoolWarps) {
+        const int r = wd / WW, x = (wd - r * WW) * 32 + lane;
         float v = 0.f;
-        if (j < ne && pidx < HW) {
-          const float a = heat[(size_t)(eg + j) * HW + pidx];
-          v = (a - mn) * kk * ramp_at(dir, (int)(pidx % W), W);
-        }
-        cond[j][q] = v;
-        tot[j] += v;
+        if (j < ne && r < rows && x < W) v = (heat[(size_t)(eg + j) * HW + (size_t)(y0 + r) * W + x] - mn) * kk * ramp[j * W32 + x];
+        cond[j * bpx + wd * 32 + lane] = v;
+        const float s = warp_sum(v);
+        if (lane == 0) wsum[j * bwp + wd] = s;
+        tot += s;
       }
-      tot[j] = warp_sum(tot[j]);
+      if (lane == 0) tot_s[warp][j] = tot;
     }
-    // deterministic S_tot partial: warp slots in shared memory, summed by thread 0
     __syncthreads();
-    if (lane == 0)
-      for (int j = 0; j < EB; ++j) acc[warp * EB + j] = tot[j];
-    __syncthreads();
-    if (threadIdx.x < ne) {
+    if (tid < ne) {
       float s = 0.f;
-      for (int w = 0; w < kPoolWarps; ++w) s += acc[w * EB + threadIdx.x];
-      ws.part_tot[(size_t)tile * E + eg + threadIdx.x] = s;
+      for (int w = 0; w < kPoolWarps; ++w) s += tot_s[w][tid];
+      ws.part_tot[(size_t)band * E + eg + tid] = s;
     }
-    __syncthreads();
 
-    for (int c0 = 0; c0 < n_cnt; c0 += nchunk) {   // chunks of masks whose accumulators fit in shared memory
-      const int cn = min(nchunk, n_cnt - c0);
-#pragma unroll 2
-      for (int k = 0; k < cn; ++k) {
-        const uint8_t* mp = masks + (size_t)(n_lo + c0 + k) * HW + px0;
-        uint32_t w[PX / 4];
-        if (vec_ok && px0 + PX <= HW) {
-          if (PX == 16) {
-            const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(mp));
-            w[0] = v.x; w[1] = v.y; w[PX / 4 - 2] = v.z; w[PX / 4 - 1] = v.w;
-          } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(mp);
-            w[0] = v.x; w[1] = v.y;
-          }
-        } else {
+    // stream the masks of this image: warp per mask, the next mask's words are in flight while this one is reduced
+    uint32_t nxt[kMaxLoads];
+    auto fetch = [&](int k) {
+      const uint32_t* mb = bits + ((size_t)(n_lo + k) * H + y0) * WW;
 #pragma unroll
-          for (int q = 0; q < PX / 4; ++q) w[q] = 0;
+      for (int u = 0; u < kMaxLoads; ++u) nxt[u] = (u < nloads && u * 32 + lane < bw) ? __ldg(mb + u * 32 + lane) : 0u;
+    };
+    if (warp < n_cnt) fetch(warp);
+    for (int k = warp; k < n_cnt; k += kPoolWarps) {
+      uint32_t cur[kMaxLoads];
 #pragma unroll
-          for (int q = 0; q < PX; ++q)
-            if (px0 + q < HW) w[q >> 2] |= (uint32_t)(mp[q] != 0) << ((q & 3) * 8);
-        }
-        float s[EB];
+      for (int u = 0; u < kMaxLoads; ++u) cur[u] = nxt[u];
+      if (k + kPoolWarps < n_cnt) fetch(k + kPoolWarps);
+      float acc[EB];
 #pragma unroll
-        for (int j = 0; j < EB; ++j) s[j] = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < PX; ++q) {
-          const bool on = ((w[q >> 2] >> ((q & 3) * 8)) & 0xffu) != 0;
-          cnt += on;
-#pragma unroll
-          for (int j = 0; j < EB; ++j) s[j] += on ? cond[j][q] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < EB; ++j) s[j] = warp_sum(s[j]);
-        cnt = warp_sum_i(cnt);
+      for (int j = 0; j < EB; ++j) acc[j] = 0.f;
+      int cnt = 0;
+      if (__ballot_sync(0xffffffffu, (cur[0] | cur[1] | cur[2] | cur[3]) != 0u) == 0u) {   // the mask does not touch this band
         if (lane == 0) {
-          float* a = acc + ((size_t)warp * nchunk + k) * (EB + 1);
 #pragma unroll
-          for (int j = 0; j < EB; ++j) a[j] = s[j];
-          a[EB] = __int_as_float(cnt);
+          for (int j = 0; j < EB; ++j)
+            if (j < ne) ws.part_sin[((size_t)band * E + eg + j) * max_n + k] = 0.f;
+          if (eg == e_lo) ws.part_area[(size_t)band * M + n_lo + k] = 0;
         }
+        continue;
       }
-      __syncthreads();
-      for (int t = threadIdx.x; t < cn * (EB + 1); t += blockDim.x) {
-        const int k = t / (EB + 1), j = t - k * (EB + 1);
-        if (j < EB) {
-          if (j < ne) {
-            float s = 0.f;
-            for (int w2 = 0; w2 < kPoolWarps; ++w2) s += acc[((size_t)w2 * nchunk + k) * (EB + 1) + j];
-            ws.part_sin[((size_t)tile * E + eg + j) * max_n + c0 + k] = s;
+#pragma unroll
+      for (int u = 0; u < kMaxLoads; ++u) {
+        if (u < nloads) {
+          const uint32_t mine = cur[u];
+          cnt += __popc(mine);
+          if (mine == 0xffffffffu) {                      // whole word inside the mask: its precomputed sum
+#pragma unroll
+            for (int j = 0; j < EB; ++j) acc[j] += wsum[j * bwp + u * 32 + lane];
           }
-        } else if (eg == e_lo) {
-          int s = 0;
-          for (int w2 = 0; w2 < kPoolWarps; ++w2) s += __float_as_int(acc[((size_t)w2 * nchunk + k) * (EB + 1) + EB]);
-          ws.part_area[(size_t)tile * M + n_lo + c0 + k] = s;
+          uint32_t part = __ballot_sync(0xffffffffu, mine != 0u && mine != 0xffffffffu);
+          while (part) {                                  // words cut by the outline: all lanes, one pixel each
+            const int src = __ffs(part) - 1;
+            part &= part - 1;
+            const uint32_t word = __shfl_sync(0xffffffffu, mine, src);
+            if ((word >> lane) & 1u) {
+              const int o = (u * 32 + src) * 32 + lane;
+#pragma unroll
+              for (int j = 0; j < EB; ++j) acc[j] += cond[j * bpx + o];
+            }
+          }
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < EB; ++j) acc[j] = warp_sum(acc[j]);
+      cnt = warp_sum_i(cnt);
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < EB; ++j)
+          if (j < ne) ws.part_sin[((size_t)band * E + eg + j) * max_n + k] = acc[j];
+        if (eg == e_lo) ws.part_area[(size_t)band * M + n_lo + k] = cnt;
+      }
     }
   }
 }
@@ -241,60 +252,58 @@ __global__ void heat_finalize_kernel(const int32_t* __restrict__ expr_off, const
   score_gem[(size_t)e * max_n + n] = out;
 }
 
-template <int EB, int PX>
-static int launch_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const uint8_t* masks, const int32_t* mask_off,
+template <int EB>
+static int launch_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const uint32_t* bits, const int32_t* mask_off,
                        int B, int M, int E, int H, int W, int max_n, HeatWs ws, cudaStream_t st) {
-  int nchunk = max_n;
-  const size_t per = (size_t)kPoolWarps * (EB + 1) * 4;
-  if ((size_t)nchunk * per > 96 * 1024) nchunk = (int)(96 * 1024 / per);
-  size_t smem = std::max<size_t>((size_t)nchunk * per, (size_t)kPoolWarps * EB * 4);
-  auto kern = heat_pool_kernel<EB, PX>;
+  const int WW = (W + 31) >> 5;
+  const size_t smem = ((size_t)EB * kPoolRows * WW * 32 + (size_t)EB * kPoolRows * WW + (size_t)EB * WW * 32) * 4;
+  auto kern = heat_pool_kernel<EB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
   dim3 grid(ws.tiles, B);
-  kern<<<grid, kPoolWarps * 32, smem, st>>>(heat, expr_off, dirflag, masks, mask_off, M, E, H, W, max_n, nchunk, ws);
+  kern<<<grid, kPoolWarps * 32, smem, st>>>(heat, expr_off, dirflag, bits, mask_off, M, E, H, W, max_n, ws);
   return launch_status("hgl_heat_pool(pool)");
 }
-
-static int pool_px_for(int maxe) { return maxe <= 4 ? 16 : 8; }
 
 }  // namespace hgl
 
 // The expression-group width is picked from the average expressions per image (E/B); images with more run extra passes.
 static int hgl_pool_eb(int B, int E) {
   const int avg = (E + B - 1) / B;
-  return avg <= 1 ? 1 : (avg <= 2 ? 2 : (avg <= 3 ? 3 : (avg <= 4 ? 4 : 8)));
+  return avg <= 1 ? 1 : (avg <= 2 ? 2 : (avg <= 3 ? 3 : (avg <= 4 ? 4 : (avg <= 6 ? 6 : 8))));
 }
 
 extern "C" int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n) {
   using namespace hgl;
   if (B < 1 || M < 0 || E < 0 || H < 1 || W < 1 || max_n < 0) return -1;
-  const int px = pool_px_for(hgl_pool_eb(B, E));
-  return (int64_t)carve(nullptr, M, E, H, W, max_n, kPoolWarps * 32 * px).bytes + 256;
+  return (int64_t)carve(nullptr, M, E, H, W, max_n).bytes + 256;
 }
 
 extern "C" int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
-                             const uint8_t* masks, const int32_t* mask_off, int B, int M, int E, int H, int W,
+                             const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W,
                              int max_n, float* score_gem, void* workspace, void* stream) {
   using namespace hgl;
-  HGL_REQUIRE(heat && dirflag && black && masks && score_gem && workspace, "hgl_heat_pool: null pointer");
+  if (E == 0 || M == 0) return HGL_OK;
+  HGL_REQUIRE(heat && dirflag && black && bits && score_gem && workspace, "hgl_heat_pool: null pointer");
   HGL_REQUIRE(B >= 1 && M >= 0 && E >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_heat_pool: bad shape");
   HGL_REQUIRE((mask_off && expr_off) || B == 1, "hgl_heat_pool: mask_off/expr_off required when B > 1");
   HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hgl_heat_pool: workspace must be 16-byte aligned");
-  if (E == 0 || M == 0) return HGL_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int eb = hgl_pool_eb(B, E);
-  const int px = pool_px_for(eb);
-  HeatWs ws = carve(workspace, M, E, H, W, max_n, kPoolWarps * 32 * px);
+  int eb = hgl_pool_eb(B, E);
+  const int WW = (W + 31) >> 5;
+  while (eb > 1 && (size_t)eb * (kPoolRows + 2) * WW * 32 * 4 > 96 * 1024) --eb;   // wide frames: fewer expressions per pass
+  HGL_REQUIRE((size_t)eb * (kPoolRows + 2) * WW * 32 * 4 <= 200 * 1024 && kPoolRows * WW <= 128, "hgl_heat_pool: W=%d too wide", W);
+  HeatWs ws = carve(workspace, M, E, H, W, max_n);
   heat_stats_kernel<<<dim3(kStatChunks, E), 256, 0, st>>>(heat, dirflag, H, W, ws.stats);
   int rc = launch_status("hgl_heat_pool(stats)");
   if (rc != HGL_OK) return rc;
   switch (eb) {
-    case 1: rc = launch_pool<1, 16>(heat, expr_off, dirflag, masks, mask_off, B, M, E, H, W, max_n, ws, st); break;
-    case 2: rc = launch_pool<2, 16>(heat, expr_off, dirflag, masks, mask_off, B, M, E, H, W, max_n, ws, st); break;
-    case 3: rc = launch_pool<3, 16>(heat, expr_off, dirflag, masks, mask_off, B, M, E, H, W, max_n, ws, st); break;
-    case 4: rc = launch_pool<4, 16>(heat, expr_off, dirflag, masks, mask_off, B, M, E, H, W, max_n, ws, st); break;
-    default: rc = launch_pool<8, 8>(heat, expr_off, dirflag, masks, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    case 1: rc = launch_pool<1>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    case 2: rc = launch_pool<2>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    case 3: rc = launch_pool<3>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    case 4: rc = launch_pool<4>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    case 5: case 6: rc = launch_pool<6>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
+    default: rc = launch_pool<8>(heat, expr_off, dirflag, bits, mask_off, B, M, E, H, W, max_n, ws, st); break;
   }
   if (rc != HGL_OK) return rc;
   heat_finalize_kernel<<<dim3(ceil_div(max_n, 128), E), 128, 0, st>>>(expr_off, mask_off, black, B, M, E, H, W, max_n, ws, score_gem);

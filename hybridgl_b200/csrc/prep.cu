@@ -524,7 +524,7 @@ extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_
   int chunk = (int)std::min<size_t>(64, (40 * 1024) / per_mask_bytes);
   chunk = std::max(chunk, 1);
   const long slots = (long)sm_count() * 3;
-  while (chunk > 8 && (long)gx * B * ceil_div(per_image, chunk) < 6 * slots) chunk >>= 1;
+  while (chunk > 8 && (long)gx * B * ceil_div(per_image, chunk) < 3 * slots) chunk = (chunk * 3) / 4;
   if (const char* ov = getenv("HGL_PREP_CHUNK")) chunk = std::max(1, atoi(ov));   // tuning hook
   chunk = std::min(chunk, std::max(1, (int)((200 * 1024) / per_mask_bytes)));
   p.chunk = chunk;

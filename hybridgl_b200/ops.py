@@ -143,13 +143,23 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
 
 
 # ---- (a2)-(a4) ----------------------------------------------------------------------------------------
-def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area: bool = False):
-    """TF.resize(pred_masks.float(), (g, g)) model/backbone.py:160 -> f32 [M,g,g] (and int32 areas [M])."""
-    m = _mask_bytes(masks)
-    M, H, W = m.shape
-    grid = torch.empty((M, g, g), dtype=torch.float32, device=m.device)
-    area = torch.empty((M,), dtype=torch.int32, device=m.device) if want_area else None
-    check(_lib.load().hgl_mask_grid(m.data_ptr(), M, H, W, g, int(bool(antialias)), grid.data_ptr(), _ptr(area), _stream()),
+def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area: bool = False, width: Optional[int] = None):
+    """TF.resize(pred_masks.float(), (g, g)) model/backbone.py:160 -> f32 [M,g,g] (and int32 areas [M]).
+    `masks`: bool/u8 [M,H,W] (packed internally) or packed int32 [M,H,ceil(W/32)] together with `width`."""
+    if masks.dtype == torch.int32:
+        if width is None:
+            raise ValueError("width is required with packed masks")
+        bits = _req(masks, torch.int32, "bits", 3)
+        M, H, W = bits.shape[0], bits.shape[1], int(width)
+        if bits.shape[2] != (W + 31) // 32:
+            raise ValueError("packed masks do not match width")
+    else:
+        m = _mask_bytes(masks)
+        M, H, W = m.shape
+        bits = pack_masks(m)
+    grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
+    area = torch.empty((M,), dtype=torch.int32, device=bits.device) if want_area else None
+    check(_lib.load().hgl_mask_grid(bits.data_ptr(), M, H, W, g, int(bool(antialias)), grid.data_ptr(), _ptr(area), _stream()),
           "hgl_mask_grid")
     return (grid, area) if want_area else grid
 
@@ -201,9 +211,9 @@ def heat_pool(heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor, ma
     """Hybridgl_main.py:204-223: conditioned GEM heat-map pooled inside / outside every mask -> score_gem f32 [E,max_n]."""
     _req(heat, torch.float32, "heat", 3)
     E, H, W = heat.shape
-    m = _mask_bytes(masks)
+    m = _bits(masks)                      # byte masks are packed on the fly; packed int32 passes through
     M = m.shape[0]
-    if tuple(m.shape[1:]) != (H, W):
+    if tuple(m.shape[1:]) != (H, (W + 31) // 32):
         raise ValueError("masks and heat-map frames differ")
     _req(dirflag, torch.int32, "dirflag", 1)
     _req(black, torch.float32, "black", 1)

@@ -74,13 +74,13 @@ class ScoringPath:
         ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
                                 dtype=self.prep_dtype, out=(local, glob), workspace=pws)
         self._mark("prep")
-        grid, area = ops.masks_to_grid(masks, self.grid, antialias=self.antialias, want_area=True)
+        grid, area = ops.masks_to_grid(bits, self.grid, antialias=self.antialias, want_area=True, width=W)
         self._mark("grid")
         feats = batch["features"] if features is None else features
         E = batch["sent"].shape[0]
         need = lib.hgl_heat_pool_workspace_bytes(B, M, E, H, W, max_n)
         ws = self._get("heat_ws", (need,), torch.uint8)
-        score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], masks, moff, eoff, max_n, workspace=ws)
+        score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
         self._mark("heat_pool")
         res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
                                batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)

@@ -78,8 +78,8 @@ HGL_API int hgl_gaussian_blur15(const uint8_t* image, uint8_t* out, int B, int H
 /* ---- (a2) mask -> patch grid ------------------------------------------------------------------------
  * Replaces TF.resize(pred_masks.float(), (g,g)) model/backbone.py:160.  antialias=1 is torchvision>=0.17
  * behaviour (this container), antialias=0 the reference's pinned torchvision 0.15.2.
- * masks u8 [M,H,W] -> grid f32 [M,g,g]; area int32 [M] (pixel count of every mask; may be NULL). */
-HGL_API int hgl_mask_grid(const uint8_t* masks, int M, int H, int W, int g, int antialias,
+ * bits = packed masks [M,H,WW] -> grid f32 [M,g,g]; area int32 [M] (pixel count of every mask; may be NULL). */
+HGL_API int hgl_mask_grid(const uint32_t* bits, int M, int H, int W, int g, int antialias,
                   float* grid, int32_t* area, void* stream);
 
 /* ---- (a3) CLS-row attention mask --------------------------------------------------------------------
@@ -103,12 +103,12 @@ HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* g
  *   A' = minmax(A) * ramp(dirflag);  A'' = A' / mean(A');
  *   score_gem[e,n] = (2-black_e) * sum(A''*m_n)/area(m_n) - black_e * sum(A''*(1-m_n))/area(1-m_n)
  * heat f32 [E,H,W] (GEM map after T.Resize, Hybridgl_main.py:201); expr_off int32 [B+1] (NULL => B==1);
- * dirflag int32 [E]; black f32 [E]; masks u8 [M,H,W]; mask_off int32 [B+1] (NULL => B==1).
+ * dirflag int32 [E]; black f32 [E]; bits = packed masks [M,H,WW]; mask_off int32 [B+1] (NULL => B==1).
  * score_gem f32 [E, max_n] row e holds the n masks of its image (max_n = row stride).
  * workspace: hgl_heat_pool_workspace_bytes(...) bytes, zeroing not required. */
 HGL_API int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n);
 HGL_API int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
-                  const uint8_t* masks, const int32_t* mask_off, int B, int M, int E, int H, int W,
+                  const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W,
                   int max_n, float* score_gem, void* workspace, void* stream);
 
 /* ---- (a6)-(a9),(a12) scoring, spatial-relationship re-ranking, per-expression argmax ----------------
