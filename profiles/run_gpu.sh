@@ -1,0 +1,22 @@
+#!/bin/bash
+# One gpurun call = parity tests + bench + ncu launch list + ncu --set full of our kernels (1 GPU).
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash profiles/run_gpu.sh r1a'
+# Outputs land in gpurun_out/<tag>_*; summaries are copied into profiles/ by profiles/summarize.py (run here, no GPU).
+tag=${1:-run}
+out=gpurun_out
+KRE='prep_main|prep_setup|pack_masks|blur15|mask_grid|mask_area|heat_stats|heat_pool|heat_finalize|score_select|iou_kernel|iou_zero|mask_pool|token_mask|attn_'
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,memory.total --format=csv > $out/${tag}_gpu.csv 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
+tail -3 $out/${tag}_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
+tail -2 $out/${tag}_smoke.log
+timeout 400 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+cat $out/${tag}_bench.json
+# launch list (cold-cache, serialised: shares only)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$KRE" -c 66 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+# full sections for one step of our kernels (second pass over the path: skip the first step's launches)
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s ${NCU_SKIP:-11} -c ${NCU_COUNT:-11} -o $out/${tag}_prof -f \
+    python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ls -la $out | tail -12
