@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_PKG, "libhgl.so")
 
 HGL_F32, HGL_BF16 = 0, 1
 HGL_BG_BLUR, HGL_BG_BLACK = 0, 1
+HGL_LND, HGL_NLD = 0, 1
 REL_CODES = {"none": 0, "left": 1, "right": 2, "up": 3, "down": 4, "big": 5, "small": 6, "within": 7}
 DIR_CODES = {"none": 0, "left": 1, "right": 2, "middle": 3, "up": 4, "down": 5}
 
@@ -26,7 +27,7 @@ SIGNATURES = {
     "hgl_mask_grid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hgl_attn_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_attn_bias": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "hgl_token_mask_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_int,
+    "hgl_token_mask_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "hgl_heat_pool_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "hgl_heat_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -282,13 +282,15 @@ __global__ void attn_bias_kernel(const float* __restrict__ grid, int M, int L, f
 // (a4) out[l,m,:] = a * w(l,m) * src[l,m,:] + b * add[l,m,:]   (8 elements = 16 B (bf16) / 2x16 B (f32) per thread-iteration)
 template <bool kBF16>
 __global__ void __launch_bounds__(256) token_mask_fuse_kernel(const void* __restrict__ src_, const void* __restrict__ add_, const float* __restrict__ grid,
-                                                              float a, float b, int L1, int M, int D, void* __restrict__ out_) {
+                                                              float a, float b, int L1, int M, int D, int nld, void* __restrict__ out_) {
   const int L = L1 - 1;
   const int dv = D / 8;                       // vectors of 8 elements per token
   const size_t total = (size_t)L1 * M * dv;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
-    const size_t tok = v / dv;                // = l*M + m
-    const int l = (int)(tok / M), m = (int)(tok - (size_t)l * M);
+    const size_t tok = v / dv;                // = l*M + m (LND) or m*L1 + l (NLD)
+    int l, m;
+    if (nld) { m = (int)(tok / L1); l = (int)(tok - (size_t)m * L1); }
+    else { l = (int)(tok / M); m = (int)(tok - (size_t)l * M); }
     float w = a;
     if (grid != nullptr && l > 0) w = a * grid[(size_t)m * L + (l - 1)];
     float x[8], y[8];
@@ -384,19 +386,20 @@ extern "C" int hgl_attn_bias(const float* grid, int M, int L, float* bias, void*
 }
 
 extern "C" int hgl_token_mask_fuse(const void* src, const void* add, const float* grid, float a, float b, int L1, int M, int D,
-                                   int dtype, void* out, void* stream) {
+                                   int dtype, int layout, void* out, void* stream) {
   using namespace hgl;
   HGL_REQUIRE(src && out, "hgl_token_mask_fuse: null pointer");
   HGL_REQUIRE(L1 >= 2 && M >= 0 && D >= 8 && D % 8 == 0, "hgl_token_mask_fuse: bad shape L1=%d M=%d D=%d (D %% 8)", L1, M, D);
   HGL_REQUIRE(dtype == HGL_F32 || dtype == HGL_BF16, "hgl_token_mask_fuse: dtype %d", dtype);
+  HGL_REQUIRE(layout == HGL_LND || layout == HGL_NLD, "hgl_token_mask_fuse: layout %d", layout);
   HGL_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add)) & 15) == 0,
               "hgl_token_mask_fuse: tensors must be 16-byte aligned");
   if (M == 0) return HGL_OK;
   const size_t total = (size_t)L1 * M * (D / 8);
   const int blocks = (int)std::min<size_t>(ceil_div64((int64_t)total, 256), (size_t)sm_count() * 16);
   if (dtype == HGL_BF16)
-    token_mask_fuse_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, L1, M, D, out);
+    token_mask_fuse_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, L1, M, D, layout, out);
   else
-    token_mask_fuse_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, L1, M, D, out);
+    token_mask_fuse_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, L1, M, D, layout, out);
   return launch_status("hgl_token_mask_fuse");
 }

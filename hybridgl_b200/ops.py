@@ -185,10 +185,15 @@ def attn_key_bias(grid: torch.Tensor) -> torch.Tensor:
 
 
 def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Optional[torch.Tensor], a: float = 1.0,
-                    b: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = a * tokenmask(src, grid) + b * add on LND streams [L+1, M, D] (model/backbone.py:235-249, 216, 290-291)."""
+                    b: float = 1.0, out: Optional[torch.Tensor] = None, layout: str = "LND") -> torch.Tensor:
+    """out = a * tokenmask(src, grid) + b * add (model/backbone.py:235-249, 216, 290-291) on token streams laid out
+    [L+1, M, D] (layout="LND", the reference's) or [M, L+1, D] (layout="NLD", the B200 forward's)."""
     _req(src, (torch.float32, torch.bfloat16), "src", 3)
-    L1, M, D = src.shape
+    lay = {"LND": _lib.HGL_LND, "NLD": _lib.HGL_NLD}[layout]
+    if lay == _lib.HGL_LND:
+        L1, M, D = src.shape
+    else:
+        M, L1, D = src.shape
     if add is not None:
         _req(add, src.dtype, "add", 3)
         if add.shape != src.shape:
@@ -200,7 +205,7 @@ def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Option
     if out is None:
         out = torch.empty_like(src)
     check(_lib.load().hgl_token_mask_fuse(src.data_ptr(), _ptr(add), _ptr(grid), float(a), float(b), L1, M, D, _dt(src.dtype),
-                                          out.data_ptr(), _stream()), "hgl_token_mask_fuse")
+                                          lay, out.data_ptr(), _stream()), "hgl_token_mask_fuse")
     return out
 
 

@@ -39,6 +39,11 @@ extern "C" {
 #define HGL_F32 0
 #define HGL_BF16 1
 
+/* token-stream layouts: the reference keeps streams as [L+1, M, D] (LND, model/backbone.py:139); the B200 forward
+ * keeps them batch-first [M, L+1, D] (NLD) so that attention runs as one batched SDPA call */
+#define HGL_LND 0
+#define HGL_NLD 1
+
 /* background of the global view outside the mask (utils.py:292-345 apply_visual_prompts option set) */
 #define HGL_BG_BLUR 0     /* Gaussian-blurred frame  (Hybridgl_main.py:99-113; utils.py:306-320) */
 #define HGL_BG_BLACK 1    /* zeros                   (utils.py:336-341) */
@@ -94,9 +99,9 @@ HGL_API int hgl_attn_bias(const float* grid, int M, int L, float* bias, void* st
  * Replaces the permute/view/mul/cat chains model/backbone.py:235-249, 214-216, 275-291:
  *   out[l,m,:] = a * w(l,m) * src[l,m,:] + b * add[l,m,:],  w = 1 for l==0 (CLS) else grid[m,l-1]
  * grid NULL => w == 1 (plain a*src + b*add);  add NULL => b term dropped.
- * src/add/out [L+1, M, D] (LND) of dtype; grid f32 [M,L]. out may alias src or add. */
+ * src/add/out [L+1, M, D] (layout HGL_LND) or [M, L+1, D] (HGL_NLD) of dtype; grid f32 [M,L]. out may alias src or add. */
 HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* grid, float a, float b,
-                        int L1, int M, int D, int dtype, void* out, void* stream);
+                        int L1, int M, int D, int dtype, int layout, void* out, void* stream);
 
 /* ---- (a10)+(a11) heat-map conditioning and mask pooling ---------------------------------------------
  * Replaces Hybridgl_main.py:204-223 and gen_dir_mask utils.py:135-161:
