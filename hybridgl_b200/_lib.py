@@ -29,6 +29,7 @@ SIGNATURES = {
     "hgl_attn_bias": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hgl_token_mask_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
+    "hgl_dir_mask": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_heat_pool_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "hgl_heat_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_void_p, c_void_p, c_void_p]),

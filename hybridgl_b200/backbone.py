@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's hybrid CLIP wrapper (model/backbone.py) on top of libhgl.
+
+Same call surface as the reference class:
+
+    CLIPViTFM(model_name='ViT-B/16').forward(local_imgs, global_imgs, pred_masks, masking_block=None, fusion_mode='G2L')
+    CLIPViTFM.calculate_score(image_features, text_features)          (model/backbone.py:74-87)
+    CLIPViTFM.make_attn_mask(pred_masks, size=None)                   (model/backbone.py:108-115)
+
+What is B200-native here (the path's rows a2-a5 of SURVEY.md section 8):
+  * mask -> patch grid (model/backbone.py:160)              -> ops.masks_to_grid      (hgl_mask_grid, packed masks)
+  * CLS-row attention mask (model/backbone.py:108-115)      -> ops.attn_key_bias      (hgl_attn_bias): a [M, L+1] additive key
+    bias for the CLS query only.  The reference materialises N*heads*(L+1)^2 booleans (1.07 GB at ViT-L/14@336 with 200
+    masks) and nn.MultiheadAttention converts them to a float mask of the same shape; here every query row runs through
+    one unmasked SDPA call and only the CLS row is recomputed with the bias (identical result: only that row is masked).
+  * token masking + stream mixes (model/backbone.py:214-216, 235-249, 275-291) -> ops.token_mask_fuse (hgl_token_mask_fuse)
+    on batch-first [M, L+1, D] streams; the 2-4 streams of a fused block go through ONE resblock call (weights read once).
+The transformer blocks themselves are plain PyTorch with random-init weights of the named architecture (north_star):
+there is no checkpoint offline.  Parameter names follow CLIP's `visual.*` state_dict so real weights load unchanged.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+# name -> (embed_dim, image_resolution, layers, width, patch, heads); last_layer as in model/backbone.py:16-21
+# (ViT-L/14@336 is the SURVEY section 8(c) extension: last_layer=22, heads=16)
+ARCH = {
+    "ViT-B/32": dict(embed_dim=512, res=224, layers=12, width=768, patch=32, heads=12, last_layer=10),
+    "ViT-B/16": dict(embed_dim=512, res=224, layers=12, width=768, patch=16, heads=12, last_layer=10),
+    "ViT-L/14@336px": dict(embed_dim=768, res=336, layers=24, width=1024, patch=14, heads=16, last_layer=22),
+}
+
+
+class LayerNormF32(nn.LayerNorm):
+    """CLIP's LayerNorm: computed in fp32 whatever the stream dtype (third_party/modified_CLIP/clip/model.py:188-195)."""
+
+    def forward(self, x):
+        return F.layer_norm(x.float(), self.normalized_shape, self.weight.float(), self.bias.float(), self.eps).to(x.dtype)
+
+
+class _Attn(nn.Module):
+    """Parameter container with nn.MultiheadAttention's names (in_proj_weight, in_proj_bias, out_proj.*)."""
+
+    def __init__(self, width: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * width, width))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * width))
+        self.out_proj = nn.Linear(width, width)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+
+
+class ResBlock(nn.Module):
+    """x + MHA(ln_1(x)); x + mlp(ln_2(x))  (third_party/modified_CLIP/clip/model.py:244-257), batch-first.
+
+    `cls_bias` f32 [M, L+1] (0 / -inf) masks patch keys for the CLS query only -- the reference's attn_mask has no other
+    blocked entry."""
+
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.heads = heads
+        self.attn = _Attn(width)
+        self.ln_1 = LayerNormF32(width)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(width, 4 * width)), ("gelu", nn.Identity()),
+                                              ("c_proj", nn.Linear(4 * width, width))]))
+        self.ln_2 = LayerNormF32(width)
+
+    def attention(self, h: torch.Tensor, cls_bias: Optional[torch.Tensor]) -> torch.Tensor:
+        M, L1, D = h.shape
+        hd = D // self.heads
+        qkv = F.linear(h, self.attn.in_proj_weight, self.attn.in_proj_bias).view(M, L1, 3, self.heads, hd)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))             # [M, heads, L1, hd]
+        o = F.scaled_dot_product_attention(q, k, v)                             # every query row, unmasked
+        if cls_bias is not None:
+            s = torch.matmul(q[:, :, :1].float(), k.float().transpose(-1, -2)) / math.sqrt(hd)    # [M, heads, 1, L1]
+            s = s + cls_bias[:, None, None, :]
+            o0 = torch.matmul(torch.softmax(s, dim=-1).to(v.dtype), v)          # [M, heads, 1, hd]
+            o = torch.cat([o0, o[:, :, 1:]], dim=2)
+        return self.attn.out_proj(o.transpose(1, 2).reshape(M, L1, D))
+
+    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = x + self.attention(self.ln_1(x), cls_bias)
+        h = self.mlp.c_fc(self.ln_2(x))
+        h = h * torch.sigmoid(1.702 * h)                                        # QuickGELU
+        return x + self.mlp.c_proj(h)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, width, layers, heads):
+        super().__init__()
+        self.resblocks = nn.ModuleList([ResBlock(width, heads) for _ in range(layers)])
+
+
+class VisionTransformer(nn.Module):
+    """CLIP ViT with the state_dict layout of clip.model.VisionTransformer (conv1, class_embedding, positional_embedding,
+    ln_pre, transformer.resblocks.*, ln_post, proj)."""
+
+    def __init__(self, res, patch, width, layers, heads, out_dim):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch, stride=patch, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((res // patch) ** 2 + 1, width))
+        self.ln_pre = LayerNormF32(width)
+        self.transformer = _Transformer(width, layers, heads)
+        self.ln_post = LayerNormF32(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, out_dim))
+
+    def embed(self, imgs: torch.Tensor) -> torch.Tensor:
+        """conv1 + class token + positional embedding + ln_pre -> [M, L+1, D]  (model/backbone.py:130-137)."""
+        x = self.conv1(imgs.to(self.conv1.weight.dtype)).flatten(2).transpose(1, 2)
+        cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
+        return self.ln_pre(torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype))
+
+    def head(self, x: torch.Tensor) -> torch.Tensor:
+        """ln_post(CLS) @ proj  (model/backbone.py:254-258)."""
+        return self.ln_post(x[:, 0, :]) @ self.proj
+
+
+class _Clip(nn.Module):
+    """Only what the path touches of clip.model.CLIP: `visual` and `logit_scale` (text encoder: inputs of the path)."""
+
+    def __init__(self, a):
+        super().__init__()
+        self.visual = VisionTransformer(a["res"], a["patch"], a["width"], a["layers"], a["heads"], a["embed_dim"])
+        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))     # clip/model.py CLIP.__init__
+
+
+class CLIPViTFM(nn.Module):
+    """Drop-in for model/backbone.py::CLIPViTFM (random-init; `load_clip_state_dict` accepts real CLIP weights)."""
+
+    def __init__(self, model_name: str = "ViT-B/16", size: int = 224, arch: Optional[dict] = None, antialias: bool = True,
+                 device="cuda", dtype: torch.dtype = torch.float32):
+        super().__init__()
+        a = dict(ARCH[model_name]) if arch is None else dict(arch)
+        self.last_layer = a["last_layer"]
+        self.num_heads = a["heads"]
+        self.antialias = antialias          # TF.resize semantics of model/backbone.py:160
+        self.model = _Clip(a).to(device=device, dtype=dtype).eval()
+
+    @property
+    def device(self):
+        return self.model.visual.conv1.weight.device
+
+    @property
+    def dtype(self):
+        return self.model.visual.conv1.weight.dtype
+
+    def load_clip_state_dict(self, sd: dict) -> None:
+        """Load a CLIP state_dict (or just its visual.* part)."""
+        vis = {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")} or dict(sd)
+        self.model.visual.load_state_dict({k: torch.as_tensor(v) for k, v in vis.items()})
+        if "logit_scale" in sd:
+            with torch.no_grad():
+                self.model.logit_scale.copy_(torch.as_tensor(sd["logit_scale"]))
+
+    # ---- model/backbone.py:74-87 -----------------------------------------------------------------------------------
+    def calculate_score(self, image_features: torch.Tensor, text_features: torch.Tensor, visual_norm_dim: int = 1) -> torch.Tensor:
+        """logit_scale.exp() * normalize(img) @ normalize(txt).T -> [N, T]; runs in hgl_score_select (scores only)."""
+        if visual_norm_dim != 1:
+            raise ValueError("only visual_norm_dim=1 (the reference's call sites) is supported")
+        T = text_features.shape[0]
+        feat = image_features.contiguous()
+        txt = text_features.float().contiguous()
+        N = feat.shape[0]
+        dev = feat.device
+        zero_off = torch.zeros(T + 1, dtype=torch.int32, device=dev)
+        # one 'expression' per text row: r=1 takes the sentence vector alone
+        res = ops.score_select(feat, txt, txt, torch.zeros((0, feat.shape[1]), device=dev), zero_off,
+                               torch.zeros((N, 4), dtype=torch.int64, device=dev), torch.zeros(T, dtype=torch.int32, device=dev),
+                               None, logit_scale_exp=float(self.model.logit_scale.exp()), r=1.0, alpha=0.0)
+        return res["score_clip"][:, :N].t().contiguous()
+
+    # ---- model/backbone.py:108-115 ---------------------------------------------------------------------------------
+    def make_attn_mask(self, pred_masks: torch.Tensor, size: Optional[int] = None) -> torch.Tensor:
+        """grid masks [N,g,g] (float) -> bool [N*heads, L+1, L+1], True = blocked.  Kept for drop-in use; forward() uses
+        the compact CLS-row bias instead."""
+        if size is not None:
+            pred_masks = ops.masks_to_grid(pred_masks.to(torch.bool) if pred_masks.dtype != torch.bool else pred_masks, size,
+                                           antialias=self.antialias)
+        return ops.make_attn_mask(pred_masks.float().contiguous(), self.num_heads)
+
+    # ---- model/backbone.py:117-309 ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, local_imgs, global_imgs, pred_masks, masking_block: Optional[int] = None, fusion_mode: str = "G2L"):
+        if masking_block is None:
+            masking_block = self.last_layer
+        vit = self.model.visual
+        blocks = vit.transformer.resblocks
+        x = vit.embed(local_imgs)                                                 # local stream  [M, L+1, D]
+        if fusion_mode == "crop":                                                 # model/backbone.py:126-128
+            for blk in blocks:
+                x = blk(x)
+            return vit.head(x)
+        x2 = vit.embed(global_imgs) if global_imgs is not None else None          # global stream
+        M, L1, D = x.shape
+        g = int(math.isqrt(L1 - 1))
+        assert g * g == L1 - 1
+        grid = ops.masks_to_grid(pred_masks, g, antialias=self.antialias)         # model/backbone.py:160
+        N = grid.shape[0]
+        final = self.last_layer + 1
+
+        if fusion_mode == "token_masking":                                        # model/backbone.py:161-184
+            for i, blk in enumerate(blocks):
+                if i >= masking_block:
+                    if x.shape[0] != N:
+                        x = x.expand(N, -1, -1).contiguous()
+                    x = blk(ops.token_mask_fuse(x, None, grid, 1.0, 0.0, layout="NLD"))
+                    if i == final:
+                        return vit.head(x)
+                else:
+                    x = blk(x)
+            return x.transpose(0, 1)
+
+        bias = ops.attn_key_bias(grid)                                            # [N, L+1], 0 / -inf
+        if fusion_mode == "attn_masking":                                         # model/backbone.py:186-203
+            for i, blk in enumerate(blocks):
+                if i >= masking_block:
+                    if i == masking_block and x.shape[0] != N:
+                        x = x.expand(N, -1, -1).contiguous()
+                    x = blk(x, bias)
+                    if i == self.last_layer:
+                        return vit.head(x)
+                else:
+                    x = blk(x)
+            return x.transpose(0, 1)
+
+        if fusion_mode not in ("L2G", "G2L", "G2L&L2G"):
+            return x.transpose(0, 1)                                              # model/backbone.py:309 (LND like the reference)
+
+        zero = torch.zeros_like(bias)
+        both = torch.cat([x, x2], dim=0)                                          # blocks < masking_block: both streams, one call
+        xhl = xhg = None
+        for i, blk in enumerate(blocks):
+            if i < masking_block:
+                both = blk(both)
+                continue
+            if i == masking_block:
+                x, x2 = both[:N], both[N:]
+                if fusion_mode == "G2L&L2G":
+                    xhl, xhg = x, x2
+            if fusion_mode == "G2L":                                              # model/backbone.py:227-260
+                mixed = ops.token_mask_fuse(x2, x, grid, 2.0, 1.0, layout="NLD")  # 2*tokenmask(x2) + x
+                out = blk(torch.cat([mixed, x2], dim=0), torch.cat([zero, bias], dim=0))
+                x, x2 = out[:N], out[N:]
+                result = x
+            elif fusion_mode == "L2G":                                            # model/backbone.py:206-225
+                mixed = ops.token_mask_fuse(x2, x, None, 2.0, 1.0, layout="NLD")  # x_old + 2*x2
+                out = blk(torch.cat([x, mixed], dim=0), torch.cat([zero, bias], dim=0))
+                x, x2 = out[:N], out[N:]
+                result = x2
+            else:                                                                 # model/backbone.py:262-306
+                mixl = ops.token_mask_fuse(x2, xhl, grid, 2.0, 1.0, layout="NLD")   # xhl + 2*tokenmask(x2)
+                mixg = ops.token_mask_fuse(xhg, x, None, 2.0, 1.0, layout="NLD")    # x + 2*xhg
+                out = blk(torch.cat([x, x2, mixl, mixg], dim=0), torch.cat([zero, bias, zero, bias], dim=0))
+                x, x2, xhl, xhg = out[:N], out[N:2 * N], out[2 * N:3 * N], out[3 * N:]
+                result = None
+            if i == final:
+                if fusion_mode == "G2L&L2G":
+                    return vit.head(xhl) + vit.head(xhg)
+                return vit.head(result)
+        return x.transpose(0, 1)

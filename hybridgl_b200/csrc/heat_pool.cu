@@ -39,6 +39,13 @@ __device__ __forceinline__ float ramp_at(int dirflag, int x, int W) {
   return 1.f;
 }
 
+// gen_dir_mask utils.py:135-161 as a tensor (the drop-in form; the pooling kernels evaluate the ramp on the fly)
+__global__ void dir_mask_kernel(int dirflag, int H, int W, float* __restrict__ out) {
+  const size_t total = (size_t)H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = ramp_at(dirflag, (int)(i % W), W);
+}
+
 struct HeatWs {            // workspace carve-up (all offsets in bytes, 16-aligned)
   float* stats;            // [E][kStatChunks][4]  min, max, sum(A*ramp), sum(ramp)
   float* part_sin;         // [tiles][E][max_n]
@@ -271,6 +278,15 @@ static int launch_pool(const float* heat, const int32_t* expr_off, const int32_t
 static int hgl_pool_eb(int B, int E) {
   const int avg = (E + B - 1) / B;
   return avg <= 1 ? 1 : (avg <= 2 ? 2 : (avg <= 3 ? 3 : (avg <= 4 ? 4 : (avg <= 6 ? 6 : 8))));
+}
+
+extern "C" int hgl_dir_mask(int dirflag, int H, int W, float* out, void* stream) {
+  using namespace hgl;
+  HGL_REQUIRE(out, "hgl_dir_mask: null pointer");
+  HGL_REQUIRE(H >= 1 && W >= 1, "hgl_dir_mask: bad shape");
+  const int blocks = (int)std::min<size_t>(((size_t)H * W + 255) / 256, (size_t)sm_count() * 8);
+  dir_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dirflag, H, W, out);
+  return launch_status("hgl_dir_mask");
 }
 
 extern "C" int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n) {

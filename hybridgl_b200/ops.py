@@ -210,6 +210,15 @@ def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Option
 
 
 # ---- (a10)+(a11) --------------------------------------------------------------------------------------
+def dir_mask(dirflag: str, height: int, width: int, device=None) -> torch.Tensor:
+    """gen_dir_mask utils.py:135-161 -> f32 [H,W] on the GPU."""
+    out = torch.empty((height, width), dtype=torch.float32, device=device if device is not None else "cuda")
+    if not out.is_cuda:
+        raise TypeError("dir_mask: expected a CUDA device (no CPU fallback)")
+    check(_lib.load().hgl_dir_mask(DIR_CODES.get(dirflag, 0), height, width, out.data_ptr(), _stream()), "hgl_dir_mask")
+    return out
+
+
 def heat_pool(heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor, masks: torch.Tensor,
               mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:

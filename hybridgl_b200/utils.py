@@ -1,0 +1,68 @@
+"""Host-side mirror of the three path functions of the reference's utils.py, same names / arguments / returns:
+
+    relation_boxes(boxi, boxj, scorei, scorej, relaword)                utils.py:240-268
+    gen_dir_mask(dirflag, height, width, device)                        utils.py:135-161
+    Compute_IoU(pred, target, cum_I, cum_U, mean_IoU=[])                utils.py:365-384
+
+They exist so that Hybridgl_main.py can switch imports without touching its call sites.  The batched path
+(pipeline.ScoringPath) does not use them: it evaluates the same formulas inside hgl_score_select / hgl_heat_pool /
+hgl_iou for all expressions at once.  gen_dir_mask and Compute_IoU run on the GPU through libhgl; relation_boxes is
+a handful of scalar comparisons on host-visible values (it is host code in the reference too).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_REL = ("none", "left", "right", "up", "down", "big", "small", "within")
+
+
+def relation_boxes(boxi, boxj, scorei, scorej, relaword):
+    """Pairwise spatial-relationship score of two XYWH boxes (centres are x+w/2, y+h/2).  'none' and unknown words
+    return scorei unchanged; every other word gates scorei*scorej by a comparison, 'within' scales it by the
+    overlap area over the area of box i."""
+    if relaword not in _REL or relaword == "none":
+        return scorei
+    xi, yi, wi, hi = boxi[0], boxi[1], boxi[2], boxi[3]
+    xj, yj, wj, hj = boxj[0], boxj[1], boxj[2], boxj[3]
+    pair = scorei * scorej
+    if relaword in ("left", "right"):
+        ci, cj = xi + wi / 2, xj + wj / 2
+        return pair * ((ci < cj) if relaword == "left" else (ci > cj))
+    if relaword in ("up", "down"):
+        ci, cj = yi + hi / 2, yj + hj / 2
+        return pair * ((ci < cj) if relaword == "up" else (ci > cj))
+    if relaword in ("big", "small"):
+        ai, aj = wi * hi, wj * hj
+        return pair * ((ai > aj) if relaword == "big" else (ai < aj))
+    left = max(xi, xj)
+    right = max(left, min(xi + wi, xj + wj))
+    top = max(yi, yj)
+    bottom = max(top, min(yi + hi, yj + hj))
+    return pair * (right - left) * (bottom - top) / (wi * hi)
+
+
+def gen_dir_mask(dirflag, height, width, device):
+    """Horizontal position ramp [H,W] (left 1->0, right 0->1, middle 0->1->0; up/down/none are all-ones exactly as in the
+    reference, whose vertical ramps are commented out).  `device` falsy -> current CUDA device."""
+    return ops.dir_mask(dirflag, int(height), int(width), device if device else "cuda")
+
+
+def Compute_IoU(pred, target, cum_I, cum_U, mean_IoU=None):
+    """I = |pred & target|, U = |pred | target| as exact integers (hgl_iou), this_iou = I/U (0.0 when U == 0).
+    Returns (this_iou, mean_IoU, cum_I, cum_U) like the reference; cum_I / cum_U may be ints or tensors."""
+    if mean_IoU is None:
+        mean_IoU = []
+    if target.dim() == 3:
+        target = target[0]
+    p = pred.to(torch.bool) if pred.dtype not in (torch.bool, torch.uint8) else pred
+    t = target.to(torch.bool) if target.dtype not in (torch.bool, torch.uint8) else target
+    zero = torch.zeros(1, dtype=torch.int64, device=p.device)
+    iu = ops.iou_accumulate(p.contiguous()[None], t.contiguous(), zero, zero, None)
+    I, U = iu[0, 0], iu[0, 1]
+    this_iou = 0.0 if int(U) == 0 else I * 1.0 / U          # the reference's `if U == 0` is the same host sync
+    cum_I = cum_I + I
+    cum_U = cum_U + U
+    mean_IoU.append(this_iou)
+    return this_iou, mean_IoU, cum_I, cum_U

@@ -111,6 +111,8 @@ HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* g
  * dirflag int32 [E]; black f32 [E]; bits = packed masks [M,H,WW]; mask_off int32 [B+1] (NULL => B==1).
  * score_gem f32 [E, max_n] row e holds the n masks of its image (max_n = row stride).
  * workspace: hgl_heat_pool_workspace_bytes(...) bytes, zeroing not required. */
+/* gen_dir_mask utils.py:135-161 as a tensor: out f32 [H,W] (left: 1->0, right: 0->1, middle: 0->1->0, others: ones) */
+HGL_API int hgl_dir_mask(int dirflag, int H, int W, float* out, void* stream);
 HGL_API int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n);
 HGL_API int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
                   const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W,

@@ -1,0 +1,104 @@
+"""GPU parity of the host-side mirrors (hybridgl_b200/backbone.py, hybridgl_b200/utils.py) against outputs recorded from
+the reference's own CLIPViTFM.forward / calculate_score / relation_boxes / gen_dir_mask / Compute_IoU
+(tests/golden/forward.npz, misc.npz, scoring.npz -- produced by tests/golden/gen_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unpack_masks
+from oracle import hybridgl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TINY = dict(embed_dim=32, res=64, layers=4, width=64, patch=16, heads=1, last_layer=2)   # gen_golden.make_model
+
+
+@pytest.fixture(scope="module")
+def model(golden):
+    from hybridgl_b200.backbone import CLIPViTFM
+    g = golden("forward")
+    torch.backends.cudnn.allow_tf32 = False          # fp32 parity: no TF32 in conv1 / matmuls
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = CLIPViTFM(arch=TINY, device=DEV)
+    sd = {k[2:]: g[k] for k in g.files if k.startswith("w/")}
+    m.load_clip_state_dict(sd)
+    with torch.no_grad():
+        m.model.logit_scale.copy_(torch.as_tensor(g["logit_scale"]))
+    return m
+
+
+@pytest.mark.parametrize("mode", ["G2L", "L2G", "G2L&L2G", "token_masking", "attn_masking", "crop"])
+def test_forward_matches_reference(model, golden, mode):
+    g = golden("forward")
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    y = model(cu(g["local"]), cu(g["global"]), cu(g["masks"]), masking_block=1, fusion_mode=mode)
+    ref = g["out/" + mode]
+    assert tuple(y.shape) == ref.shape
+    # fp32 backbone on the GPU (TF32 off) vs the reference's CPU fp32: tolerance 2e-4 abs on O(1) features
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref, rtol=2e-3, atol=2e-4)
+
+
+def test_calculate_score_matches_reference(model, golden):
+    g = golden("forward")
+    feat = torch.from_numpy(g["out/G2L"]).to(DEV)
+    txt = torch.from_numpy(g["score_text"]).to(DEV)
+    got = model.calculate_score(feat, txt).cpu().numpy()
+    np.testing.assert_allclose(got, g["score"], rtol=1e-3, atol=1e-4)      # north-star tolerance: 1e-3 relative
+
+
+def test_make_attn_mask_dropin(model, golden):
+    g = golden("grid")
+    grid = torch.from_numpy(g["d_aa"]).to(DEV)
+    model.num_heads, keep = 3, model.num_heads
+    try:
+        am = model.make_attn_mask(grid).cpu().numpy()
+    finally:
+        model.num_heads = keep
+    assert np.array_equal(am[:, 0, :], g["d_attn_row0"]) and not am[:, 1:, :].any()
+
+
+def test_cls_bias_attention_equals_full_mask(model):
+    """The compact CLS-row bias must reproduce nn.MultiheadAttention with the reference's full boolean mask."""
+    torch.manual_seed(0)
+    blk = model.model.visual.transformer.resblocks[1]
+    M, L1, D = 6, 17, 64
+    x = torch.randn(M, L1, D, device=DEV)
+    grid = torch.rand(M, 4, 4, device=DEV); grid[grid < 0.5] = 0
+    from hybridgl_b200 import ops
+    bias = ops.attn_key_bias(grid)
+    full = ops.make_attn_mask(grid, 1)                                    # [M*1, L1, L1] True = blocked
+    mha = torch.nn.MultiheadAttention(D, 1).to(DEV)
+    with torch.no_grad():
+        mha.in_proj_weight.copy_(blk.attn.in_proj_weight); mha.in_proj_bias.copy_(blk.attn.in_proj_bias)
+        mha.out_proj.weight.copy_(blk.attn.out_proj.weight); mha.out_proj.bias.copy_(blk.attn.out_proj.bias)
+        h = blk.ln_1(x)
+        ref = mha(h.transpose(0, 1), h.transpose(0, 1), h.transpose(0, 1), need_weights=False, attn_mask=full)[0].transpose(0, 1)
+        got = blk.attention(h, bias)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_utils_mirror(golden):
+    from hybridgl_b200 import utils as U
+    g = golden("misc")
+    for key in g.files:
+        if key.startswith("dir_"):
+            _, d, hw = key.split("_")
+            h, w = map(int, hw.split("x"))
+            got = U.gen_dir_mask(d, h, w, DEV).cpu().numpy()
+            assert np.array_equal(got, g[key]), key                         # bit-exact ramp (ATen linspace restated)
+    for bi, bj, si, sj, word, ref in zip(g["rel_bi"], g["rel_bj"], g["rel_si"], g["rel_sj"], g["rel_word"], g["rel_out"]):
+        v = U.relation_boxes(torch.from_numpy(bi), torch.from_numpy(bj), torch.tensor(si), torch.tensor(sj), str(word))
+        np.testing.assert_allclose(float(v), ref, rtol=2e-7, atol=0)
+    s = golden("scoring")
+    for ci in (0, 7, 26):
+        p = f"c{ci:02d}_"
+        _, h, w, n, _ = s[p + "meta"].tolist()
+        masks = unpack_masks(s[p + "masks"], w); target = unpack_masks(s[p + "target"], w)
+        cum_I, cum_U, lst = 0, 0, []
+        for pick, (ri, ru) in zip((int(s[p + "idx_hybrid"]), int(s[p + "idx_final"])), (s[p + "IU"][:2], s[p + "IU"][2:])):
+            iou, lst, ci_, cu_ = U.Compute_IoU(torch.from_numpy(masks[pick]).to(DEV), torch.from_numpy(target.astype(np.uint8))[None].to(DEV), 0, 0, lst)
+            assert [int(ci_), int(cu_)] == [int(ri), int(ru)]
+            i0, u0, ref_iou = O.compute_iou(masks[pick], target)
+            assert abs(float(iou) - ref_iou) < 1e-6
+        assert len(lst) == 2
