@@ -185,8 +185,8 @@ def algorithmic_bytes(cfg, B, prep_bytes):
         "blur": 2 * B * H * W * 3,
         "pack": M * H * W + M * H * ((W + 31) // 32) * 4,
         "prep": M * H * ((W + 31) // 32) * 4 + 2 * B * H * W * 3 + 2 * M * 3 * S * S * prep_bytes,
-        "grid": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4,
-        "heat_pool": M * H * ((W + 31) // 32) * 4 + 2 * ET * H * W * 4 + ET * N * 4,
+        # one pass over the packed masks (grid + pooling) + the heat-maps once (+ their row-prefix tables written once)
+        "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + 2 * ET * H * W * 4 + ET * N * 4,
         "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
         "iou": 2 * 2 * ET * H * W,
     }

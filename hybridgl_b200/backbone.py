@@ -174,7 +174,7 @@ class CLIPViTFM(nn.Module):
         # one 'expression' per text row: r=1 takes the sentence vector alone
         res = ops.score_select(feat, txt, txt, torch.zeros((0, feat.shape[1]), device=dev), zero_off,
                                torch.zeros((N, 4), dtype=torch.int64, device=dev), torch.zeros(T, dtype=torch.int32, device=dev),
-                               None, logit_scale_exp=float(self.model.logit_scale.exp()), r=1.0, alpha=0.0)
+                               None, logit_scale_exp=float(self.model.logit_scale.detach().exp()), r=1.0, alpha=0.0)
         return res["score_clip"][:, :N].t().contiguous()
 
     # ---- model/backbone.py:108-115 ---------------------------------------------------------------------------------

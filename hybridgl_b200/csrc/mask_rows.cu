@@ -1,0 +1,675 @@
+// (a2) mask -> patch grid (antialiased)  and  (a10)+(a11) heat-map conditioning + per-mask pooling, in ONE pass over the
+// packed masks.
+//
+//   (a2)   model/backbone.py:160   TF.resize(pred_masks.float(), (g,g)) under torchvision >= 0.17: ATen
+//          _upsample_bilinear2d_aa = separable triangle filter, horizontal pass then vertical pass.
+//   (a10)  Hybridgl_main.py:204-209, utils.py:135-161   A' = minmax(A) * ramp(dirflag);  A'' = A' / mean(A')
+//   (a11)  Hybridgl_main.py:211-223   score_gem[n] = (2-black) * sum(A''*m_n)/|m_n|  -  black * sum(A''*(1-m_n)) / |1-m_n|
+// The reference loops over masks in Python (~8 full-frame kernels + a D2H sync per mask) and resamples every mask pixel.
+//
+// B200 design -- everything is expressed on the RUNS of a packed bit row (SAM proposals are blobs: one or two runs per
+// row), so a row costs O(#runs) instead of O(W):
+//   * horizontal filter sum of bin gx over a run [s,e)   =  P_gx(e) - P_gx(s)      P_gx = prefix sum of the filter taps
+//   * heat-map sum over the same run                     =  C_e[y][e] - C_e[y][s]  C_e  = row prefix sum of A*ramp
+//   * area                                               =  popcount
+// heat_prefix_kernel builds C_e (and the row min / max / sum that give min-max and mean) in one coalesced pass over the
+// heat-maps; heat_consts_kernel folds them into (min, 1/(range*mean), sum A'') per expression; mask_rows_kernel then
+// streams the packed masks: a WARP owns a band of rows of one mask and one LANE owns a bit row (16-byte loads straight
+// from global memory, no staging, no CTA barrier in the hot loop), 32 rows at a time.  While the words of a row are in
+// registers the lane only records which words contain a 0<->1 transition; the run logic then touches just those (two per
+// row for a blob).  After every 32-row block the warp folds the rows' horizontal sums into the <= 4 vertical bins they
+// feed (ascending row order).  Bands are independent tasks; the LAST band of a mask to finish (atomic ticket after a
+// __threadfence) adds the four partial results in a fixed order, so results are bit-reproducible from run to run.
+#include "hgl_common.cuh"
+
+namespace hgl {
+
+constexpr int kMaxG = 32;          // grid side limit (14 for ViT-B/16, 24 for ViT-L/14@336)
+constexpr int kRowsThreads = 256;  // one thread per bit row of a 256-row tile
+constexpr int kEB = 4;             // expressions pooled per pass over a mask
+constexpr int kPrefWarps = 8;
+
+// ---- shared with heat conditioning -----------------------------------------------------------------------------------
+__device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {  // ATen linspace (float): both-ends evaluation
+  if (n <= 1) return a;
+  const float step = __fdiv_rn(__fsub_rn(b, a), (float)(n - 1));
+  return (i < n / 2) ? __fmaf_rn(step, (float)i, a) : __fmaf_rn(-step, (float)(n - 1 - i), b);
+}
+// gen_dir_mask utils.py:135-161 (up/down/none are all-ones: the vertical ramps are commented out in the reference)
+__device__ __forceinline__ float ramp_at(int dirflag, int x, int W) {
+  if (dirflag == HGL_DIR_LEFT) return linspace_at(1.f, 0.f, W, x);
+  if (dirflag == HGL_DIR_RIGHT) return linspace_at(0.f, 1.f, W, x);
+  if (dirflag == HGL_DIR_MIDDLE) {
+    const int h = W / 2;
+    return (x < h) ? linspace_at(0.f, 1.f, h, x) : linspace_at(1.f, 0.f, W - h, x - h);
+  }
+  return 1.f;
+}
+
+// gen_dir_mask as a tensor (the drop-in form; the pooling path never materialises it)
+__global__ void dir_mask_kernel(int dirflag, int H, int W, float* __restrict__ out) {
+  const size_t total = (size_t)H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = ramp_at(dirflag, (int)(i % W), W);
+}
+
+// ATen _compute_indices_min_size_weights_aa for the triangle (bilinear) filter; one thread per output index.
+__device__ void aa_fill(int i, int in_size, int out_size, int maxk, int* xmin_out, int* xsize_out, float* w) {
+  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+  float support, invscale;
+  if (scale >= 1.f) { support = scale; invscale = __fdiv_rn(1.f, scale); } else { support = 1.f; invscale = 1.f; }
+  const float center = (float)((double)scale * ((double)i + 0.5));
+  int xmin = (int)((double)__fsub_rn(center, support) + 0.5);
+  xmin = max(xmin, 0);
+  int xsize = min((int)((double)__fadd_rn(center, support) + 0.5), in_size) - xmin;
+  xsize = max(min(xsize, maxk), 0);
+  float total = 0.f;
+  for (int j = 0; j < xsize; ++j) {
+    float t = (float)(((double)__fsub_rn((float)(j + xmin), center) + 0.5) * (double)invscale);
+    t = fabsf(t);
+    const float wt = (t < 1.f) ? __fsub_rn(1.f, t) : 0.f;
+    w[j] = wt;
+    total = __fadd_rn(total, wt);
+  }
+  if (total != 0.f)
+    for (int j = 0; j < xsize; ++j) w[j] = __fdiv_rn(w[j], total);
+  for (int j = xsize; j < maxk; ++j) w[j] = 0.f;
+  *xmin_out = xmin; *xsize_out = xsize;
+}
+
+static int aa_maxk(int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.f ? scale : 1.f;
+  return (int)ceilf(support) * 2 + 1;
+}
+
+// ---- heat-map prefix tables -------------------------------------------------------------------------------------------
+struct HeatWs {            // workspace carve-up (byte offsets 256-aligned)
+  float* cr;               // [E][H][Wp]   cr[y][x] = sum_{x' < x} A[y][x'] * ramp(x'),  x in [0, W]
+  float* rp;               // [E][Wp]      rp[x]    = sum_{x' < x} ramp(x')
+  float* rowstat;          // [E][H][4]    min A, max A, cr[y][W], -
+  float* consts;           // [E][4]       min A, kk = 1/(range*mean A'), sum A'' , -
+  int Wp;
+  size_t bytes;
+};
+
+static HeatWs heat_carve(void* ws, int E, int H, int W) {
+  HeatWs h;
+  h.Wp = (W + 1 + 3) & ~3;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~size_t(255); return o; };
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  h.cr = reinterpret_cast<float*>(base + take((size_t)E * H * h.Wp * 4));
+  h.rp = reinterpret_cast<float*>(base + take((size_t)E * h.Wp * 4));
+  h.rowstat = reinterpret_cast<float*>(base + take((size_t)E * H * 4 * 4));
+  h.consts = reinterpret_cast<float*>(base + take((size_t)E * 4 * 4));
+  h.bytes = off;
+  return h;
+}
+
+// One warp per (expression, row): coalesced load into shared memory, each lane scans its own contiguous chunk, one
+// warp scan of the 32 chunk totals, coalesced store of the exclusive prefix.  Row 0's warp also emits the ramp prefix.
+// The ramp row is evaluated once per CTA (shared memory); the lane -> (chunk, offset) map is advanced incrementally.
+__global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag,
+                                                                      int H, int W, int Wp, float* __restrict__ cr, float* __restrict__ rp,
+                                                                      float* __restrict__ rowstat) {
+  extern __shared__ float smp[];
+  const int e = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (W + 31) >> 5;                      // elements per lane chunk
+  const int stride = c | 1;                         // odd: lane-chunk walks are bank-conflict free
+  float* ramp = smp;                                // [32*c]
+  float* buf = smp + 32 * c + (size_t)warp * 32 * stride;
+  const int dir = dirflag[e];
+  for (int x = threadIdx.x; x < 32 * c; x += blockDim.x) ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
+  __syncthreads();
+  const int y = blockIdx.x * kPrefWarps + warp;
+  if (y >= H) return;                               // whole warp; no block-level barrier below
+  const float* A = heat + ((size_t)e * H + y) * W;
+  const int dq = 32 / c, dr = 32 - dq * c;          // x += 32  ==>  (q, r) += (dq, dr) with carry
+  const int q0 = lane / c, r0 = lane - q0 * c;
+  for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
+    float mn = INFINITY, mx = -INFINITY;
+    int q = q0, r = r0;
+    for (int x = lane; x < 32 * c; x += 32) {
+      float v = 0.f;
+      if (x < W) {
+        if (pass == 0) v = ramp[x];
+        else { const float a = __ldg(A + x); mn = fminf(mn, a); mx = fmaxf(mx, a); v = __fmul_rn(a, ramp[x]); }
+      }
+      buf[q * stride + r] = v;
+      q += dq; r += dr;
+      if (r >= c) { r -= c; ++q; }
+    }
+    __syncwarp();
+    float run = 0.f;
+    for (int k = 0; k < c; ++k) {
+      const float t = buf[lane * stride + k];
+      buf[lane * stride + k] = run;                 // exclusive prefix inside the chunk
+      run = __fadd_rn(run, t);
+    }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl = __fadd_rn(incl, nb);
+    }
+    float off = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive chunk offset = inclusive scan of the previous lane
+    if (lane == 0) off = 0.f;
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
+    q = q0; r = r0;
+    for (int x = lane; x < 32 * c; x += 32) {
+      const float o = __shfl_sync(0xffffffffu, off, q);
+      if (x < W) dst[x] = __fadd_rn(o, buf[q * stride + r]);
+      q += dq; r += dr;
+      if (r >= c) { r -= c; ++q; }
+    }
+    if (lane == 0) dst[W] = total;
+    if (pass == 1) {
+      mn = warp_min(mn); mx = warp_max(mx);
+      if (lane == 0) {
+        float* o = rowstat + ((size_t)e * H + y) * 4;
+        o[0] = mn; o[1] = mx; o[2] = total; o[3] = 0.f;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// per expression: min, kk = 1 / (range * mean(A')), sum(A'')   (Hybridgl_main.py:204,209) from the row statistics
+__global__ void __launch_bounds__(128) heat_consts_kernel(const float* __restrict__ rowstat, const float* __restrict__ rp, int H, int W, int Wp,
+                                                          float* __restrict__ consts) {
+  const int e = blockIdx.x, tid = threadIdx.x;
+  float lo = INFINITY, hi = -INFINITY;
+  double s1 = 0.0;
+  for (int y = tid; y < H; y += blockDim.x) {
+    const float* o = rowstat + ((size_t)e * H + y) * 4;
+    lo = fminf(lo, o[0]); hi = fmaxf(hi, o[1]); s1 += (double)o[2];
+  }
+  __shared__ float slo[4], shi[4];
+  __shared__ double ss[4];
+  lo = warp_min(lo); hi = warp_max(hi);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  if ((tid & 31) == 0) { slo[tid >> 5] = lo; shi[tid >> 5] = hi; ss[tid >> 5] = s1; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); s1 += ss[w]; }
+    const double s0 = (double)H * (double)rp[(size_t)e * Wp + W];     // sum of the ramp over the frame
+    const double range = (double)hi - (double)lo;
+    const double sum_ap = (s1 - (double)lo * s0) / range;               // sum of A' = minmax(A) * ramp
+    const double mean = sum_ap / ((double)H * (double)W);
+    const double kk = 1.0 / (range * mean);
+    float* o = consts + (size_t)e * 4;
+    o[0] = lo; o[1] = (float)kk; o[2] = (float)(kk * (s1 - (double)lo * s0)); o[3] = 0.f;
+  }
+}
+
+// ---- the pass over the packed masks ----------------------------------------------------------------------------------
+constexpr int kBands = 4;                              // row bands (= independent warp tasks) per mask
+
+struct RowsScratch {         // global scratch of one launch (byte offsets 256-aligned)
+  int32_t* tickets;          // [M]            zero at launch
+  int32_t* pcnt;             // [M][kBands]    pixels per band
+  float* pgrid;              // [M][kBands][g*g]
+  float* pheat;              // [E][max_n][kBands][2]   (sum cr, sum rp) per band
+  size_t bytes;
+};
+static RowsScratch rows_carve(void* ws, int M, int g, int E, int max_n) {
+  RowsScratch r;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~size_t(255); return o; };
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  r.tickets = reinterpret_cast<int32_t*>(base + take((size_t)M * 4));
+  r.pcnt = reinterpret_cast<int32_t*>(base + take((size_t)M * kBands * 4));
+  r.pgrid = reinterpret_cast<float*>(base + take((size_t)M * kBands * g * g * 4));
+  r.pheat = reinterpret_cast<float*>(base + take((size_t)E * max_n * kBands * 2 * 4));
+  r.bytes = off;
+  return r;
+}
+
+struct RowsParams {
+  const uint32_t* bits;          // [M,H,WW]
+  int M, H, W, WW;
+  // grid part
+  int g, maxky, maxkx;
+  float* grid;                   // [M,g,g]
+  int32_t* area;                 // [M] or null
+  // heat part
+  const int32_t* mask_off; const int32_t* expr_off;
+  int B, E, max_n, Wp;
+  const float* cr; const float* rp; const float* consts; const float* black;
+  float* score_gem;              // [E,max_n]
+  RowsScratch sc;
+  // shared-memory carve-up (byte offsets)
+  int off_wy, off_wx, off_psum, off_hbuf, off_pgrid;
+};
+
+template <bool kGrid, bool kHeat>
+__global__ void __launch_bounds__(kRowsThreads) mask_rows_kernel(const RowsParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int* ymin = reinterpret_cast<int*>(smem);
+  int* ysize = ymin + kMaxG;
+  int* xlo = ysize + kMaxG;
+  int* xhi = xlo + kMaxG;
+  float* wy = reinterpret_cast<float*>(smem + p.off_wy);        // [g][maxky]
+  float* wx = reinterpret_cast<float*>(smem + p.off_wx);        // [g][maxkx]
+  double* psum = reinterpret_cast<double*>(smem + p.off_psum);  // [g][maxkx+1] prefix sums of wx (double: tiny edge taps survive)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W, WW = p.WW, g = p.g, gg = g * g;
+  const int gp = g | 1;
+  float* hbuf = reinterpret_cast<float*>(smem + p.off_hbuf) + (size_t)warp * 32 * gp;     // [32][gp] horizontal sums of this warp's 32 rows
+  float* pgrid = reinterpret_cast<float*>(smem + p.off_pgrid) + (size_t)warp * gg;        // [g][g] this band's share of the grid
+  const int pk = p.maxkx + 1;
+  float inv_sx = 0.f;
+  if (kGrid) {
+    if (tid < g) aa_fill(tid, H, g, p.maxky, &ymin[tid], &ysize[tid], wy + tid * p.maxky);
+    else if (tid >= 32 && tid < 32 + g) {
+      const int i = tid - 32;
+      int xm, xs;
+      aa_fill(i, W, g, p.maxkx, &xm, &xs, wx + i * p.maxkx);
+      xlo[i] = xm; xhi[i] = xm + xs;
+      double run = 0.0;
+      psum[i * pk] = 0.0;
+      for (int k = 0; k < p.maxkx; ++k) { run += (double)wx[i * p.maxkx + k]; psum[i * pk + k + 1] = run; }
+    }
+    inv_sx = (float)g / (float)W;
+    __syncthreads();
+  }
+
+  const int band_rows = (H + kBands - 1) / kBands;
+  const size_t mask_words = (size_t)H * WW;
+  const bool vec = (WW & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bits) & 15) == 0;
+  const float hw = (float)((size_t)H * W);
+  const int total_tasks = p.M * kBands;
+  for (int task = blockIdx.x * (kRowsThreads / 32) + warp; task < total_tasks; task += gridDim.x * (kRowsThreads / 32)) {
+    const int m = task / kBands, band = task - m * kBands;
+    const int y_begin = band * band_rows, y_end = min(H, y_begin + band_rows);
+    int b = 0, n_lo = 0, e_lo = 0, e_hi = 0;
+    if (kHeat) {
+      if (p.mask_off) {                                  // image of mask m: last b with mask_off[b] <= m
+        int lo = 0, hi = p.B - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.mask_off[mid] <= m) lo = mid; else hi = mid - 1; }
+        b = lo; n_lo = p.mask_off[b];
+      }
+      e_lo = p.expr_off ? p.expr_off[b] : 0;
+      e_hi = p.expr_off ? p.expr_off[b + 1] : p.E;
+    }
+    const uint32_t* mb = p.bits + (size_t)m * mask_words;
+    int cnt = 0;
+    if (kGrid)
+      for (int t = lane; t < gg; t += 32) pgrid[t] = 0.f;
+    bool first = true;
+    for (int eg = e_lo; first || eg < e_hi; eg += kEB) {     // groups of kEB expressions; more than one pass is rare
+      const int ne = kHeat ? max(0, min(kEB, e_hi - eg)) : 0;
+      const bool do_grid = kGrid && first;
+      float acc[kEB], accr[kEB];
+#pragma unroll
+      for (int j = 0; j < kEB; ++j) { acc[j] = 0.f; accr[j] = 0.f; }
+      for (int y0 = y_begin; y0 < y_end; y0 += 32) {
+        const int y = y0 + lane;
+        const bool have = y < y_end;
+        const uint32_t* rowp = mb + (size_t)(have ? y : y_begin) * WW;
+        // ---- phase A: the row's words pass through registers once: pixel count + bitmap of words with a transition
+        uint64_t im = 0;
+        int c_row = 0;
+        if (have) {
+          uint32_t prev = 0;                                          // last bit of the previous word
+          auto look = [&](uint32_t v, int w) {
+            c_row += __popc(v);
+            if (v != (0u - prev)) im |= 1ull << w;                    // neither "all outside" after a 0 nor "all inside" after a 1
+            prev = v >> 31;
+          };
+          if (vec) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(rowp);
+            for (int u = 0; u < (WW >> 2); ++u) {
+              const uint4 v = __ldg(r4 + u);
+              look(v.x, 4 * u); look(v.y, 4 * u + 1); look(v.z, 4 * u + 2); look(v.w, 4 * u + 3);
+            }
+          } else {
+            for (int w = 0; w < WW; ++w) look(__ldg(rowp + w), w);
+          }
+          if (prev) im |= 1ull << WW;                                 // run open at the frame edge: closed by the virtual zero word WW
+        }
+        if (first) cnt += c_row;
+        const bool nonempty = c_row != 0;
+        float* hr = hbuf + lane * gp;
+        int bx_lo = g, bx_hi = -1;
+        if (do_grid && nonempty)
+          for (int i = 0; i < g; ++i) hr[i] = 0.f;
+        // ---- phase B: only the words that hold a transition (two per row for a blob)
+        if (im != 0ull) {
+          const float* crow[kEB];
+          const float* rrow[kEB];
+#pragma unroll
+          for (int j = 0; j < kEB; ++j) {
+            const int ej = eg + min(j, max(ne - 1, 0));
+            crow[j] = kHeat ? p.cr + ((size_t)ej * H + y) * p.Wp : nullptr;
+            rrow[j] = kHeat ? p.rp + (size_t)ej * p.Wp : nullptr;
+          }
+          uint32_t carry = 0;
+          int xs = 0;
+#pragma unroll 1
+          while (im) {
+            const int w = __ffsll((long long)im) - 1;
+            im &= im - 1;
+            const uint32_t v = (w < WW) ? __ldg(rowp + w) : 0u;       // L1 hit: loaded a moment ago
+            uint32_t t = v ^ ((v << 1) | carry);
+            carry = v >> 31;
+            while (t) {
+              const int bp = __ffs(t) - 1;
+              t &= t - 1;
+              const int x = 32 * w + bp;
+              if ((v >> bp) & 1u) { xs = x; continue; }
+              const int s0 = xs, e0 = min(x, W);                      // pixels [s0, e0) of row y are inside the mask
+              if (do_grid) {
+                int i = max(0, min(g - 1, (int)((float)s0 * inv_sx - 1.5f) - 1));
+                while (i < g && xhi[i] <= s0) ++i;
+                bx_lo = min(bx_lo, i);
+                for (; i < g && xlo[i] < e0; ++i) {
+                  const double* ps = psum + i * pk - xlo[i];
+                  const int a0 = min(max(s0, xlo[i]), xhi[i]), a1 = min(max(e0, xlo[i]), xhi[i]);
+                  hr[i] += (float)(ps[a1] - ps[a0]);
+                }
+                bx_hi = max(bx_hi, i - 1);
+              }
+              if (kHeat) {
+#pragma unroll
+                for (int j = 0; j < kEB; ++j) {
+                  if (j < ne) {
+                    acc[j] += __ldg(crow[j] + e0) - __ldg(crow[j] + s0);
+                    accr[j] += __ldg(rrow[j] + e0) - __ldg(rrow[j] + s0);
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (do_grid) {
+          // fold the block's rows into the vertical bins they feed, ascending row order:
+          //   pgrid[gy][gx] = pgrid[gy][gx] + h[y][gx] * wy[gy][y - ymin[gy]]     (separate multiply and add, like the reference)
+          const uint32_t rows_mask = __ballot_sync(0xffffffffu, nonempty);
+          if (rows_mask != 0u) {
+            int gx0 = bx_lo, gx1 = bx_hi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              gx0 = min(gx0, __shfl_xor_sync(0xffffffffu, gx0, o));
+              gx1 = max(gx1, __shfl_xor_sync(0xffffffffu, gx1, o));
+            }
+            const int r_first = __ffs(rows_mask) - 1, r_last = 31 - __clz(rows_mask);
+            const int ya = y0 + r_first, yb = y0 + r_last;           // first / last non-empty row of the block
+            int gy_lo = 0;
+            while (gy_lo < g && ymin[gy_lo] + ysize[gy_lo] <= ya) ++gy_lo;
+            int gy_hi = gy_lo;
+            while (gy_hi + 1 < g && ymin[gy_hi + 1] <= yb) ++gy_hi;
+            const int nbx = gx1 - gx0 + 1, nel = (gy_hi - gy_lo + 1) * nbx;
+            __syncwarp();
+            for (int t = lane; t < nel; t += 32) {
+              const int gyl = t / nbx, gx = gx0 + t - gyl * nbx, gy = gy_lo + gyl;
+              const int y_lo = ymin[gy], y_sz = ysize[gy];
+              const float* wp = wy + gy * p.maxky + (y0 - y_lo);
+              const float* hp = hbuf + gx;
+              const int k_lo = max(r_first, y_lo - y0), k_hi = min(r_last, y_lo + y_sz - 1 - y0);
+              float a = pgrid[gy * g + gx];
+#pragma unroll 4
+              for (int r = k_lo; r <= k_hi; ++r)
+                if ((rows_mask >> r) & 1u) a = __fadd_rn(a, __fmul_rn(hp[r * gp], wp[r]));
+              pgrid[gy * g + gx] = a;
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (kHeat && ne > 0) {                                          // this band's pooled sums of the group
+#pragma unroll
+        for (int j = 0; j < kEB; ++j) {
+          const float sc = warp_sum(acc[j]), sr = warp_sum(accr[j]);
+          if (lane == 0 && j < ne) {
+            float* o = p.sc.pheat + (((size_t)(eg + j) * p.max_n + (m - n_lo)) * kBands + band) * 2;
+            o[0] = sc; o[1] = sr;
+          }
+        }
+      }
+      first = false;
+    }
+    cnt = warp_sum_i(cnt);
+    if (lane == 0) p.sc.pcnt[m * kBands + band] = cnt;
+    if (kGrid) {
+      __syncwarp();
+      float* o = p.sc.pgrid + ((size_t)m * kBands + band) * gg;
+      for (int t = lane; t < gg; t += 32) o[t] = pgrid[t];
+    }
+    // ---- ticket: the last band of mask m combines the four partial results in band order
+    __threadfence();
+    __syncwarp();                                                     // every lane's partial results are fenced before the ticket
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(p.sc.tickets + m, 1) == kBands - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) continue;
+    __threadfence();
+    int area_m = 0;
+#pragma unroll
+    for (int q = 0; q < kBands; ++q) area_m += __ldcg(p.sc.pcnt + m * kBands + q);
+    if (lane == 0 && p.area) p.area[m] = area_m;
+    if (kGrid) {
+      const float* pg = p.sc.pgrid + (size_t)m * kBands * gg;
+      for (int t = lane; t < gg; t += 32) {
+        float a = __ldcg(pg + t);
+#pragma unroll
+        for (int q = 1; q < kBands; ++q) a = __fadd_rn(a, __ldcg(pg + q * gg + t));
+        p.grid[(size_t)m * gg + t] = a;
+      }
+    }
+    if (kHeat) {
+      for (int e = e_lo + lane; e < e_hi; e += 32) {
+        const float* o = p.sc.pheat + ((size_t)e * p.max_n + (m - n_lo)) * kBands * 2;
+        float sc = 0.f, sr = 0.f;
+#pragma unroll
+        for (int q = 0; q < kBands; ++q) { sc += __ldcg(o + 2 * q); sr += __ldcg(o + 2 * q + 1); }
+        const float mn = p.consts[e * 4], kk = p.consts[e * 4 + 1], s_tot = p.consts[e * 4 + 2];
+        const float s_in = kk * (sc - mn * sr);
+        const float bl = p.black[e];
+        p.score_gem[(size_t)e * p.max_n + (m - n_lo)] = (2.f - bl) * s_in / (float)area_m - bl * (s_tot - s_in) / (hw - (float)area_m);
+      }
+    }
+  }
+}
+
+// ---- legacy 4-tap path and small helpers ------------------------------------------------------------------------------
+// non-antialiased: 4-tap bilinear sample of the packed mask at the g x g grid positions (ATen upsample_bilinear2d;
+// what the reference's pinned torchvision 0.15.2 computes for TF.resize on tensors)
+__global__ void mask_grid_noaa_kernel(const uint32_t* __restrict__ bits, int M, int H, int W, int g, float* __restrict__ grid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * g * g) return;
+  const int gx = idx % g, gy = (idx / g) % g, m = idx / (g * g);
+  const int WW = (W + 31) >> 5;
+  auto taps = [](int dst, int in_size, int out_size, int& i0, int& d, float& w0, float& w1) {
+    if (in_size == out_size) { i0 = dst; d = 0; w0 = 1.f; w1 = 0.f; return; }
+    const float scale = __fdiv_rn((float)in_size, (float)out_size);
+    float src = fmaxf(__fmaf_rn(scale, (float)dst + 0.5f, -0.5f), 0.f);
+    i0 = min((int)src, in_size - 1);
+    d = (i0 < in_size - 1) ? 1 : 0;
+    w1 = fminf(fmaxf(__fsub_rn(src, (float)i0), 0.f), 1.f);
+    w0 = __fsub_rn(1.f, w1);
+  };
+  int y0, dy, x0, dx; float wy0, wy1, wx0, wx1;
+  taps(gy, H, g, y0, dy, wy0, wy1);
+  taps(gx, W, g, x0, dx, wx0, wx1);
+  const uint32_t* b = bits + (size_t)m * H * WW;
+  auto bit = [&](int y, int x) { return ((b[(size_t)y * WW + (x >> 5)] >> (x & 31)) & 1u) ? 1.f : 0.f; };
+  const float a = bit(y0, x0), bb = bit(y0, x0 + dx), c = bit(y0 + dy, x0), d = bit(y0 + dy, x0 + dx);
+  const float top = __fmaf_rn(a, wx0, __fmul_rn(bb, wx1)), bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
+  grid[idx] = __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
+}
+
+// pixel count per mask from the packed words (used when antialias == 0 and the caller still wants areas)
+__global__ void __launch_bounds__(256) mask_area_kernel(const uint32_t* __restrict__ bits, int M, size_t words, int32_t* __restrict__ area) {
+  __shared__ int red[8];
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const uint32_t* b = bits + (size_t)m * words;
+    int s = 0;
+    for (size_t i = threadIdx.x; i < words; i += blockDim.x) s += __popc(b[i]);
+    s = warp_sum_i(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += red[w]; area[m] = t; }
+    __syncthreads();
+  }
+}
+
+// Launch the pass.  want_grid / want_heat select the template instance.
+static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scratch, cudaStream_t st) {
+  HGL_REQUIRE(p.WW <= 63, "mask rows pass: W=%d wider than 2016", p.W);
+  p.sc = rows_carve(scratch, p.M, want_grid ? p.g : 0, want_heat ? p.E : 0, want_heat ? p.max_n : 0);
+  cudaError_t e = cudaMemsetAsync(p.sc.tickets, 0, (size_t)p.M * 4, st);
+  if (e != cudaSuccess) { set_error("mask rows pass: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+  size_t off = (size_t)4 * kMaxG * 4;
+  auto take = [&](size_t n, size_t align) { off = (off + align - 1) & ~(align - 1); size_t o = off; off += n; return (int)o; };
+  const int warps = kRowsThreads / 32;
+  p.off_wy = take(want_grid ? (size_t)p.g * p.maxky * 4 : 0, 16);
+  p.off_wx = take(want_grid ? (size_t)p.g * p.maxkx * 4 : 0, 16);
+  p.off_psum = take(want_grid ? (size_t)p.g * (p.maxkx + 1) * 8 : 0, 16);
+  p.off_hbuf = take(want_grid ? (size_t)warps * 32 * (p.g | 1) * 4 : 0, 16);
+  p.off_pgrid = take(want_grid ? (size_t)warps * p.g * p.g * 4 : 0, 16);
+  const size_t smem = off;
+  HGL_REQUIRE(smem <= 220 * 1024, "mask rows pass: frame %dx%d (g=%d) needs %zu B of shared memory", p.H, p.W, p.g, smem);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+  const int ctas = std::min(ceil_div(p.M * kBands, warps), sm_count() * per_sm);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) { set_error("mask rows pass: cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return HGL_ECUDA; }
+    kern<<<ctas, kRowsThreads, smem, st>>>(p);
+    return launch_status("mask rows pass");
+  };
+  if (want_grid && want_heat) return go(mask_rows_kernel<true, true>);
+  if (want_grid) return go(mask_rows_kernel<true, false>);
+  return go(mask_rows_kernel<false, true>);
+}
+
+static int launch_heat_tables(const float* heat, const int32_t* dirflag, int E, int H, int W, const HeatWs& ws, cudaStream_t st) {
+  const int c = (W + 31) >> 5;
+  const size_t smem = ((size_t)32 * c + (size_t)kPrefWarps * 32 * (c | 1)) * 4;
+  HGL_REQUIRE(smem <= 200 * 1024, "hgl_heat_pool: W=%d too wide", W);
+  cudaError_t e = cudaFuncSetAttribute(heat_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+  heat_prefix_kernel<<<dim3(ceil_div(H, kPrefWarps), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, ws.cr, ws.rp, ws.rowstat);
+  int rc = launch_status("hgl_heat_pool(prefix)");
+  if (rc != HGL_OK) return rc;
+  heat_consts_kernel<<<E, 128, 0, st>>>(ws.rowstat, ws.rp, H, W, ws.Wp, ws.consts);
+  return launch_status("hgl_heat_pool(consts)");
+}
+
+}  // namespace hgl
+
+extern "C" int hgl_dir_mask(int dirflag, int H, int W, float* out, void* stream) {
+  using namespace hgl;
+  HGL_REQUIRE(out, "hgl_dir_mask: null pointer");
+  HGL_REQUIRE(H >= 1 && W >= 1, "hgl_dir_mask: bad shape");
+  const int blocks = (int)std::min<size_t>(((size_t)H * W + 255) / 256, (size_t)sm_count() * 8);
+  dir_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dirflag, H, W, out);
+  return launch_status("hgl_dir_mask");
+}
+
+extern "C" int64_t hgl_mask_grid_workspace_bytes(int M, int g) {
+  if (M < 0 || g < 1 || g > hgl::kMaxG) return -1;
+  return (int64_t)hgl::rows_carve(nullptr, M, g, 0, 0).bytes + 256;
+}
+
+extern "C" int hgl_mask_grid(const uint32_t* bits, int M, int H, int W, int g, int antialias, float* grid, int32_t* area,
+                             void* workspace, void* stream) {
+  using namespace hgl;
+  if (M == 0) return HGL_OK;
+  HGL_REQUIRE(bits && grid, "hgl_mask_grid: null pointer");
+  HGL_REQUIRE(M >= 0 && H >= 1 && W >= 1 && g >= 1 && g <= kMaxG, "hgl_mask_grid: bad shape M=%d H=%d W=%d g=%d", M, H, W, g);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int WW = (W + 31) >> 5;
+  if (!antialias) {
+    const int total = M * g * g;
+    mask_grid_noaa_kernel<<<ceil_div(total, 256), 256, 0, st>>>(bits, M, H, W, g, grid);
+    int rc = launch_status("hgl_mask_grid(noaa)");
+    if (rc != HGL_OK) return rc;
+    if (area) {
+      mask_area_kernel<<<std::min(M, sm_count() * 8), 256, 0, st>>>(bits, M, (size_t)H * WW, area);
+      return launch_status("hgl_mask_grid(area)");
+    }
+    return HGL_OK;
+  }
+  HGL_REQUIRE(H >= g && W >= g, "hgl_mask_grid: antialiased path is a down-sampler (H=%d W=%d g=%d)", H, W, g);
+  HGL_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hgl_mask_grid: 16-byte aligned workspace required");
+  RowsParams p = {};
+  p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = WW;
+  p.g = g; p.maxky = aa_maxk(H, g); p.maxkx = aa_maxk(W, g); p.grid = grid; p.area = area;
+  void* scratch = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  return launch_rows(p, true, false, scratch, st);
+}
+
+extern "C" int64_t hgl_grid_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int g, int max_n) {
+  using namespace hgl;
+  if (B < 1 || M < 0 || E < 0 || H < 1 || W < 1 || max_n < 0 || g < 0 || g > kMaxG) return -1;
+  return (int64_t)heat_carve(nullptr, E, H, W).bytes + (int64_t)rows_carve(nullptr, M, g, E, max_n).bytes + 256;
+}
+
+extern "C" int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n) {
+  return hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, 0, max_n);
+}
+
+// shared argument checks + table build of the two pooling entry points
+static int hgl_heat_common(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, const uint32_t* bits,
+                           const int32_t* mask_off, int B, int M, int E, int H, int W, int max_n, float* score_gem, void* workspace,
+                           hgl::HeatWs* ws, void** scratch, cudaStream_t st) {
+  using namespace hgl;
+  HGL_REQUIRE(heat && dirflag && black && bits && score_gem && workspace, "hgl_heat_pool: null pointer");
+  HGL_REQUIRE(B >= 1 && M >= 0 && E >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_heat_pool: bad shape");
+  HGL_REQUIRE((mask_off && expr_off) || B == 1, "hgl_heat_pool: mask_off/expr_off required when B > 1");
+  HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hgl_heat_pool: workspace must be 16-byte aligned");
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  *ws = heat_carve(base, E, H, W);
+  *scratch = base + ws->bytes;
+  cudaError_t e = cudaMemsetAsync(score_gem, 0, (size_t)E * max_n * 4, st);    // rows of images with fewer than max_n masks
+  if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+  return launch_heat_tables(heat, dirflag, E, H, W, *ws, st);
+}
+
+static void hgl_fill_heat(hgl::RowsParams& p, const hgl::HeatWs& ws, const float* black, const int32_t* mask_off, const int32_t* expr_off,
+                          int B, int E, int max_n, float* score_gem) {
+  p.mask_off = mask_off; p.expr_off = expr_off; p.B = B; p.E = E; p.max_n = max_n; p.Wp = ws.Wp;
+  p.cr = ws.cr; p.rp = ws.rp; p.consts = ws.consts; p.black = black; p.score_gem = score_gem;
+}
+
+extern "C" int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
+                             const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W,
+                             int max_n, float* score_gem, void* workspace, void* stream) {
+  using namespace hgl;
+  if (E == 0 || M == 0) return HGL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  HeatWs ws;
+  void* scratch = nullptr;
+  int rc = hgl_heat_common(heat, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  if (rc != HGL_OK) return rc;
+  RowsParams p = {};
+  p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
+  hgl_fill_heat(p, ws, black, mask_off, expr_off, B, E, max_n, score_gem);
+  return launch_rows(p, false, true, scratch, st);
+}
+
+extern "C" int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                                  float* grid, int32_t* area,
+                                  const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
+                                  int max_n, float* score_gem, void* workspace, void* stream) {
+  using namespace hgl;
+  if (M == 0) return HGL_OK;
+  if (E == 0) return hgl_mask_grid(bits, M, H, W, g, 1, grid, area, workspace, stream);
+  HGL_REQUIRE(grid, "hgl_grid_heat_pool: null pointer");
+  HGL_REQUIRE(g >= 1 && g <= kMaxG && H >= g && W >= g, "hgl_grid_heat_pool: bad grid side g=%d for %dx%d", g, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  HeatWs ws;
+  void* scratch = nullptr;
+  int rc = hgl_heat_common(heat, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  if (rc != HGL_OK) return rc;
+  RowsParams p = {};
+  p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
+  p.g = g; p.maxky = aa_maxk(H, g); p.maxkx = aa_maxk(W, g); p.grid = grid; p.area = area;
+  hgl_fill_heat(p, ws, black, mask_off, expr_off, B, E, max_n, score_gem);
+  return launch_rows(p, true, true, scratch, st);
+}

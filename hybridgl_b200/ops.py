@@ -159,8 +159,11 @@ def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area
         bits = pack_masks(m)
     grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
     area = torch.empty((M,), dtype=torch.int32, device=bits.device) if want_area else None
-    check(_lib.load().hgl_mask_grid(bits.data_ptr(), M, H, W, g, int(bool(antialias)), grid.data_ptr(), _ptr(area), _stream()),
-          "hgl_mask_grid")
+    ws = None
+    if antialias:
+        ws = torch.empty((max(_lib.load().hgl_mask_grid_workspace_bytes(M, g), 1),), dtype=torch.uint8, device=bits.device)
+    check(_lib.load().hgl_mask_grid(bits.data_ptr(), M, H, W, g, int(bool(antialias)), grid.data_ptr(), _ptr(area), _ptr(ws),
+                                    _stream()), "hgl_mask_grid")
     return (grid, area) if want_area else grid
 
 
@@ -248,11 +251,45 @@ def heat_pool(heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor, ma
     return out
 
 
+def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor,
+                   mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
+                   workspace: Optional[torch.Tensor] = None):
+    """masks_to_grid(antialias=True, want_area=True) and heat_pool in one pass over the packed masks.
+    Returns (grid f32 [M,g,g], area int32 [M], score_gem f32 [E,max_n])."""
+    _req(bits, torch.int32, "bits", 3)
+    _req(heat, torch.float32, "heat", 3)
+    M, H, W = bits.shape[0], bits.shape[1], int(width)
+    E = heat.shape[0]
+    if bits.shape[2] != (W + 31) // 32 or tuple(heat.shape[1:]) != (H, W):
+        raise ValueError("packed masks, width and heat-map frames disagree")
+    _req(dirflag, torch.int32, "dirflag", 1)
+    _req(black, torch.float32, "black", 1)
+    B = 1 if mask_off is None else mask_off.numel() - 1
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    lib = _lib.load()
+    need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, g, max_n)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=bits.device)
+    grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
+    area = torch.empty((M,), dtype=torch.int32, device=bits.device)
+    out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
+    check(lib.hgl_grid_heat_pool(bits.data_ptr(), _ptr(moff), B, M, H, W, g, grid.data_ptr(), area.data_ptr(),
+                                 heat.data_ptr(), _ptr(eoff), dirflag.data_ptr(), black.data_ptr(), E, max_n,
+                                 out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_grid_heat_pool")
+    return grid, area, out
+
+
 # ---- (a6)-(a9),(a12) ----------------------------------------------------------------------------------
 def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, others: torch.Tensor, other_off: torch.Tensor,
                  boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],
                  mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None,
-                 max_n: Optional[int] = None, logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6):
+                 max_n: Optional[int] = None, logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
+                 workspace: Optional[torch.Tensor] = None):
     """Hybridgl_main.py:153-196,225-227 for a batch.  Returns dict(score_clip[E,max_n], idx_hybrid[E], idx_final[E],
     top_idx[E,3], blended[E,3])."""
     _req(feat, (torch.float32, torch.bfloat16), "feat", 2)
@@ -283,11 +320,14 @@ def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, oth
     idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
     top = torch.empty((E, 3), dtype=torch.int32, device=dev)
     blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    need = _lib.load().hgl_score_select_workspace_bytes(B, E, max_n)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
     check(_lib.load().hgl_score_select(feat.data_ptr(), _dt(feat.dtype), sent.data_ptr(), noun.data_ptr(), others.data_ptr(),
                                        other_off.data_ptr(), boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
                                        _ptr(moff), _ptr(eoff), B, M, E, De, max_n, float(logit_scale_exp), float(r), float(alpha),
                                        score_clip.data_ptr(), idx_h.data_ptr(), idx_f.data_ptr(), top.data_ptr(),
-                                       blended.data_ptr(), _stream()), "hgl_score_select")
+                                       blended.data_ptr(), workspace.data_ptr(), _stream()), "hgl_score_select")
     return dict(score_clip=score_clip, idx_hybrid=idx_h, idx_final=idx_f, top_idx=top, blended=blended)
 
 

@@ -74,23 +74,28 @@ class ScoringPath:
         ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
                                 dtype=self.prep_dtype, out=(local, glob), workspace=pws)
         self._mark("prep")
-        grid, area = ops.masks_to_grid(bits, self.grid, antialias=self.antialias, want_area=True, width=W)
-        self._mark("grid")
         feats = batch["features"] if features is None else features
         E = batch["sent"].shape[0]
-        need = lib.hgl_heat_pool_workspace_bytes(B, M, E, H, W, max_n)
+        need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n)
         ws = self._get("heat_ws", (need,), torch.uint8)
-        score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
-        self._mark("heat_pool")
+        if self.antialias:     # mask grid + heat-map pooling share one pass over the packed masks
+            grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, batch["heat"], batch["dirflag"], batch["black"],
+                                                       moff, eoff, max_n, workspace=ws)
+        else:
+            grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
+            score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
+        self._mark("grid_heat_pool")
+        sws = self._get("score_ws", (max(lib.hgl_score_select_workspace_bytes(B, E, max_n), 1),), torch.uint8)
         res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
-                               batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)
+                               batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha,
+                               workspace=sws)
         self._mark("score_select")
         iu = ops.iou_accumulate(masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
         self._mark("iou")
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits)
         return res
 
-    # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid 1, heat_pool 3, score_select 1, iou 2
+    # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), score_select 2 (text, score+select), iou 2
     LAUNCHES_PER_RUN = 11
 
     def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:

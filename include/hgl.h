@@ -83,9 +83,11 @@ HGL_API int hgl_gaussian_blur15(const uint8_t* image, uint8_t* out, int B, int H
 /* ---- (a2) mask -> patch grid ------------------------------------------------------------------------
  * Replaces TF.resize(pred_masks.float(), (g,g)) model/backbone.py:160.  antialias=1 is torchvision>=0.17
  * behaviour (this container), antialias=0 the reference's pinned torchvision 0.15.2.
- * bits = packed masks [M,H,WW] -> grid f32 [M,g,g]; area int32 [M] (pixel count of every mask; may be NULL). */
+ * bits = packed masks [M,H,WW] -> grid f32 [M,g,g]; area int32 [M] (pixel count of every mask; may be NULL).
+ * workspace: hgl_mask_grid_workspace_bytes(M, g) bytes, 16-byte aligned (only read when antialias != 0; may be NULL otherwise). */
+HGL_API int64_t hgl_mask_grid_workspace_bytes(int M, int g);
 HGL_API int hgl_mask_grid(const uint32_t* bits, int M, int H, int W, int g, int antialias,
-                  float* grid, int32_t* area, void* stream);
+                  float* grid, int32_t* area, void* workspace, void* stream);
 
 /* ---- (a3) CLS-row attention mask --------------------------------------------------------------------
  * Replaces CLIPViTFM.make_attn_mask model/backbone.py:108-115.
@@ -109,14 +111,22 @@ HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* g
  *   score_gem[e,n] = (2-black_e) * sum(A''*m_n)/area(m_n) - black_e * sum(A''*(1-m_n))/area(1-m_n)
  * heat f32 [E,H,W] (GEM map after T.Resize, Hybridgl_main.py:201); expr_off int32 [B+1] (NULL => B==1);
  * dirflag int32 [E]; black f32 [E]; bits = packed masks [M,H,WW]; mask_off int32 [B+1] (NULL => B==1).
- * score_gem f32 [E, max_n] row e holds the n masks of its image (max_n = row stride).
- * workspace: hgl_heat_pool_workspace_bytes(...) bytes, zeroing not required. */
+ * score_gem f32 [E, max_n] row e holds the n masks of its image (max_n = row stride; the tail is zero-filled).
+ * workspace: hgl_heat_pool_workspace_bytes(...) bytes (row prefix tables of the heat-maps), zeroing not required. */
 /* gen_dir_mask utils.py:135-161 as a tensor: out f32 [H,W] (left: 1->0, right: 0->1, middle: 0->1->0, others: ones) */
 HGL_API int hgl_dir_mask(int dirflag, int H, int W, float* out, void* stream);
 HGL_API int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int max_n);
 HGL_API int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black,
                   const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W,
                   int max_n, float* score_gem, void* workspace, void* stream);
+/* (a2) + (a10) + (a11) in ONE pass over the packed masks: hgl_mask_grid(antialias=1) and hgl_heat_pool fused (same
+ * arguments, same results); this is what the batched pipeline launches.  E == 0 degenerates to hgl_mask_grid.
+ * workspace: hgl_grid_heat_pool_workspace_bytes(...) bytes. */
+HGL_API int64_t hgl_grid_heat_pool_workspace_bytes(int B, int M, int E, int H, int W, int g, int max_n);
+HGL_API int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                       float* grid, int32_t* area,
+                       const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
+                       int max_n, float* score_gem, void* workspace, void* stream);
 
 /* ---- (a6)-(a9),(a12) scoring, spatial-relationship re-ranking, per-expression argmax ----------------
  * Replaces Hybridgl_main.py:153-196 and :225-227 plus CLIPViTFM.calculate_score model/backbone.py:74-87 and
@@ -128,13 +138,15 @@ HGL_API int hgl_heat_pool(const float* heat, const int32_t* expr_off, const int3
  * feat [M,De] feat_dtype; sent/noun f32 [E,De]; others f32 [K,De] with other_off int32 [E+1];
  * boxes int64 [M,4] XYWH; relaflag int32 [E]; score_gem f32 [E,max_n] or NULL (=> alpha term skipped);
  * outputs: score_clip f32 [E,max_n] (pre-softmax), idx_hybrid/idx_final int64 [E] (index local to the image),
- * top_idx int32 [E,3] (-1 padded), blended f32 [E,3]. */
+ * top_idx int32 [E,3] (-1 padded), blended f32 [E,3].
+ * workspace: hgl_score_select_workspace_bytes(B, E, max_n) bytes, 256-byte aligned (negative scores + per-image tickets). */
+HGL_API int64_t hgl_score_select_workspace_bytes(int B, int E, int max_n);
 HGL_API int hgl_score_select(const void* feat, int feat_dtype, const float* sent, const float* noun, const float* others,
                      const int32_t* other_off, const int64_t* boxes, const int32_t* relaflag, const float* score_gem,
                      const int32_t* mask_off, const int32_t* expr_off, int B, int M, int E, int De, int max_n,
                      double logit_scale_exp, double r, double alpha,
                      float* score_clip, int64_t* idx_hybrid, int64_t* idx_final, int32_t* top_idx, float* blended,
-                     void* stream);
+                     void* workspace, void* stream);
 
 /* ---- (a13) IoU accounting ---------------------------------------------------------------------------
  * Replaces Compute_IoU utils.py:365-384 (called at Hybridgl_main.py:171,230):

@@ -44,7 +44,7 @@ def test_library_loads_and_reports_errors(lib):
     # argument validation happens before any CUDA call, so it is testable without a device
     rc = h.hgl_prep(None, None, None, None, 1, 1, 1, 8, 8, 8, 0, 0, None, None, None, None)
     assert rc == -1 and b"null pointer" in h.hgl_last_error()
-    rc = h.hgl_mask_grid(1, 1, 8, 8, 99, 1, 1, None, None)
+    rc = h.hgl_mask_grid(1, 1, 8, 8, 99, 1, 1, None, None, None)
     assert rc == -1 and b"bad shape" in h.hgl_last_error()
     assert h.hgl_heat_pool_workspace_bytes(2, 10, 3, 48, 64, 8) > 0
 

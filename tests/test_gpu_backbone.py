@@ -91,7 +91,7 @@ def test_utils_mirror(golden):
         v = U.relation_boxes(torch.from_numpy(bi), torch.from_numpy(bj), torch.tensor(si), torch.tensor(sj), str(word))
         np.testing.assert_allclose(float(v), ref, rtol=2e-7, atol=0)
     s = golden("scoring")
-    for ci in (0, 7, 26):
+    for ci in (0, 7, 24):
         p = f"c{ci:02d}_"
         _, h, w, n, _ = s[p + "meta"].tolist()
         masks = unpack_masks(s[p + "masks"], w); target = unpack_masks(s[p + "target"], w)
