@@ -132,8 +132,19 @@ __global__ void __launch_bounds__(256) pack_masks_rows_kernel(const uint8_t* __r
 // taps:   [B][6][S*S] u32; words 0-2 image bytes, 3-5 background bytes, byte index inside the 12 = tap*3 + channel
 template <bool kBF16>
 __global__ void __launch_bounds__(256) prep_setup_kernel(const uint8_t* __restrict__ image, const uint8_t* __restrict__ blur, int H, int W, int S,
-                                                         void* __restrict__ planes, uint32_t* __restrict__ taps) {
+                                                         void* __restrict__ planes, uint32_t* __restrict__ taps, float* __restrict__ lut) {
+  // per-byte maps: [v] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255): the correctly-rounded divisions are done
+  // 4 x 256 times per CTA instead of ~40 times per pixel
+  __shared__ float slut[1024];
+  {
+    const uint32_t v = threadIdx.x;
+    slut[v] = to_unit(v);
+    slut[256 + v] = to_norm(v, 0); slut[512 + v] = to_norm(v, 1); slut[768 + v] = to_norm(v, 2);
+  }
+  __syncthreads();
   const int b = blockIdx.y;
+  if (blockIdx.x == 0 && b == 0)         // the same tables for the fix-up pass of prep_main_kernel
+    for (int k = threadIdx.x; k < 1024; k += 256) lut[k] = slut[k];
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   const int SS = S * S;
   if (px >= SS) return;
@@ -157,10 +168,11 @@ __global__ void __launch_bounds__(256) prep_setup_kernel(const uint8_t* __restri
       bw[k >> 2] |= vb[t] << ((k & 3) * 8);
     }
     const float mean = c_in_mean[c], stdv = c_in_std[c], pm = c_clip_mean[c];
-    v[0 + c] = bilerp(to_norm(vi[0], c), to_norm(vi[1], c), to_norm(vi[2], c), to_norm(vi[3], c), tx.w0, tx.w1, ty.w0, ty.w1);
-    v[3 + c] = __fdiv_rn(__fsub_rn(bilerp(to_unit(vi[0]), to_unit(vi[1]), to_unit(vi[2]), to_unit(vi[3]), tx.w0, tx.w1, ty.w0, ty.w1), mean), stdv);
+    const float* nl = slut + 256 + 256 * c;
+    v[0 + c] = bilerp(nl[vi[0]], nl[vi[1]], nl[vi[2]], nl[vi[3]], tx.w0, tx.w1, ty.w0, ty.w1);
+    v[3 + c] = __fdiv_rn(__fsub_rn(bilerp(slut[vi[0]], slut[vi[1]], slut[vi[2]], slut[vi[3]], tx.w0, tx.w1, ty.w0, ty.w1), mean), stdv);
     v[6 + c] = bilerp(pm, pm, pm, pm, tx.w0, tx.w1, ty.w0, ty.w1);
-    v[9 + c] = __fdiv_rn(__fsub_rn(bilerp(to_unit(vb[0]), to_unit(vb[1]), to_unit(vb[2]), to_unit(vb[3]), tx.w0, tx.w1, ty.w0, ty.w1), mean), stdv);
+    v[9 + c] = __fdiv_rn(__fsub_rn(bilerp(slut[vb[0]], slut[vb[1]], slut[vb[2]], slut[vb[3]], tx.w0, tx.w1, ty.w0, ty.w1), mean), stdv);
   }
 #pragma unroll
   for (int k = 0; k < 12; ++k) {
@@ -183,10 +195,14 @@ struct PrepParams {
   const int32_t* mask_off;
   const void* planes;         // [B,12,S*S]
   const uint32_t* taps;       // [B,6,S*S]
+  const float* lut;           // [1024] byte -> unit / normalised value
   void* local_out;
   void* global_out;
   int B, M, H, W, S, WW;
-  int chunk;                  // masks per CTA
+  int stage_words;            // ring pitch of the shared-memory bit-row stages (words)
+  int sub;                    // masks per stage
+  int gw, gh, cw, nbx;        // thread -> pixel map (PrepGeom)
+  int debug;                  // profiling only (HGL_PREP_DEBUG): 1 = skip the fix-up pass, 2 = skip the stores of P1
   int narrow;                 // 1 if the 8 taps of 4 adjacent pixels always fit one 32-bit window
 };
 
@@ -218,9 +234,12 @@ struct Pack {
 };
 
 // boundary pixel: exact per-tap evaluation (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel).
-// Only pixels whose taps straddle the mask outline come here, through the dense fix-up pass at the end of each CTA.
+// Only pixels whose taps straddle the mask outline come here, through the dense fix-up pass of each stage.
+// lut: tables (built by prep_setup_kernel, L1-resident) of the two per-byte maps, [0..255] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255)
+// -- the same correctly-rounded divisions as to_unit / to_norm, evaluated once per CTA instead of 27 times per pixel.
 __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__ taps, size_t tap0, int SS, uint32_t code,
-                                                    float wx0, float wx1, float wy0, float wy1, float* __restrict__ out6) {
+                                                    float wx0, float wx1, float wy0, float wy1, const float* __restrict__ lut,
+                                                    float* __restrict__ out6) {
   uint32_t iw[3], bw[3];
 #pragma unroll
   for (int w = 0; w < 3; ++w) {
@@ -236,209 +255,268 @@ __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__
       const uint32_t vi = (iw[kk >> 2] >> ((kk & 3) * 8)) & 0xffu;
       const uint32_t vb = (bw[kk >> 2] >> ((kk & 3) * 8)) & 0xffu;
       const bool in = (code >> t) & 1u;
-      gv[t] = to_unit(in ? vi : vb);
-      lv[t] = in ? to_norm(vi, c) : c_clip_mean[c];
+      gv[t] = __ldg(lut + (in ? vi : vb));
+      lv[t] = in ? __ldg(lut + 256 + 256 * c + vi) : c_clip_mean[c];
     }
     out6[3 + c] = __fdiv_rn(__fsub_rn(bilerp(gv[0], gv[1], gv[2], gv[3], wx0, wx1, wy0, wy1), c_in_mean[c]), c_in_std[c]);
     out6[c] = bilerp(lv[0], lv[1], lv[2], lv[3], wx0, wx1, wy0, wy1);
   }
 }
 
-constexpr int kPrepQueue = 3072;    // boundary pixels a CTA can defer (entry = k << 16 | local pixel << 4 | tap code)
+constexpr int kPrepQueue = 3072;    // boundary pixels a CTA can defer per stage (entry = k << 16 | local pixel << 4 | tap code)
+constexpr int kPrepStages = 3;      // shared-memory ring of bit-row stages
+constexpr int kPrepSubDefault = 8;  // masks per stage (PrepParams::sub; HGL_PREP_SUB overrides for tuning)
 
-// One CTA = 256 pixel groups (PX adjacent pixels each) of one image x `chunk` masks.
-//   P0  the bit rows the tile touches, for all masks of the chunk, are copied to shared memory with fully independent
-//       coalesced loads (one exposed memory latency per CTA instead of one per mask), the FG/BG answers go to registers
-//   P1  per mask: window from shared memory, FG/BG decision for the whole group, stores.  No global load in the loop.
-//       Pixels on the mask outline get a placeholder and are queued.
-//   P2  dense fix-up: one thread per queued pixel evaluates the exact formula and patches the freshly written line (L2 hit)
-template <bool kBF16, int PX>
-__global__ void __launch_bounds__(kPrepThreads, (kBF16 && PX == 4) ? 4 : 2) prep_main_kernel(const PrepParams p) {
-  extern __shared__ __align__(16) uint32_t sm_prep[];
-  __shared__ int q_count;
-  constexpr int kTilePx = kPrepThreads * PX;
-  uint32_t* queue = sm_prep;                       // [kPrepQueue]
-  uint32_t* stage = sm_prep + kPrepQueue;          // [chunk][nrows][WW]
+// Thread -> pixel map.  A lane owns PX adjacent output pixels (one 16-byte store per plane); the 32 lanes of a warp form a
+// 2-D patch of gw groups x gh rows (gw * gh = 32) and the cw warps of a CTA sit side by side, so a CTA covers a band of gh
+// output rows.  Compared with a warp = one long row strip, a mask outline crosses far fewer patches than strips, so the
+// (longer) mixed-group path runs for ~10 % of the warp iterations instead of ~30 %.
+struct PrepGeom {
+  int gw, gh, cw, nbx;     // groups per patch row, rows per patch, warps (patches) per CTA, CTAs per band
+};
+__device__ __forceinline__ void prep_pixel_of(const PrepGeom& gm, int bxi, int byi, int t, int PX, int& i, int& j0) {
+  const int warp = t >> 5, lane = t & 31;
+  const int gr = lane / gm.gw, gc = lane - gr * gm.gw;
+  i = byi * gm.gh + gr;
+  j0 = ((bxi * gm.cw + warp) * gm.gw + gc) * PX;
+}
+
+// One CTA = a band tile of one image x a span of masks (blockIdx.z-th share of the image's masks), processed as a pipeline
+// of stages of kPrepSub masks:
+//   fill   the bit rows the band touches, for the masks of a stage, land in shared memory.  kTMA: one thread issues a 1-D
+//          bulk async copy (cp.async.bulk, SASS UBLKCP) per mask onto the stage's mbarrier, kPrepStages stages ahead of the
+//          consumer, so the load latency is hidden behind the stores of earlier stages; !kTMA (rows not 16-byte aligned):
+//          cooperative coalesced loads, one exposed latency per stage.
+//   P1     per mask: window from shared memory, FG/BG decision for the whole group, 6 streaming stores.  No global load in
+//          the loop; the FG/BG answers sit in registers for the CTA's whole span.  Groups cut by the outline are merged
+//          with two AND/compare per pixel; pixels whose own four taps straddle the outline get a placeholder and are queued.
+//   P2     dense fix-up per stage: one thread per queued pixel evaluates the exact formula and patches the freshly written
+//          line (L2 hit); a full queue makes the owning thread patch its pixel itself right after its store
+template <bool kBF16, int PX, bool kTMA>
+__global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepParams p) {
+  extern __shared__ __align__(128) uint8_t sm_prep[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages] (64 bytes reserved)
+  uint32_t* queue = reinterpret_cast<uint32_t*>(sm_prep + 64);                 // [kPrepQueue]
+  uint32_t* stage_base = queue + kPrepQueue;                                   // [kPrepStages][kPrepSub][stage_rows * WW], 16-byte aligned
+  __shared__ int q_count[2];
+  const float* lut = p.lut;
+  const int nthreads = blockDim.x;
 
   const int H = p.H, W = p.W, S = p.S, WW = p.WW;
-  const int SS = S * S, tpr = S / PX;
+  const int SS = S * S;
+  const PrepGeom gm = {p.gw, p.gh, p.cw, p.nbx};
+  const int bxi = blockIdx.x % gm.nbx, byi = blockIdx.x / gm.nbx;
   const int b = blockIdx.y, tid = threadIdx.x;
   int n_lo = 0, n_hi = p.M;
   if (p.mask_off) { n_lo = p.mask_off[b]; n_hi = p.mask_off[b + 1]; }
-  n_lo += blockIdx.z * p.chunk;
-  n_hi = min(n_hi, n_lo + p.chunk);
+  {
+    const int per = (n_hi - n_lo + (int)gridDim.z - 1) / (int)gridDim.z;       // this CTA's share of the image's masks
+    n_lo += blockIdx.z * per;
+    n_hi = min(n_hi, n_lo + per);
+  }
   if (n_lo >= n_hi) return;                                          // uniform for the whole CTA
   const int cnt = n_hi - n_lo;
+  const int kPrepSub = p.sub;
+  const int nst = (cnt + kPrepSub - 1) / kPrepSub;
 
-  const int tile0 = blockIdx.x * kTilePx;                            // first pixel of the tile
-  const int row_first = tile0 / S, row_last = min(tile0 + kTilePx - 1, SS - 1) / S;
+  const int row_first = byi * gm.gh, row_last = min(S, row_first + gm.gh) - 1;   // output rows of the band
   const int ylo = make_taps(row_first, H, S).i0;
   const Taps tl = make_taps(row_last, H, S);
   const int nrows = tl.i0 + tl.d - ylo + 1;
   const size_t mask_words = (size_t)H * WW;
-  {  // ---- P0
-    const int per_mask = nrows * WW;
-    const uint32_t* src = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW;
-    for (int t = tid; t < cnt * per_mask; t += kPrepThreads) {
-      const int k = t / per_mask, o = t - k * per_mask;
-      stage[t] = __ldg(src + (size_t)k * mask_words + o);
+  const int per_mask = nrows * WW;                                   // words of one mask inside a stage
+  const int stage_words = p.stage_words;                             // ring pitch (host: kPrepSub * max rows * WW)
+  const uint32_t* src0 = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW;
+
+  // stage fill: masks [c*kPrepSub, ...) of the span into ring slot c % kPrepStages
+  auto issue = [&](int c) {                                          // kTMA: called by one thread
+    const int c0 = c * kPrepSub, cn = min(kPrepSub, cnt - c0);
+    uint32_t* dst = stage_base + (size_t)(c % kPrepStages) * stage_words;
+    uint64_t* bar = bars + (c % kPrepStages);
+    mbar_expect_tx(bar, (uint32_t)(cn * per_mask * 4));
+    for (int k = 0; k < cn; ++k) bulk_g2s(dst + k * per_mask, src0 + (size_t)(c0 + k) * mask_words, (uint32_t)(per_mask * 4), bar);
+  };
+  if (kTMA) {
+    if (tid == 0) {
+      for (int s = 0; s < kPrepStages; ++s) mbar_init(bars + s, 1);
+      mbar_fence_init();
     }
-    if (tid == 0) q_count = 0;
   }
-  const int pg = blockIdx.x * kPrepThreads + tid;                    // pixel group inside the image
-  const bool live = pg < SS / PX;
-  const int i = live ? pg / tpr : 0, j0 = live ? (pg - i * tpr) * PX : 0;
+  if (tid == 0) { q_count[0] = 0; q_count[1] = 0; }
+  __syncthreads();
+  if (kTMA && tid == 0)
+    for (int c = 0; c < min(kPrepStages, nst); ++c) issue(c);
+
+  int i, j0;
+  prep_pixel_of(gm, bxi, byi, tid, PX, i, j0);
+  const bool live = i < S;                                           // partial last band
+  if (!live) { i = S - 1; }
   const Taps ty = make_taps(i, H, S);
   const int bx = make_taps(j0, W, S).i0;
   uint32_t tapmask = 0;
-  uint64_t xpack = 0;                // per pixel 5 bits (x0 - bx) + 1 bit (dx)
-  if (p.narrow) {
+  uint32_t tm[PX];                   // per pixel: the two tap columns as bits of the 32-bit window starting at bx
 #pragma unroll
-    for (int q = 0; q < PX; ++q) {
+  for (int q = 0; q < PX; ++q) {
+    tm[q] = 0;
+    if (p.narrow) {
       const Taps tx = make_taps(j0 + q, W, S);
-      tapmask |= (1u << (tx.i0 - bx)) | (1u << (tx.i0 + tx.d - bx));
-      xpack |= (uint64_t)((tx.i0 - bx) | (tx.d << 5)) << (6 * q);
+      tm[q] = (1u << (tx.i0 - bx)) | (1u << (tx.i0 + tx.d - bx));
+      tapmask |= tm[q];
     }
   }
   const int wi = bx >> 5, sh = bx & 31;
   const int wi1 = min(wi + 1, WW - 1);                               // clamped: bits beyond the row are never selected
   Pack<kBF16, PX> ans[12];
   const size_t px0 = (size_t)i * S + j0;
-  if (live) {
 #pragma unroll
-    for (int k = 0; k < 12; ++k) ans[k].load(p.planes, ((size_t)b * 12 + k) * SS + px0);
-  }
-  __syncthreads();
+  for (int k = 0; k < 12; ++k) ans[k].load(p.planes, ((size_t)b * 12 + k) * SS + px0);
 
-  // ---- P1
   constexpr size_t kElem = kBF16 ? 2 : 4;
   const size_t plane_bytes = (size_t)SS * kElem;
   uint8_t* lp = reinterpret_cast<uint8_t*>(p.local_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
   uint8_t* gp = reinterpret_cast<uint8_t*>(p.global_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
-  const uint32_t* s0 = stage + (ty.i0 - ylo) * WW;                   // tap rows inside the stage of mask 0
-  const uint32_t* s1 = s0 + ty.d * WW;
-  const int stride = nrows * WW;
-  for (int k = 0; live && k < cnt; ++k, s0 += stride, s1 += stride) {
-    uint32_t a0 = 0, a1 = 0;
-    bool uniform = false, inside = false;
-    if (p.narrow) {
-      a0 = __funnelshift_r(s0[wi], s0[wi1], sh);
-      a1 = __funnelshift_r(s1[wi], s1[wi1], sh);
-      const uint32_t t0 = a0 & tapmask, t1 = a1 & tapmask;
-      inside = (t0 == tapmask) && (t1 == tapmask);
-      uniform = inside || ((t0 | t1) == 0u);
-    }
-    Pack<kBF16, PX> ol[3], og[3];
-    if (uniform) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
-          ol[c].w[w] = inside ? ans[0 + c].w[w] : ans[6 + c].w[w];
-          og[c].w[w] = inside ? ans[3 + c].w[w] : ans[9 + c].w[w];
-        }
-      }
-    } else {
-      // mixed group: per-pixel FG/BG merge with bit masks; true boundary pixels keep the BG placeholder and are queued
-      uint32_t codes = 0;                 // 4 bits per pixel
-#pragma unroll
-      for (int q = 0; q < PX; ++q) {
-        uint32_t code;
-        if (p.narrow) {
-          const int oa = (int)(xpack >> (6 * q)) & 31, ob = oa + ((int)(xpack >> (6 * q + 5)) & 1);
-          code = ((a0 >> oa) & 1u) | (((a0 >> ob) & 1u) << 1) | (((a1 >> oa) & 1u) << 2) | (((a1 >> ob) & 1u) << 3);
-        } else {
-          const Taps tx = make_taps(j0 + q, W, S);
-          const int xa = tx.i0, xb = tx.i0 + tx.d;
-          code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
-                 (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
-        }
-        codes |= code << (4 * q);
-        if (code != 0u && code != 15u) {
-          const int slot = atomicAdd(&q_count, 1);
-          if (slot < kPrepQueue) queue[slot] = ((uint32_t)k << 16) | ((uint32_t)(tid * PX + q) << 4) | code;
-        }
-      }
-#pragma unroll
-      for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
-        uint32_t m;                        // all-ones in the lanes of pixels that are fully inside
-        if (kBF16) m = ((((codes >> (8 * w)) & 15u) == 15u) ? 0x0000ffffu : 0u) | ((((codes >> (8 * w + 4)) & 15u) == 15u) ? 0xffff0000u : 0u);
-        else m = (((codes >> (4 * w)) & 15u) == 15u) ? 0xffffffffu : 0u;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          ol[c].w[w] = (ans[0 + c].w[w] & m) | (ans[6 + c].w[w] & ~m);
-          og[c].w[w] = (ans[3 + c].w[w] & m) | (ans[9 + c].w[w] & ~m);
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      ol[c].store(lp + (size_t)c * plane_bytes);
-      og[c].store(gp + (size_t)c * plane_bytes);
-    }
-    lp += 3 * plane_bytes; gp += 3 * plane_bytes;
-  }
+  const int row_off0 = (ty.i0 - ylo) * WW, row_off1 = row_off0 + ty.d * WW;
 
-  // ---- P2: dense fix-up of the queued boundary pixels
-  __syncthreads();
-  const int nq_all = q_count;
-  const int nq = min(nq_all, kPrepQueue);
-  for (int e = tid; e < nq; e += kPrepThreads) {
-    const uint32_t ent = queue[e];
-    const uint32_t code = ent & 15u;
-    const int lpx = (ent >> 4) & 0xfff, k = ent >> 16;
-    const int gpx = tile0 + lpx;                       // pixel inside the image
-    const int pi = gpx / S, pj = gpx - pi * S;
+  // exact value of one pixel whose taps straddle the outline of mask n_lo + kk; overwrites the placeholder
+  auto patch = [&](int kk, int pi, int pj, uint32_t code) {
+    const int gpx = pi * S + pj;
     const Taps tyy = make_taps(pi, H, S), txx = make_taps(pj, W, S);
     float o6[6];
-    prep_boundary_pixel(p.taps, (size_t)b * 6 * SS + gpx, SS, code, txx.w0, txx.w1, tyy.w0, tyy.w1, o6);
-    const size_t o = ((size_t)(n_lo + k) * 3) * SS + gpx;
+    prep_boundary_pixel(p.taps, (size_t)b * 6 * SS + gpx, SS, code, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
+    const size_t o = ((size_t)(n_lo + kk) * 3) * SS + gpx;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int ch = 0; ch < 3; ++ch) {
       if (kBF16) {
-        reinterpret_cast<__nv_bfloat16*>(p.local_out)[o + (size_t)c * SS] = __float2bfloat16_rn(o6[c]);
-        reinterpret_cast<__nv_bfloat16*>(p.global_out)[o + (size_t)c * SS] = __float2bfloat16_rn(o6[3 + c]);
+        reinterpret_cast<__nv_bfloat16*>(p.local_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[ch]);
+        reinterpret_cast<__nv_bfloat16*>(p.global_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[3 + ch]);
       } else {
-        reinterpret_cast<float*>(p.local_out)[o + (size_t)c * SS] = o6[c];
-        reinterpret_cast<float*>(p.global_out)[o + (size_t)c * SS] = o6[3 + c];
+        reinterpret_cast<float*>(p.local_out)[o + (size_t)ch * SS] = o6[ch];
+        reinterpret_cast<float*>(p.global_out)[o + (size_t)ch * SS] = o6[3 + ch];
       }
     }
-  }
-  if (nq_all > kPrepQueue) {
-    // queue overflow (pathological outlines): rescan the whole tile x chunk, skipping what the queue already covered is
-    // not possible, so every boundary pixel is simply re-evaluated in place (idempotent)
-    for (int t = tid; t < cnt * kTilePx; t += kPrepThreads) {
-      const int k = t / kTilePx, lpx = t - k * kTilePx;
-      const int gpx = tile0 + lpx;
-      if (gpx >= SS) continue;
-      const int pi = gpx / S, pj = gpx - pi * S;
-      const Taps tyy = make_taps(pi, H, S), txx = make_taps(pj, W, S);
-      const uint32_t* q0 = stage + (size_t)k * stride + (tyy.i0 - ylo) * WW;
-      const uint32_t* q1 = q0 + tyy.d * WW;
-      const int xa = txx.i0, xb = txx.i0 + txx.d;
-      const uint32_t code = ((q0[xa >> 5] >> (xa & 31)) & 1u) | (((q0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
-                            (((q1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((q1[xb >> 5] >> (xb & 31)) & 1u) << 3);
-      if (code == 0u || code == 15u) continue;
-      float o6[6];
-      prep_boundary_pixel(p.taps, (size_t)b * 6 * SS + gpx, SS, code, txx.w0, txx.w1, tyy.w0, tyy.w1, o6);
-      const size_t o = ((size_t)(n_lo + k) * 3) * SS + gpx;
+  };
+
+  for (int c = 0; c < nst; ++c) {
+    const int c0 = c * kPrepSub, cn = min(kPrepSub, cnt - c0);
+    uint32_t* stage = stage_base + (size_t)(c % kPrepStages) * stage_words;
+    int* qc = &q_count[c & 1];
+    if (kTMA) {
+      mbar_wait(bars + (c % kPrepStages), (uint32_t)((c / kPrepStages) & 1));
+    } else {
+      const uint32_t* src = src0 + (size_t)c0 * mask_words;
+      for (int t = tid; t < cn * per_mask; t += nthreads) {
+        const int k = t / per_mask, o = t - k * per_mask;
+        stage[t] = __ldg(src + (size_t)k * mask_words + o);
+      }
+      __syncthreads();
+    }
+
+    // ---- P1
+    const uint32_t* s0 = stage + row_off0;                           // tap rows inside the stage of mask 0
+    const uint32_t* s1 = stage + row_off1;
+    for (int k = 0; live && k < cn; ++k, s0 += per_mask, s1 += per_mask) {
+      Pack<kBF16, PX> ol[3], og[3];
+      bool uniform = false, inside = false;
+      uint32_t X = 0, Y = 0, overflow_any = 0;
+      if (p.narrow) {
+        const uint32_t a0 = __funnelshift_r(s0[wi], s0[wi1], sh);
+        const uint32_t a1 = __funnelshift_r(s1[wi], s1[wi1], sh);
+        X = a0 & a1; Y = a0 | a1;                                    // bit set: column inside on both / on either tap row
+        inside = (X & tapmask) == tapmask;
+        uniform = inside || ((Y & tapmask) == 0u);
+      }
+      if (uniform) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (kBF16) {
-          reinterpret_cast<__nv_bfloat16*>(p.local_out)[o + (size_t)c * SS] = __float2bfloat16_rn(o6[c]);
-          reinterpret_cast<__nv_bfloat16*>(p.global_out)[o + (size_t)c * SS] = __float2bfloat16_rn(o6[3 + c]);
-        } else {
-          reinterpret_cast<float*>(p.local_out)[o + (size_t)c * SS] = o6[c];
-          reinterpret_cast<float*>(p.global_out)[o + (size_t)c * SS] = o6[3 + c];
+        for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+          for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
+            ol[ch].w[w] = inside ? ans[0 + ch].w[w] : ans[6 + ch].w[w];
+            og[ch].w[w] = inside ? ans[3 + ch].w[w] : ans[9 + ch].w[w];
+          }
+        }
+      } else {
+        // mixed group: per-pixel FG/BG merge with bit masks; pixels whose own taps straddle the outline keep the BG
+        // placeholder and are queued with their 4-bit tap code
+        uint32_t in_bits = 0;               // bit q: pixel q fully inside
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          bool in_q, bnd_q;
+          if (p.narrow) {
+            in_q = (X & tm[q]) == tm[q];
+            bnd_q = !in_q && (Y & tm[q]) != 0u;
+          } else {
+            const Taps tx = make_taps(j0 + q, W, S);
+            const int xa = tx.i0, xb = tx.i0 + tx.d;
+            const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
+                                  (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
+            in_q = code == 15u; bnd_q = code != 15u && code != 0u;
+          }
+          in_bits |= (in_q ? 1u : 0u) << q;
+          if (bnd_q) {                                               // rare: a pixel ON the outline
+            const Taps tx = make_taps(j0 + q, W, S);
+            const int xa = tx.i0, xb = tx.i0 + tx.d;
+            const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
+                                  (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
+            const int slot = atomicAdd(qc, 1);
+            if (slot < kPrepQueue) queue[slot] = ((uint32_t)k << 16) | ((uint32_t)(tid * PX + q) << 4) | code;
+            else overflow_any |= 1u << q;                                  // queue full: this thread patches the pixel itself below
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
+          uint32_t m;                        // all-ones in the lanes of pixels that are fully inside
+          if (kBF16) m = (((in_bits >> (2 * w)) & 1u) ? 0x0000ffffu : 0u) | (((in_bits >> (2 * w + 1)) & 1u) ? 0xffff0000u : 0u);
+          else m = ((in_bits >> w) & 1u) ? 0xffffffffu : 0u;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            ol[ch].w[w] = (ans[0 + ch].w[w] & m) | (ans[6 + ch].w[w] & ~m);
+            og[ch].w[w] = (ans[3 + ch].w[w] & m) | (ans[9 + ch].w[w] & ~m);
+          }
         }
       }
+      if (!(p.debug & 2)) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          ol[ch].store(lp + (size_t)ch * plane_bytes);
+          og[ch].store(gp + (size_t)ch * plane_bytes);
+        }
+      } else if (ol[0].w[0] == 0x12345u && og[2].w[1] == 0x54321u) {
+        ol[0].store(lp);
+      }
+      if (overflow_any) {                                            // queue full (pathological outlines): same thread, program order
+        for (int q = 0; q < PX; ++q) {
+          if (!((overflow_any >> q) & 1u)) continue;
+          const Taps tx = make_taps(j0 + q, W, S);
+          const int xa = tx.i0, xb = tx.i0 + tx.d;
+          const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
+                                (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
+          patch(c0 + k, i, j0 + q, code);
+        }
+      }
+      lp += 3 * plane_bytes; gp += 3 * plane_bytes;
     }
+    // ---- P2: dense fix-up of the queued boundary pixels of this stage.  (A barrier per stage measured faster than
+    //      barrier-free ring slots with one fix-up pass per CTA: it keeps the CTA's warps writing the same lines together
+    //      and the patched lines are still in L2.)
+    __syncthreads();
+    const int nq = (p.debug & 1) ? 0 : min(*qc, kPrepQueue);
+    for (int e = tid; e < nq; e += nthreads) {
+      const uint32_t ent = queue[e];
+      const int lpx = (ent >> 4) & 0xfff;
+      int pi, pj0;
+      prep_pixel_of(gm, bxi, byi, lpx / PX, PX, pi, pj0);
+      patch(c0 + (int)(ent >> 16), pi, pj0 + lpx % PX, ent & 15u);
+    }
+    if (tid == 0) q_count[(c + 1) & 1] = 0;            // the other counter: nobody touches it between the two barriers
+    __syncthreads();                                   // stage slot and queue are free again
+    if (kTMA && tid == 0 && c + kPrepStages < nst) issue(c + kPrepStages);
   }
 }
 
 struct PrepWs {
   void* planes;
   uint32_t* taps;
+  float* lut;
   size_t bytes;
 };
 static PrepWs prep_carve(void* ws, int B, int S, int out_dtype) {
@@ -449,6 +527,7 @@ static PrepWs prep_carve(void* ws, int B, int S, int out_dtype) {
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   w.planes = base + take((size_t)B * 12 * SS * elem);
   w.taps = reinterpret_cast<uint32_t*>(base + take((size_t)B * 6 * SS * 4));
+  w.lut = reinterpret_cast<float*>(base + take(1024 * 4));
   w.bytes = off;
   return w;
 }
@@ -499,47 +578,72 @@ extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_
   PrepWs ws = prep_carve(workspace, B, S, out_dtype);
   const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : nullptr;
   if (out_dtype == HGL_BF16)
-    prep_setup_kernel<true><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps);
+    prep_setup_kernel<true><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps, ws.lut);
   else
-    prep_setup_kernel<false><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps);
+    prep_setup_kernel<false><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps, ws.lut);
   int rc = launch_status("hgl_prep(setup)");
   if (rc != HGL_OK) return rc;
 
   PrepParams p;
-  p.bits = bits; p.mask_off = mask_off; p.planes = ws.planes; p.taps = ws.taps;
+  p.bits = bits; p.mask_off = mask_off; p.planes = ws.planes; p.taps = ws.taps; p.lut = ws.lut;
   p.local_out = local_out; p.global_out = global_out;
   p.B = B; p.M = M; p.H = H; p.W = W; p.S = S; p.WW = (W + 31) >> 5;
   const double sx = (double)W / (double)S;
   // pixels per thread: 8 (16-byte bf16 stores) when the 16 taps still fit one 32-bit window, else 4
   const int px = (out_dtype == HGL_BF16 && S % 8 == 0 && (int)(7.0 * sx) + 3 <= 31) ? 8 : kPrepPx;
   p.narrow = ((int)((px - 1) * sx) + 3 <= 31) ? 1 : 0;
-  // chunk = masks per CTA: bounded by the shared-memory stage of their bit rows, small enough for several waves
-  const int gx = ceil_div(SS / px, kPrepThreads);
+  // thread -> pixel map: patch = gw groups x gh rows per warp, cw patches side by side per CTA (see PrepGeom)
+  const int G = S / px;                                                       // groups per output row
+  int gw = 1;
+  while (gw < 8 && G % (gw * 2) == 0) gw *= 2;
+  const int gh = 32 / gw, ppr = G / gw;
+  int cw = 1;
+  for (int d = 1; d <= 8; ++d) if (ppr % d == 0) cw = d;
+  p.gw = gw; p.gh = gh; p.cw = cw; p.nbx = ppr / cw;
+  const int nby = ceil_div(S, gh);
+  const int threads = 32 * cw;
+  // the 2*px tap columns of a lane must fit one 32-bit window for the fast path
+  // grid: (band tiles, images, z) -- z splits an image's masks so that the launch fills whole waves of resident CTAs
+  const int gx = p.nbx * nby;
   const int per_image = (B == 1) ? M : std::min(max_n, M);
   const double sy = (double)H / (double)S;
-  const int tile_rows = (kPrepThreads * px + S - 1) / S + 1;                 // output rows a tile can touch
-  const int stage_rows = std::min(H, (int)(tile_rows * sy) + 3);            // source rows behind them
+  const int stage_rows = std::min(H, (int)(gh * sy) + 3);                    // source rows behind a band
   const size_t per_mask_bytes = (size_t)stage_rows * p.WW * 4;
-  HGL_REQUIRE(per_mask_bytes <= 96 * 1024, "hgl_prep: frame %dx%d too large for the bit-row stage", H, W);
-  int chunk = (int)std::min<size_t>(64, (40 * 1024) / per_mask_bytes);
-  chunk = std::max(chunk, 1);
-  const long slots = (long)sm_count() * 3;
-  while (chunk > 8 && (long)gx * B * ceil_div(per_image, chunk) < 3 * slots) chunk = (chunk * 3) / 4;
-  if (const char* ov = getenv("HGL_PREP_CHUNK")) chunk = std::max(1, atoi(ov));   // tuning hook
-  chunk = std::min(chunk, std::max(1, (int)((200 * 1024) / per_mask_bytes)));
-  p.chunk = chunk;
-  dim3 grid(gx, B, ceil_div(per_image, chunk));
+  int kPrepSub = kPrepSubDefault;
+  if (const char* sv = getenv("HGL_PREP_SUB")) kPrepSub = std::max(1, std::min(32, atoi(sv)));
+  while (kPrepSub > 1 && (size_t)kPrepStages * kPrepSub * per_mask_bytes > 96 * 1024) kPrepSub /= 2;
+  p.sub = kPrepSub;
+  HGL_REQUIRE((size_t)kPrepStages * kPrepSub * per_mask_bytes <= 160 * 1024, "hgl_prep: frame %dx%d too large for the bit-row stages", H, W);
+  p.stage_words = (int)(kPrepSub * per_mask_bytes / 4);
+  const size_t smem = 64 + (size_t)kPrepQueue * 4 + (size_t)kPrepStages * kPrepSub * per_mask_bytes;
+  const int resident = std::max(1, std::min(std::min(2 * kPrepThreads / threads, (int)((220 * 1024) / smem)), 65536 / (threads * 128)));
+  const long slots = (long)sm_count() * resident;
+  int gz = 1;
+  {
+    double best = -1.0;
+    const int gz_max = std::max(1, std::min(64, per_image / (2 * kPrepSub)));     // at least two stages per CTA
+    for (int z = 1; z <= gz_max; ++z) {
+      const long ctas = (long)gx * B * z;
+      const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots) - 0.004 * z;   // wave fill, mild bias to few splits
+      if (eff > best) { best = eff; gz = z; }
+    }
+  }
+  if (const char* ov = getenv("HGL_PREP_GZ")) gz = std::max(1, atoi(ov));         // tuning hook
+  p.debug = 0;
+  if (const char* dv = getenv("HGL_PREP_DEBUG")) p.debug = atoi(dv);              // profiling only: results are wrong when set
+  dim3 grid(gx, B, gz);
   HGL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "hgl_prep: batch too large for one launch (B=%d, max_n=%d)", B, max_n);
-  const size_t smem = (size_t)kPrepQueue * 4 + (size_t)chunk * per_mask_bytes;
+  // 1-D bulk copies need 16-byte aligned rows: WW % 4 == 0 and an aligned base; otherwise cooperative loads
+  const bool tma = (p.WW % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kPrepThreads, smem, st>>>(p);
+    kern<<<grid, threads, smem, st>>>(p);
   };
   if (out_dtype == HGL_BF16) {
-    if (px == 8) launch(prep_main_kernel<true, 8>);
-    else launch(prep_main_kernel<true, kPrepPx>);
+    if (px == 8) { if (tma) launch(prep_main_kernel<true, 8, true>); else launch(prep_main_kernel<true, 8, false>); }
+    else { if (tma) launch(prep_main_kernel<true, kPrepPx, true>); else launch(prep_main_kernel<true, kPrepPx, false>); }
   } else {
-    launch(prep_main_kernel<false, kPrepPx>);
+    if (tma) launch(prep_main_kernel<false, kPrepPx, true>); else launch(prep_main_kernel<false, kPrepPx, false>);
   }
   return launch_status("hgl_prep(main)");
 }
