@@ -284,6 +284,34 @@ def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, d
     return grid, area, out
 
 
+# ---- (b3') --------------------------------------------------------------------------------------------
+def mask_pool(weights: torch.Tensor, tokens: torch.Tensor, mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
+              normalize: bool = True, dtype: torch.dtype = torch.float32, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-space mask pooling on the tensor cores: out[n] = normalize(sum_l weights[n,l] * tokens[b(n)][l,:]).
+    weights f32 [M,L] or [M,g,g]; tokens bf16 [B,L,D] (or [L,D] for one image).  Returns [M,D] of `dtype`."""
+    _req(weights, torch.float32, "weights")
+    w = weights.reshape(weights.shape[0], -1)
+    tok = tokens[None] if tokens.dim() == 2 else tokens
+    _req(tok, torch.bfloat16, "tokens", 3)
+    M, L = w.shape
+    B, Lt, D = tok.shape
+    if Lt != L:
+        raise ValueError(f"weights have {L} cells per mask, tokens {Lt} per image")
+    moff = _offsets(mask_off, B, "mask_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    lib = _lib.load()
+    out = torch.empty((M, D), dtype=dtype, device=w.device)
+    need = lib.hgl_mask_pool_workspace_bytes(M, D, _dt(dtype))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=w.device)
+    check(lib.hgl_mask_pool(w.data_ptr(), tok.data_ptr(), _ptr(moff), B, M, max_n, L, D, int(bool(normalize)), _dt(dtype),
+                            out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_mask_pool")
+    return out
+
+
 # ---- (a6)-(a9),(a12) ----------------------------------------------------------------------------------
 def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, others: torch.Tensor, other_off: torch.Tensor,
                  boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],

@@ -128,6 +128,17 @@ HGL_API int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, in
                        const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
                        int max_n, float* score_gem, void* workspace, void* stream);
 
+/* ---- (b3') token-space mask pooling + L2 normalisation (tensor cores) ---------------------------------
+ * The masks x tokens x D contraction of the north star; token-space form of the pooling loop Hybridgl_main.py:218-223
+ * (S_in = (M~ . F^) . t) with the normalisation of model/backbone.py:79 fused:
+ *   pooled[n,:] = sum_l weights[n,l] * tokens[b(n)][l,:];   out[n,:] = normalize ? pooled / ||pooled||_2 : pooled
+ * weights f32 [M,L] (e.g. the soft grid masks of hgl_mask_grid, L = g*g); tokens bf16 [B,L,D] (D % 16 == 0);
+ * mask_off int32 [B+1] (NULL => B==1); out [M,D] of out_dtype.  bf16 x bf16 -> f32 on tcgen05 (weights are rounded to
+ * bf16 once).  workspace: hgl_mask_pool_workspace_bytes(M, D, out_dtype) bytes, 16-byte aligned (may be NULL for f32 output). */
+HGL_API int64_t hgl_mask_pool_workspace_bytes(int M, int D, int out_dtype);
+HGL_API int hgl_mask_pool(const float* weights, const void* tokens, const int32_t* mask_off, int B, int M, int max_n, int L, int D,
+                  int normalize, int out_dtype, void* out, void* workspace, void* stream);
+
 /* ---- (a6)-(a9),(a12) scoring, spatial-relationship re-ranking, per-expression argmax ----------------
  * Replaces Hybridgl_main.py:153-196 and :225-227 plus CLIPViTFM.calculate_score model/backbone.py:74-87 and
  * relation_boxes utils.py:240-268, one launch for a whole batch of images:

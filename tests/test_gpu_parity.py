@@ -307,3 +307,36 @@ def test_full_size_properties(ops):
     frac = area.double() / (cfg["h"] * cfg["w"])
     assert torch.allclose(grid.double().mean(dim=(1, 2)), frac, atol=2e-3)
     assert torch.all(grid[0] > 0.999999)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core mask pooling
+@pytest.mark.parametrize("B,n,L,D,dtype", [(1, 100, 196, 768, torch.float32), (2, 37, 196, 512, torch.float32), (1, 200, 576, 1024, torch.float32),
+                                           (3, 130, 49, 64, torch.float32), (1, 5, 16, 32, torch.bfloat16), (2, 150, 196, 768, torch.bfloat16)])
+def test_mask_pool_tcgen05_vs_oracle(ops, B, n, L, D, dtype):
+    """tcgen05 masks x tokens x D contraction + fused L2 norm vs the numpy oracle (bf16 operands, f32 accumulation:
+    tolerance 1e-3 relative on unit-length rows)."""
+    rng = np.random.default_rng(B * 1000 + n)
+    counts = [n] + [max(1, n // (i + 2)) for i in range(B - 1)]        # ragged
+    moff = np.cumsum([0] + counts).astype(np.int32)
+    M = int(moff[-1])
+    w = rng.random((M, L)).astype(np.float32); w[w < 0.4] = 0          # soft grid masks with exact zeros
+    tok = synth.bf16_round(rng.standard_normal((B, L, D)).astype(np.float32))
+    for normalize in (True, False):
+        got = ops.mask_pool(cu(w), cu(tok, torch.bfloat16), cu(moff) if B > 1 else None, max(counts), normalize=normalize, dtype=dtype)
+        got = got.float().cpu().numpy()
+        for b in range(B):
+            ref = O.mask_pool_tokens(w[moff[b]:moff[b + 1]], tok[b], normalize=normalize)
+            g = got[moff[b]:moff[b + 1]]
+            scale = np.abs(ref).max()
+            tol = (1e-3 if dtype == torch.float32 else 1e-2) * scale
+            np.testing.assert_allclose(g, ref, rtol=0, atol=tol, err_msg=f"image {b} normalize={normalize}")
+
+
+def test_mask_pool_from_grid_masks(ops):
+    """End of row (b): packed masks -> soft grid (hgl_mask_grid) -> tensor-core pooling of dense tokens."""
+    it = synth.make_item(91, 240, 320, 12, 0, with_features=False)
+    grid = ops.masks_to_grid(cu(it.masks), 14)
+    tok = synth.bf16_round(np.random.default_rng(3).standard_normal((196, 256)).astype(np.float32))
+    got = ops.mask_pool(grid, cu(tok, torch.bfloat16)).cpu().numpy()
+    ref = O.mask_pool_tokens(grid.cpu().numpy().reshape(12, -1), tok)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-3)

@@ -110,3 +110,35 @@ def test_heatmap_resize_aa_matches_reference(golden):
             np.testing.assert_allclose(got, c["heat_resized"], rtol=0, atol=2e-7)
             seen += 1
     assert seen >= 10
+
+
+def test_token_space_pooling_equals_pixel_space_pooling():
+    """Pins O.mask_pool_tokens (the tensor-core kernel's oracle) to the pinned pixel-space O.gem_pool:
+    if the heat-map is A = U h (U = bilinear up-sampling of a token-grid map h = F t), then for every mask
+    sum_p m[p] A[p] == (U^T m) . h == ((U^T m) F) . t  -- SURVEY.md Appendix A-2."""
+    rng = np.random.default_rng(5)
+    gh, gw, h, w, d, n = 6, 8, 24, 32, 16, 5
+    F = synth.bf16_round(rng.standard_normal((gh * gw, d)).astype(np.float32))
+    t = rng.standard_normal(d).astype(np.float32)
+    # U as an explicit [h*w, gh*gw] matrix: resize_bilinear applied to the basis maps
+    basis = np.eye(gh * gw, dtype=np.float32).reshape(gh * gw, gh, gw)
+    U = O.resize_bilinear(basis, h, w).reshape(gh * gw, h * w).T.astype(np.float64)
+    masks = synth.make_masks(rng, n, h, w, min_area=20)
+    heat = (U @ (F.astype(np.float64) @ t.astype(np.float64))).reshape(h, w)
+    s_in_pixel = (heat[None] * masks).reshape(n, -1).sum(1)
+    weights = (masks.reshape(n, -1).astype(np.float64) @ U).astype(np.float32)          # U^T m, one row per mask
+    # exact identity with unrounded weights ...
+    np.testing.assert_allclose((weights.astype(np.float64) @ F.astype(np.float64)) @ t, s_in_pixel, rtol=1e-5)
+    # ... and the oracle (weights rounded to bf16 like the kernel's A operand) within bf16 accuracy
+    pooled = O.mask_pool_tokens(weights, F, normalize=False)
+    np.testing.assert_allclose(pooled.astype(np.float64) @ t, s_in_pixel, rtol=2e-2, atol=2e-2 * np.abs(s_in_pixel).max())
+    # closed form of Hybridgl_main.py:220 from the pooled sums == gem_pool on the pixel map
+    black = 1.8
+    area = masks.reshape(n, -1).sum(1)
+    ref = O.gem_pool(heat.astype(np.float32), masks, black)
+    s_in = (weights.astype(np.float64) @ F.astype(np.float64)) @ t
+    got = (2 - black) * s_in / area - black * (heat.sum() - s_in) / (h * w - area)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+    # normalised rows have unit length
+    pn = O.mask_pool_tokens(weights, F, normalize=True)
+    np.testing.assert_allclose(np.linalg.norm(pn.astype(np.float64), axis=1), 1.0, rtol=1e-6)
