@@ -30,14 +30,17 @@ METRIC = "expressions/sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", type=int, default=2, help="BASELINE.json config index (1-based), default 2")
     ap.add_argument("--images", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
+                    help="tokens: pool dense patch tokens under the grid masks on the tensor cores (hgl_mask_pool) and score those; "
+                         "supplied: score hybrid features given as an input")
     return ap.parse_args()
 
 
@@ -59,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -173,7 +176,7 @@ def run_reference(args, cfg):
 def workload_name(cfg):
     return (f"RefCOCO-shaped synthetic batch: {cfg['images_per_gpu_per_step']} images/GPU/step, {cfg['h']}x{cfg['w']}, "
             f"{cfg['n_masks']} masks/image, {cfg['n_expr']} expressions/image, ViT-B/16 geometry (S={cfg['S']}, g={cfg['g']}, "
-            f"De={cfg['De']}), fusion_mode {cfg['fusion_mode']} (features supplied)")
+            f"De={cfg['De']}), fusion_mode {cfg['fusion_mode']}; features: dense tokens pooled per mask (hgl_mask_pool) unless --features supplied")
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -187,6 +190,8 @@ def algorithmic_bytes(cfg, B, prep_bytes):
         "prep": M * H * ((W + 31) // 32) * 4 + 2 * B * H * W * 3 + 2 * M * 3 * S * S * prep_bytes,
         # one pass over the packed masks (grid + pooling) + the heat-maps once (+ their row-prefix tables written once)
         "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + 2 * ET * H * W * 4 + ET * N * 4,
+        # tensor-core pooling of the dense tokens: soft masks f32 + tokens bf16 in, pooled rows bf16 out (flops: MASK_POOL_FLOPS)
+        "mask_pool": M * cfg["g"] ** 2 * 4 + B * cfg["g"] ** 2 * De * 2 + M * De * 2,
         "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
         "iou": 2 * 2 * ET * H * W,
     }
@@ -209,9 +214,10 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
-    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype)
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features)
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
-    batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev)
+    batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
+                                         grid=cfg["g"])
                for i in range(2)]
     max_n = cfg["n_masks"]
     torch.cuda.synchronize()
@@ -263,6 +269,7 @@ def run_ours(args, cfg):
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     alg = algorithmic_bytes(cfg, B, 2 if prep_dtype == torch.bfloat16 else 4)
+    world_local_masks = B * cfg["n_masks"]
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -274,6 +281,12 @@ def run_ours(args, cfg):
             ach = b / (avg_ms[k] * 1e-3) / 1e9
             kernels[k] = {"ms": round(avg_ms[k], 4), "algorithmic_bytes": b, "achieved_gbs": round(ach, 1), "frac": round(ach / peak_hbm, 4),
                           "share_of_step": round(avg_ms[k] / sum(avg_ms.values()), 4)}
+    if "mask_pool" in kernels:           # the tensor-core stage also gets its flop rate against the measured bf16 peak
+        flop = 2.0 * world_local_masks * cfg["g"] ** 2 * cfg["De"]
+        tf = flop / (kernels["mask_pool"]["ms"] * 1e-3) / 1e12
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        kernels["mask_pool"].update({"algorithmic_flop": flop, "achieved_tflops": round(tf, 2), "frac_tensor": round(tf / peak_tf, 5),
+                                     "tensor_peak_tflops": peak_tf})
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     roofline = {"kernel": f"hgl_{top}", "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak_hbm, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src}
@@ -295,7 +308,7 @@ def run_ours(args, cfg):
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": expr_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": METRIC,
-               "h2d_bytes_per_step": ScoringPath.h2d_bytes(host[0]), "d2h_bytes_per_step": path.d2h_bytes(),
+               "h2d_bytes_per_step": path.h2d_bytes(host[0]), "d2h_bytes_per_step": path.d2h_bytes(),
                "steps": args.e2e_steps, "api": "hybridgl_b200.pipeline.ScoringPath.run_host (pinned host tensors in / out)"}
         del out
 
@@ -310,7 +323,7 @@ def run_ours(args, cfg):
                 "config": {"workload": workload_name(cfg), "l2": "two alternating batches, masks alone are "
                            f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
                            **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": ScoringPath.LAUNCHES_PER_RUN * args.steps,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
                         "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}

@@ -18,7 +18,7 @@ import torch
 from . import ops
 
 # host->device inputs of one step and their dtypes (what a caller must provide per batch)
-INPUT_KEYS = ("image", "masks", "boxes", "target", "features", "sent", "noun", "others", "other_off", "heat",
+INPUT_KEYS = ("image", "masks", "boxes", "target", "features", "tokens", "sent", "noun", "others", "other_off", "heat",
               "dirflag", "relaflag", "black", "mask_off", "expr_off")
 # device->host results of one step
 OUTPUT_KEYS = ("score_clip", "score_gem", "idx_hybrid", "idx_final", "top_idx", "blended", "iu")
@@ -29,7 +29,13 @@ class ScoringPath:
 
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
-                 device: Optional[torch.device] = None):
+                 feature_source: str = "supplied", device: Optional[torch.device] = None):
+        """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
+        "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
+        under every proposal's soft grid mask on the tensor cores (hgl_mask_pool) and the pooled, normalised rows are scored."""
+        if feature_source not in ("supplied", "tokens"):
+            raise ValueError(feature_source)
+        self.feature_source = feature_source
         ops.device_ok()
         self.size, self.grid = size, grid
         self.prep_dtype, self.antialias, self.background = prep_dtype, antialias, background
@@ -74,7 +80,7 @@ class ScoringPath:
         ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
                                 dtype=self.prep_dtype, out=(local, glob), workspace=pws)
         self._mark("prep")
-        feats = batch["features"] if features is None else features
+        feats = features if features is not None else batch.get("features")
         E = batch["sent"].shape[0]
         need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n)
         ws = self._get("heat_ws", (need,), torch.uint8)
@@ -85,6 +91,10 @@ class ScoringPath:
             grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
             score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
         self._mark("grid_heat_pool")
+        if self.feature_source == "tokens" and features is None:
+            mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
+            feats = ops.mask_pool(grid, batch["tokens"], moff, max_n, normalize=True, dtype=torch.bfloat16, workspace=mws)
+            self._mark("mask_pool")
         sws = self._get("score_ws", (max(lib.hgl_score_select_workspace_bytes(B, E, max_n), 1),), torch.uint8)
         res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
                                batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha,
@@ -92,16 +102,23 @@ class ScoringPath:
         self._mark("score_select")
         iu = ops.iou_accumulate(masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
         self._mark("iou")
-        res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits)
+        res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
 
     # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), score_select 2 (text, score+select), iou 2
-    LAUNCHES_PER_RUN = 11
+    LAUNCHES_PER_RUN = 11      # + 1 (mask_pool) with feature_source="tokens"
+
+    def launches_per_run(self) -> int:
+        return self.LAUNCHES_PER_RUN + (1 if self.feature_source == "tokens" else 0)
+
+    def input_keys(self):
+        skip = "features" if self.feature_source == "tokens" else "tokens"
+        return tuple(k for k in INPUT_KEYS if k != skip)
 
     def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:
         """End-to-end call with HOST buffers (pinned): H2D of every input, the kernels, D2H of the results,
         then a stream synchronise.  This is what bench.py times as `e2e`."""
-        for k in INPUT_KEYS:
+        for k in self.input_keys():
             src = host_batch[k]
             dst = self._dev_in.get(k)
             if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
@@ -121,9 +138,8 @@ class ScoringPath:
         torch.cuda.current_stream().synchronize()
         return out
 
-    @staticmethod
-    def h2d_bytes(host_batch: Dict[str, torch.Tensor]) -> int:
-        return sum(host_batch[k].numel() * host_batch[k].element_size() for k in INPUT_KEYS)
+    def h2d_bytes(self, host_batch: Dict[str, torch.Tensor]) -> int:
+        return sum(host_batch[k].numel() * host_batch[k].element_size() for k in self.input_keys())
 
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._host_out.values())

@@ -186,7 +186,7 @@ CONFIGS = {
 # device-side generator for benchmark-sized batches (same shapes / statistics, torch RNG on the GPU)
 # --------------------------------------------------------------------------------------------------
 def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_expr: int, de: int,
-                      device="cuda", n_other: int = 2, pinned_host: bool = False):
+                      device="cuda", n_other: int = 2, pinned_host: bool = False, grid: int = 14):
     """RefCOCO-shaped batch laid out for the batched C ABI (ragged offsets, here uniform).
     Returns a dict of tensors on `device` (or pinned host tensors when pinned_host=True)."""
     import torch
@@ -224,6 +224,7 @@ def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_
     pick = torch.randint(0, N, (B,), generator=gen, device=device) + torch.arange(B, device=device) * N
     target = torch.roll(masks[pick], shifts=(3, -4), dims=(1, 2)).to(torch.uint8)       # [B,H,W]
     feats = torch.randn((M, de), generator=gen, device=device).to(torch.bfloat16)
+    tokens = torch.randn((B, grid * grid, de), generator=gen, device=device).to(torch.bfloat16)     # dense patch tokens in embedding space
     anchor = feats[torch.randint(0, N, (ET,), generator=gen, device=device)
                    + torch.arange(B, device=device).repeat_interleave(E) * N].float() * 0.25
     sent = (torch.randn((ET, de), generator=gen, device=device) + 1.5 * anchor).to(torch.bfloat16).float()
@@ -234,7 +235,7 @@ def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_
     dirflag = torch.randint(0, 6, (ET,), generator=gen, device=device).to(torch.int32)
     relaflag = torch.randint(0, 8, (ET,), generator=gen, device=device).to(torch.int32)
     black = torch.where(relaflag == 5, 1.95, torch.where(relaflag == 6, 1.5, 1.8)).to(torch.float32)
-    out = dict(image=image, masks=masks, boxes=boxes, target=target, features=feats, sent=sent, noun=noun, others=others,
+    out = dict(image=image, masks=masks, boxes=boxes, target=target, features=feats, tokens=tokens, sent=sent, noun=noun, others=others,
                other_off=other_off, heat=heat, dirflag=dirflag, relaflag=relaflag, black=black,
                mask_off=(torch.arange(B + 1, device=device) * N).to(torch.int32),
                expr_off=(torch.arange(B + 1, device=device) * E).to(torch.int32))

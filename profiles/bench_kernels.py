@@ -99,7 +99,37 @@ def prep_sweep():
         del loc, glo
 
 
+def mask_pool_sweep():
+    import json
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0)); bw_peak = float(peaks.get("hbm_gbs", 6650.0))
+    for name, B, n, L, D in (("cfg2 B=16", 16, 100, 196, 768), ("cfg2 B=256", 256, 100, 196, 768), ("cfg4 B=16", 16, 200, 576, 1024),
+                             ("cfg4 B=128", 128, 200, 576, 1024), ("cfg5 B=256", 256, 200, 196, 768)):
+        M = B * n
+        w = torch.rand((M, L), device="cuda"); w[w < 0.5] = 0
+        tok = torch.randn((B, L, D), device="cuda").to(torch.bfloat16)
+        moff = (torch.arange(B + 1, device="cuda") * n).to(torch.int32)
+        for dtype, ob in ((torch.float32, 4), (torch.bfloat16, 2)):
+            ws = torch.empty((M * D * 4 + 512,), dtype=torch.uint8, device="cuda")
+            fn = lambda: ops.mask_pool(w, tok, moff, n, normalize=True, dtype=dtype, workspace=ws)  # noqa: E731
+            best, med = timeit(fn)
+            flop = 2.0 * M * L * D
+            byts = M * L * 4 + B * L * D * 2 + M * D * ob
+            log(f"mask_pool {name} out={str(dtype)[6:]}: median {med * 1e3:.1f} us, {flop / med / 1e9:.1f} TFLOP/s ({flop / med / 1e9 / tf_peak * 100:.1f}% of measured bf16 peak), "
+                f"{byts / med / 1e6:.0f} GB/s algorithmic ({byts / med / 1e6 / bw_peak * 100:.1f}% of measured HBM peak), AI {flop / byts:.0f} flop/B")
+        del w, tok
+
+
 if __name__ == "__main__":
     ops.device_ok()
-    membw()
-    prep_sweep()
+    which = sys.argv[2:] or ["membw", "prep", "mask_pool"]
+    if "membw" in which:
+        membw()
+    if "prep" in which:
+        prep_sweep()
+    if "mask_pool" in which:
+        mask_pool_sweep()

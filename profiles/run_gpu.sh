@@ -11,12 +11,12 @@ timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; e
 tail -3 $out/${tag}_pytest.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
 tail -2 $out/${tag}_smoke.log
-timeout 400 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 cat $out/${tag}_bench.json
 # launch list (cold-cache, serialised: shares only)
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$KRE" -c 66 --csv --log-file $out/${tag}_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$KRE" -c 72 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 # full sections for one step of our kernels (second pass over the path: skip the first step's launches)
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s ${NCU_SKIP:-11} -c ${NCU_COUNT:-11} -o $out/${tag}_prof -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-12} -o $out/${tag}_prof -f \
     python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $out | tail -12

@@ -340,3 +340,23 @@ def test_mask_pool_from_grid_masks(ops):
     got = ops.mask_pool(grid, cu(tok, torch.bfloat16)).cpu().numpy()
     ref = O.mask_pool_tokens(grid.cpu().numpy().reshape(12, -1), tok)
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-3)
+
+
+def test_pipeline_token_features_vs_oracle(ops):
+    """ScoringPath(feature_source="tokens"): grid masks -> tcgen05 pooling -> scoring, against the oracle chain."""
+    from hybridgl_b200.pipeline import ScoringPath
+    B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
+    batch = synth.make_batch_device(77, B, h, w, n, e, de, device=DEV, grid=g)
+    path = ScoringPath(size=32, grid=g, prep_dtype=torch.float32, feature_source="tokens")
+    res = path.run(batch, n)
+    torch.cuda.synchronize()
+    masks = batch["masks"].cpu().numpy(); tok = batch["tokens"].float().cpu().numpy()
+    feats = res["features"].float().cpu().numpy()
+    for b in range(B):
+        grid = O.mask_to_grid(masks[b * n:(b + 1) * n], g, antialias=True).reshape(n, -1)
+        ref = O.mask_pool_tokens(grid, tok[b])
+        np.testing.assert_allclose(feats[b * n:(b + 1) * n], ref, rtol=0, atol=1.5e-2)          # bf16 output rows of unit length
+        for j in range(e):
+            ei = b * e + j
+            sc = O.calculate_score(feats[b * n:(b + 1) * n], (0.5 * batch["sent"][ei] + 0.5 * batch["noun"][ei]).cpu().numpy()[None], 100.0)[:, 0]
+            np.testing.assert_allclose(res["score_clip"][ei, :n].cpu().numpy(), sc, rtol=1e-3, atol=1e-3)
