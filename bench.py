@@ -111,11 +111,13 @@ def _oracle_one_image(args):
     t0 = time.perf_counter()
     blur = O.gaussian_blur_u8(it.image)
     O.prep(it.image, blur, it.masks, cfg["S"])
-    O.mask_to_grid(it.masks, cfg["g"], antialias=True)
+    grid = O.mask_to_grid(it.masks, cfg["g"], antialias=True)
+    tokens = synth.bf16_round(np.random.default_rng(seed).standard_normal((cfg["g"] ** 2, cfg["De"])).astype(np.float32))
+    feats = O.mask_pool_tokens(grid.reshape(grid.shape[0], -1), tokens)            # dense tokens pooled under every soft grid mask
     cum = np.zeros(4, np.int64)
     for ex in it.expressions:
         sg = O.gem_pool(O.condition_heatmap(ex.heatmap, ex.dirflag), it.masks, O.black_for(ex.relaflag))
-        r = O.score_and_select(it.features, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag, score_gem=sg)
+        r = O.score_and_select(feats, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag, score_gem=sg)
         i0, u0, _ = O.compute_iou(it.masks[r["idx_hybrid"]], it.target)
         i1, u1, _ = O.compute_iou(it.masks[r["idx_final"]], it.target)
         cum += np.array([i0, u0, i1, u1])

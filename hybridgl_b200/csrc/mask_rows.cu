@@ -107,70 +107,66 @@ static HeatWs heat_carve(void* ws, int E, int H, int W) {
   return h;
 }
 
-// One warp per (expression, row): coalesced load into shared memory, each lane scans its own contiguous chunk, one
-// warp scan of the 32 chunk totals, coalesced store of the exclusive prefix.  Row 0's warp also emits the ramp prefix.
-// The ramp row is evaluated once per CTA (shared memory); the lane -> (chunk, offset) map is advanced incrementally.
+// One warp per (expression, row), 128 pixels per round: a lane owns 4 adjacent pixels (one 16-byte load, one 16-byte store),
+// scans them in registers, the 32 lane totals go through one shuffle scan, and a running carry links the rounds.  Row 0's
+// warp also emits the ramp prefix.  The ramp row is evaluated once per CTA (shared memory).
 __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag,
                                                                       int H, int W, int Wp, float* __restrict__ cr, float* __restrict__ rp,
                                                                       float* __restrict__ rowstat) {
-  extern __shared__ float smp[];
+  extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]
   const int e = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = (W + 31) >> 5;                      // elements per lane chunk
-  const int stride = c | 1;                         // odd: lane-chunk walks are bank-conflict free
-  float* ramp = smp;                                // [32*c]
-  float* buf = smp + 32 * c + (size_t)warp * 32 * stride;
+  const int W128 = (W + 127) & ~127;
   const int dir = dirflag[e];
-  for (int x = threadIdx.x; x < 32 * c; x += blockDim.x) ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
+  for (int x = threadIdx.x; x < W128; x += blockDim.x) ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
   __syncthreads();
   const int y = blockIdx.x * kPrefWarps + warp;
   if (y >= H) return;                               // whole warp; no block-level barrier below
   const float* A = heat + ((size_t)e * H + y) * W;
-  const int dq = 32 / c, dr = 32 - dq * c;          // x += 32  ==>  (q, r) += (dq, dr) with carry
-  const int q0 = lane / c, r0 = lane - q0 * c;
+  const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
   for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
-    float mn = INFINITY, mx = -INFINITY;
-    int q = q0, r = r0;
-    for (int x = lane; x < 32 * c; x += 32) {
-      float v = 0.f;
-      if (x < W) {
-        if (pass == 0) v = ramp[x];
-        else { const float a = __ldg(A + x); mn = fminf(mn, a); mx = fmaxf(mx, a); v = __fmul_rn(a, ramp[x]); }
-      }
-      buf[q * stride + r] = v;
-      q += dq; r += dr;
-      if (r >= c) { r -= c; ++q; }
-    }
-    __syncwarp();
-    float run = 0.f;
-    for (int k = 0; k < c; ++k) {
-      const float t = buf[lane * stride + k];
-      buf[lane * stride + k] = run;                 // exclusive prefix inside the chunk
-      run = __fadd_rn(run, t);
-    }
-    float incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float nb = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl = __fadd_rn(incl, nb);
-    }
-    float off = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive chunk offset = inclusive scan of the previous lane
-    if (lane == 0) off = 0.f;
-    const float total = __shfl_sync(0xffffffffu, incl, 31);
-    __syncwarp();
     float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
-    q = q0; r = r0;
-    for (int x = lane; x < 32 * c; x += 32) {
-      const float o = __shfl_sync(0xffffffffu, off, q);
-      if (x < W) dst[x] = __fadd_rn(o, buf[q * stride + r]);
-      q += dq; r += dr;
-      if (r >= c) { r -= c; ++q; }
+    float mn = INFINITY, mx = -INFINITY, carry = 0.f;
+    for (int x0 = 0; x0 < W; x0 += 128) {
+      const int x = x0 + 4 * lane;
+      const float4 r4 = *reinterpret_cast<const float4*>(ramp + x);
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pass == 0) { a[0] = r4.x; a[1] = r4.y; a[2] = r4.z; a[3] = r4.w; }
+      else {
+        float h4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && x + 3 < W) { const float4 v = __ldg(reinterpret_cast<const float4*>(A + x)); h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w; }
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = __ldg(A + x + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (x + q < W) { mn = fminf(mn, h4[q]); mx = fmaxf(mx, h4[q]); }
+        a[0] = __fmul_rn(h4[0], r4.x); a[1] = __fmul_rn(h4[1], r4.y); a[2] = __fmul_rn(h4[2], r4.z); a[3] = __fmul_rn(h4[3], r4.w);
+      }
+      const float p0 = a[0], p1 = __fadd_rn(p0, a[1]), p2 = __fadd_rn(p1, a[2]), p3 = __fadd_rn(p2, a[3]);
+      float incl = p3;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = __fadd_rn(incl, nb);
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);            // sum of the lanes before this one (exact, no subtraction)
+      if (lane == 0) excl = 0.f;
+      const float base = __fadd_rn(carry, excl);                     // exclusive prefix of this lane's first pixel
+      const float4 o4 = make_float4(base, __fadd_rn(base, p0), __fadd_rn(base, p1), __fadd_rn(base, p2));
+      if (x + 3 < Wp) *reinterpret_cast<float4*>(dst + x) = o4;      // entries beyond W inside the padded row are never read
+      else {
+        const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (x + q < Wp) dst[x + q] = ov[q];
+      }
+      carry = __fadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
     }
-    if (lane == 0) dst[W] = total;
+    if (lane == 0 && (W & 127) == 0) dst[W] = carry;              // otherwise the lane that owns index W wrote it above
     if (pass == 1) {
       mn = warp_min(mn); mx = warp_max(mx);
       if (lane == 0) {
         float* o = rowstat + ((size_t)e * H + y) * 4;
-        o[0] = mn; o[1] = mx; o[2] = total; o[3] = 0.f;
+        o[0] = mn; o[1] = mx; o[2] = carry; o[3] = 0.f;
       }
     }
     __syncwarp();
@@ -210,7 +206,7 @@ __global__ void __launch_bounds__(128) heat_consts_kernel(const float* __restric
 constexpr int kBands = 4;                              // row bands (= independent warp tasks) per mask
 
 struct RowsScratch {         // global scratch of one launch (byte offsets 256-aligned)
-  int32_t* tickets;          // [M]            zero at launch
+  int32_t* tickets;          // [M + 1]        zero at launch; entry M is the task counter of the dynamic scheduler
   int32_t* pcnt;             // [M][kBands]    pixels per band
   float* pgrid;              // [M][kBands][g*g]
   float* pheat;              // [E][max_n][kBands][2]   (sum cr, sum rp) per band
@@ -221,7 +217,7 @@ static RowsScratch rows_carve(void* ws, int M, int g, int E, int max_n) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~size_t(255); return o; };
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
-  r.tickets = reinterpret_cast<int32_t*>(base + take((size_t)M * 4));
+  r.tickets = reinterpret_cast<int32_t*>(base + take((size_t)(M + 1) * 4));
   r.pcnt = reinterpret_cast<int32_t*>(base + take((size_t)M * kBands * 4));
   r.pgrid = reinterpret_cast<float*>(base + take((size_t)M * kBands * g * g * 4));
   r.pheat = reinterpret_cast<float*>(base + take((size_t)E * max_n * kBands * 2 * 4));
@@ -283,7 +279,12 @@ __global__ void __launch_bounds__(kRowsThreads) mask_rows_kernel(const RowsParam
   const bool vec = (WW & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bits) & 15) == 0;
   const float hw = (float)((size_t)H * W);
   const int total_tasks = p.M * kBands;
-  for (int task = blockIdx.x * (kRowsThreads / 32) + warp; task < total_tasks; task += gridDim.x * (kRowsThreads / 32)) {
+  // dynamic scheduling: masks differ a lot in how many rows they touch, so warps pull (mask, band) tasks from a counter
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = atomicAdd(p.sc.tickets + p.M, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= total_tasks) break;
     const int m = task / kBands, band = task - m * kBands;
     const int y_begin = band * band_rows, y_end = min(H, y_begin + band_rows);
     int b = 0, n_lo = 0, e_lo = 0, e_hi = 0;
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(256) mask_area_kernel(const uint32_t* __restri
 static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scratch, cudaStream_t st) {
   HGL_REQUIRE(p.WW <= 63, "mask rows pass: W=%d wider than 2016", p.W);
   p.sc = rows_carve(scratch, p.M, want_grid ? p.g : 0, want_heat ? p.E : 0, want_heat ? p.max_n : 0);
-  cudaError_t e = cudaMemsetAsync(p.sc.tickets, 0, (size_t)p.M * 4, st);
+  cudaError_t e = cudaMemsetAsync(p.sc.tickets, 0, (size_t)(p.M + 1) * 4, st);
   if (e != cudaSuccess) { set_error("mask rows pass: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
   size_t off = (size_t)4 * kMaxG * 4;
   auto take = [&](size_t n, size_t align) { off = (off + align - 1) & ~(align - 1); size_t o = off; off += n; return (int)o; };
@@ -548,8 +549,7 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
 }
 
 static int launch_heat_tables(const float* heat, const int32_t* dirflag, int E, int H, int W, const HeatWs& ws, cudaStream_t st) {
-  const int c = (W + 31) >> 5;
-  const size_t smem = ((size_t)32 * c + (size_t)kPrefWarps * 32 * (c | 1)) * 4;
+  const size_t smem = (size_t)((W + 127) & ~127) * 4;
   HGL_REQUIRE(smem <= 200 * 1024, "hgl_heat_pool: W=%d too wide", W);
   cudaError_t e = cudaFuncSetAttribute(heat_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
