@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--images", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="launch every stage in order on one stream (no side-stream chain)")
+    ap.add_argument("--serial-steps", type=int, default=50, help="extra untimed-for-value pass with overlap off: each kernel timed alone")
+    ap.add_argument("--rle-steps", type=int, default=50, help="extra pass with the proposals given as SAM uncompressed RLE (0 = skip)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
                     help="tokens: pool dense patch tokens under the grid masks on the tensor cores (hgl_mask_pool) and score those; "
@@ -216,7 +219,7 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
-    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features)
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap)
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
     batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
                                          grid=cfg["g"])
@@ -257,12 +260,35 @@ def run_ours(args, cfg):
     expr_per_step = world * B * cfg["n_expr"]
     value = expr_per_step * args.steps / (ms_total / 1e3)
 
-    # per-kernel durations from the events recorded inside the timed region
-    dur = {}
-    for evs in stage_events:
-        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
-            dur.setdefault(n1, []).append(e0.elapsed_time(e1))
-    avg_ms = {k: sum(v) / len(v) for k, v in dur.items()}
+    # per-stage durations from the event pairs recorded inside the timed region, each pair on the stream its stage runs on
+    # (the post-pack chain runs concurrently with prep on a side stream, so these are durations UNDER that overlap)
+    def stage_avg(all_events):
+        dur = {}
+        for evs in all_events:
+            for name, e0, e1 in evs:
+                dur.setdefault(name, []).append(e0.elapsed_time(e1))
+        return {k: sum(v) / len(v) for k, v in dur.items()}
+    avg_ms = stage_avg(stage_events)
+    # the same stages launched back to back on one stream (no overlap): each kernel timed ALONE, after the timed region
+    serial_events = []
+    ms_serial = None
+    if args.serial_steps > 0:
+        path.overlap = False
+        for w in range(3):
+            path.run(batches[w % 2], max_n)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for s in range(args.serial_steps):
+            path.events = []
+            path.run(batches[s % 2], max_n)
+            serial_events.append(path.events)
+        s1.record()
+        path.events = None
+        path.overlap = not args.no_overlap
+        barrier()
+        ms_serial = s0.elapsed_time(s1) / args.serial_steps
+    alone_ms = stage_avg(serial_events)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -283,6 +309,9 @@ def run_ours(args, cfg):
             ach = b / (avg_ms[k] * 1e-3) / 1e9
             kernels[k] = {"ms": round(avg_ms[k], 4), "algorithmic_bytes": b, "achieved_gbs": round(ach, 1), "frac": round(ach / peak_hbm, 4),
                           "share_of_step": round(avg_ms[k] / sum(avg_ms.values()), 4)}
+            if alone_ms.get(k, 0) > 0:
+                a1 = b / (alone_ms[k] * 1e-3) / 1e9
+                kernels[k].update({"ms_alone": round(alone_ms[k], 4), "achieved_gbs_alone": round(a1, 1), "frac_alone": round(a1 / peak_hbm, 4)})
     if "mask_pool" in kernels:           # the tensor-core stage also gets its flop rate against the measured bf16 peak
         flop = 2.0 * world_local_masks * cfg["g"] ** 2 * cfg["De"]
         tf = flop / (kernels["mask_pool"]["ms"] * 1e-3) / 1e12
@@ -291,7 +320,12 @@ def run_ours(args, cfg):
                                      "tensor_peak_tflops": peak_tf})
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     roofline = {"kernel": f"hgl_{top}", "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak_hbm, "unit": "GB/s",
-                "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src}
+                "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src,
+                "timing": ("CUDA events around the stage on its own stream inside the timed region" +
+                           ("; the side-stream chain (pack, mask grid + heat-map pooling, mask pooling, score/select, IoU) runs "
+                            "concurrently with prep, so `frac` is prep's share of HBM while sharing it; `frac_alone` is the same "
+                            "kernel timed alone in the serial pass" if path.overlap else "")),
+                "frac_alone": kernels[top].get("frac_alone"), "achieved_alone": kernels[top].get("achieved_gbs_alone")}
 
     # ---- e2e: the public API with pinned HOST buffers
     e2e = None
@@ -314,6 +348,64 @@ def run_ours(args, cfg):
                "steps": args.e2e_steps, "api": "hybridgl_b200.pipeline.ScoringPath.run_host (pinned host tensors in / out)"}
         del out
 
+    # ---- the same workload with the proposals handed over as SAM's uncompressed RLE (amg.py:107-135) instead of byte masks:
+    # hgl_rle_to_bits replaces hgl_pack_masks, the H*W-byte masks exist neither on the host nor in HBM.  Reported NEXT TO the
+    # byte-mask numbers above (which stay the headline: byte masks are what the reference's call surface receives).
+    rle_info = None
+    if args.rle_steps > 0:
+        rb = []
+        for b in batches:
+            c_, o_ = synth.masks_to_rle_device(b["masks"])
+            d = {k: v for k, v in b.items() if k != "masks"}
+            d["rle_counts"], d["rle_off"] = c_, o_
+            rb.append(d)
+        cum_bytes = path.cum.clone()
+        for w in range(3):
+            path.run(rb[w % 2], max_n)
+        barrier()
+        r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
+        rle_events = []
+        r0.record()
+        for s in range(args.rle_steps):
+            path.events = []
+            path.run(rb[s % 2], max_n)
+            rle_events.append(path.events)
+        r1.record()
+        path.events = None
+        barrier()
+        rms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+        rle_ms = float(rms.item()) / args.rle_steps
+        rle_stage = stage_avg(rle_events).get("rle", 0.0)
+        rle_bytes = rb[0]["rle_counts"].numel() * 4 + B * cfg["n_masks"] * cfg["h"] * ((cfg["w"] + 31) // 32) * 4
+        rle_info = {"value": expr_per_step / (rle_ms / 1e3), "unit": METRIC, "ms_per_step": rle_ms, "steps": args.rle_steps,
+                    "runs_per_mask": rb[0]["rle_counts"].numel() / max(1, B * cfg["n_masks"]),
+                    "rle_to_bits": {"ms": round(rle_stage, 4), "algorithmic_bytes": rle_bytes,
+                                    "achieved_gbs": round(rle_bytes / max(rle_stage, 1e-9) / 1e6, 1),
+                                    "frac": round(rle_bytes / max(rle_stage, 1e-9) / 1e6 / peak_hbm, 4)},
+                    "note": "proposals as SAM uncompressed RLE (SamAutomaticMaskGenerator(output_mode='uncompressed_rle')); "
+                            "results bit-identical to the byte-mask run (tests/test_gpu_parity.py::test_pipeline_rle_input_equals_byte_mask_input)"}
+        if args.e2e_steps > 0:
+            rhost = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in rb]
+            for w in range(2):
+                path.run_host(rhost[w % 2], max_n)
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for s in range(args.e2e_steps):
+                out = path.run_host(rhost[s % 2], max_n)
+            t1.record()
+            barrier()
+            ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            rle_info["e2e"] = {"value": expr_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": METRIC,
+                               "h2d_bytes_per_step": path.h2d_bytes(rhost[0]), "d2h_bytes_per_step": path.d2h_bytes(),
+                               "steps": args.e2e_steps}
+            del out, rhost
+        path.cum.copy_(cum_bytes)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -326,7 +418,9 @@ def run_ours(args, cfg):
                            f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
                            **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+                "streams": ("2 (prep chain on the caller's stream, post-pack chain on a high-priority side stream)" if path.overlap else "1"),
+                "ms_per_step_serial": ms_serial,
+                "roofline": roofline, "kernels": kernels, "rle_input": rle_info, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
                         "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}
         print(json.dumps(line), flush=True)

@@ -46,6 +46,9 @@ SIGNATURES = {
     "hgl_score_select_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "hgl_iou": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p]),
+    "hgl_iou_bits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p]),
+    "hgl_rle_to_bits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -91,6 +91,26 @@ def pack_masks(masks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     return out
 
 
+def rle_to_bits(counts: torch.Tensor, rle_off: torch.Tensor, height: int, width: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SAM uncompressed RLE (amg.py:107-149; column-major runs, first run counts zeros) -> packed int32 [M,H,ceil(W/32)],
+    the same tensor pack_masks() gives for np.stack([rle_to_mask(r) for r in rles]).
+    counts int32 [R]: the `counts` lists of all proposals back to back; rle_off int32 [M+1]: their boundaries."""
+    _req(counts, torch.int32, "counts", 1)
+    _req(rle_off, torch.int32, "rle_off", 1)
+    M = rle_off.numel() - 1
+    if M < 0:
+        raise ValueError("rle_off must hold M+1 entries")
+    H, W = int(height), int(width)
+    if out is None:
+        out = torch.empty((M, H, (W + 31) // 32), dtype=torch.int32, device=counts.device)
+    else:
+        _req(out, torch.int32, "bits", 3)
+        if tuple(out.shape) != (M, H, (W + 31) // 32):
+            raise ValueError(f"bits must be [M,H,ceil(W/32)] int32, got {tuple(out.shape)}")
+    check(_lib.load().hgl_rle_to_bits(counts.data_ptr(), rle_off.data_ptr(), M, H, W, out.data_ptr(), _stream()), "hgl_rle_to_bits")
+    return out
+
+
 def _bits(masks_or_bits: torch.Tensor, W: Optional[int] = None) -> torch.Tensor:
     """Accept either byte masks (packed on the fly) or an already packed int32 tensor."""
     if masks_or_bits.dtype == torch.int32:
@@ -364,12 +384,21 @@ def iou_accumulate(masks: torch.Tensor, target: torch.Tensor, idx_hybrid: torch.
                    cum: Optional[torch.Tensor], mask_off: Optional[torch.Tensor] = None,
                    expr_off: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Compute_IoU utils.py:365-384 for both picks of every expression.  Returns iu int64 [E,4] =
-    (I_hybrid, U_hybrid, I_final, U_final) and adds the column sums into cum int64 [4]."""
-    m = _mask_bytes(masks)
-    M, H, W = m.shape
+    (I_hybrid, U_hybrid, I_final, U_final) and adds the column sums into cum int64 [4].
+    `masks`: bool/u8 [M,H,W], or the packed int32 [M,H,ceil(W/32)] (the frame size is then taken from `target`)."""
     t = target[None] if target.dim() == 2 else target
     t = _mask_bytes(t, "target")
-    B = t.shape[0]
+    B, H, W = t.shape
+    packed = masks.dtype == torch.int32
+    if packed:
+        m = _req(masks, torch.int32, "bits", 3)
+        if tuple(m.shape[1:]) != (H, (W + 31) // 32):
+            raise ValueError("packed masks and target frames differ")
+    else:
+        m = _mask_bytes(masks)
+        if tuple(m.shape[1:]) != (H, W):
+            raise ValueError("masks and target frames differ")
+    M = m.shape[0]
     _req(idx_hybrid, torch.int64, "idx_hybrid", 1)
     _req(idx_final, torch.int64, "idx_final", 1)
     E = idx_hybrid.numel()
@@ -378,6 +407,7 @@ def iou_accumulate(masks: torch.Tensor, target: torch.Tensor, idx_hybrid: torch.
     if cum is not None:
         _req(cum, torch.int64, "cum", 1)
     iu = torch.empty((E, 4), dtype=torch.int64, device=m.device)
-    check(_lib.load().hgl_iou(m.data_ptr(), t.data_ptr(), idx_hybrid.data_ptr(), idx_final.data_ptr(), _ptr(moff), _ptr(eoff),
-                              B, M, E, H, W, iu.data_ptr(), _ptr(cum), _stream()), "hgl_iou")
+    fn = _lib.load().hgl_iou_bits if packed else _lib.load().hgl_iou
+    check(fn(m.data_ptr(), t.data_ptr(), idx_hybrid.data_ptr(), idx_final.data_ptr(), _ptr(moff), _ptr(eoff),
+             B, M, E, H, W, iu.data_ptr(), _ptr(cum), _stream()), "hgl_iou_bits" if packed else "hgl_iou")
     return iu

@@ -29,7 +29,7 @@ class ScoringPath:
 
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
-                 feature_source: str = "supplied", device: Optional[torch.device] = None):
+                 feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
         under every proposal's soft grid mask on the tensor cores (hgl_mask_pool) and the pooled, normalised rows are scored."""
@@ -45,7 +45,9 @@ class ScoringPath:
         self._buf: Dict[str, torch.Tensor] = {}
         self._dev_in: Dict[str, torch.Tensor] = {}
         self._host_out: Dict[str, torch.Tensor] = {}
-        self.events = None            # optional per-stage CUDA events (bench.py)
+        self.events = None            # optional per-stage CUDA event pairs (bench.py): [(stage, start, end)]
+        self.overlap = overlap        # fork the post-pack chain onto a high-priority side stream (see run())
+        self._side: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype) -> torch.Tensor:
@@ -55,53 +57,101 @@ class ScoringPath:
             self._buf[name] = t
         return t
 
-    def _mark(self, name: str):
-        if self.events is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            self.events.append((name, ev))
+    class _Span:
+        """Brackets one stage with CUDA events on the stream it is launched on (bench.py reads them)."""
+        def __init__(self, path, name):
+            self.path, self.name = path, name
+
+        def __enter__(self):
+            if self.path.events is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *exc):
+            if self.path.events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.path.events.append((self.name, self.e0, e1))
+            return False
+
+    def _span(self, name: str):
+        return ScoringPath._Span(self, name)
 
     def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """One pass over a device-resident batch.  Returns device tensors (see OUTPUT_KEYS) plus the prep
-        outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M]."""
-        img, masks = batch["image"], batch["masks"]
+        outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M].
+
+        Stage graph (self.overlap=True): the bandwidth-bound chain  blur -> prep  stays on the caller's stream; the chain
+        pack (or RLE decode) -> mask grid + heat-map pooling -> [mask pooling] -> score/select -> IoU  (small, latency-bound kernels after
+        the pack) is forked onto a high-priority side stream, so it runs in the shadow of the prep writes.  Both chains are
+        joined before run() returns; with overlap=False every stage is launched in order on the caller's stream."""
+        img = batch["image"]
         B, H, W, _ = img.shape
-        M = masks.shape[0]
+        rle = "rle_counts" in batch          # proposals as SAM uncompressed RLE instead of byte masks
+        masks = None if rle else batch["masks"]
+        M = batch["rle_off"].numel() - 1 if rle else masks.shape[0]
         moff, eoff = batch["mask_off"], batch["expr_off"]
-        self._mark("start")
-        blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
-        self._mark("blur")
-        bits = ops.pack_masks(masks, out=self._get("bits", (M, H, (W + 31) // 32), torch.int32))
-        self._mark("pack")
+        lib = ops._lib.load()
+        main = torch.cuda.current_stream()
+        side = main
+        if self.overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            side = self._side
+            side.wait_stream(main)
+
+        # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
+        with torch.cuda.stream(side):
+            bits = self._get("bits", (M, H, (W + 31) // 32), torch.int32)
+            if rle:
+                with self._span("rle"):
+                    ops.rle_to_bits(batch["rle_counts"], batch["rle_off"], H, W, out=bits)
+            else:
+                with self._span("pack"):
+                    ops.pack_masks(masks, out=bits)
+            ev_pack = None
+            if self.overlap:
+                ev_pack = torch.cuda.Event()
+                ev_pack.record()
+
+        # ---- chain P (caller's stream): blur -> prep
+        with self._span("blur"):
+            blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
         local = self._get("local", (M, 3, self.size, self.size), self.prep_dtype)
         glob = self._get("global", (M, 3, self.size, self.size), self.prep_dtype)
-        lib = ops._lib.load()
         pws = self._get("prep_ws", (max(lib.hgl_prep_workspace_bytes(B, self.size, ops._dt(self.prep_dtype)), 1),), torch.uint8)
-        ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
-                                dtype=self.prep_dtype, out=(local, glob), workspace=pws)
-        self._mark("prep")
-        feats = features if features is not None else batch.get("features")
-        E = batch["sent"].shape[0]
-        need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n)
-        ws = self._get("heat_ws", (need,), torch.uint8)
-        if self.antialias:     # mask grid + heat-map pooling share one pass over the packed masks
-            grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, batch["heat"], batch["dirflag"], batch["black"],
-                                                       moff, eoff, max_n, workspace=ws)
-        else:
-            grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
-            score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
-        self._mark("grid_heat_pool")
-        if self.feature_source == "tokens" and features is None:
-            mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
-            feats = ops.mask_pool(grid, batch["tokens"], moff, max_n, normalize=True, dtype=torch.bfloat16, workspace=mws)
-            self._mark("mask_pool")
-        sws = self._get("score_ws", (max(lib.hgl_score_select_workspace_bytes(B, E, max_n), 1),), torch.uint8)
-        res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
-                               batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha,
-                               workspace=sws)
-        self._mark("score_select")
-        iu = ops.iou_accumulate(masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
-        self._mark("iou")
+        if ev_pack is not None:
+            main.wait_event(ev_pack)
+        with self._span("prep"):
+            ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
+                                    dtype=self.prep_dtype, out=(local, glob), workspace=pws)
+
+        # ---- chain S continued: everything that only needs the packed masks
+        with torch.cuda.stream(side):
+            feats = features if features is not None else batch.get("features")
+            E = batch["sent"].shape[0]
+            need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n)
+            ws = self._get("heat_ws", (need,), torch.uint8)
+            with self._span("grid_heat_pool"):
+                if self.antialias:     # mask grid + heat-map pooling share one pass over the packed masks
+                    grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, batch["heat"], batch["dirflag"], batch["black"],
+                                                               moff, eoff, max_n, workspace=ws)
+                else:
+                    grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
+                    score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
+            if self.feature_source == "tokens" and features is None:
+                mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
+                with self._span("mask_pool"):
+                    feats = ops.mask_pool(grid, batch["tokens"], moff, max_n, normalize=True, dtype=torch.bfloat16, workspace=mws)
+            sws = self._get("score_ws", (max(lib.hgl_score_select_workspace_bytes(B, E, max_n), 1),), torch.uint8)
+            with self._span("score_select"):
+                res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
+                                       batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha,
+                                       workspace=sws)
+            with self._span("iou"):
+                iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
+        if self.overlap:
+            main.wait_stream(side)
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
 
@@ -111,21 +161,26 @@ class ScoringPath:
     def launches_per_run(self) -> int:
         return self.LAUNCHES_PER_RUN + (1 if self.feature_source == "tokens" else 0)
 
-    def input_keys(self):
-        skip = "features" if self.feature_source == "tokens" else "tokens"
-        return tuple(k for k in INPUT_KEYS if k != skip)
+    def input_keys(self, host_batch=None):
+        skip = {"features" if self.feature_source == "tokens" else "tokens"}
+        keys = INPUT_KEYS
+        if host_batch is not None and "rle_counts" in host_batch:       # RLE proposals replace the byte masks
+            skip.add("masks")
+            keys = keys + ("rle_counts", "rle_off")
+        return tuple(k for k in keys if k not in skip)
 
     def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:
         """End-to-end call with HOST buffers (pinned): H2D of every input, the kernels, D2H of the results,
         then a stream synchronise.  This is what bench.py times as `e2e`."""
-        for k in self.input_keys():
+        for k in self.input_keys(host_batch):
             src = host_batch[k]
             dst = self._dev_in.get(k)
             if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
                 dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
                 self._dev_in[k] = dst
             dst.copy_(src, non_blocking=True)
-        res = self.run(self._dev_in, max_n)
+        dev_in = {k: self._dev_in[k] for k in self.input_keys(host_batch)}
+        res = self.run(dev_in, max_n)
         out = {}
         for k in OUTPUT_KEYS:
             src = res[k]
@@ -139,7 +194,7 @@ class ScoringPath:
         return out
 
     def h2d_bytes(self, host_batch: Dict[str, torch.Tensor]) -> int:
-        return sum(host_batch[k].numel() * host_batch[k].element_size() for k in self.input_keys())
+        return sum(host_batch[k].numel() * host_batch[k].element_size() for k in self.input_keys(host_batch))
 
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._host_out.values())

@@ -104,6 +104,52 @@ def masks_to_boxes(masks: np.ndarray) -> np.ndarray:
     return boxes
 
 
+def masks_to_rle(masks: np.ndarray):
+    """SAM's uncompressed RLE of every mask (amg.py:107-135: column-major runs, first run counts zeros), laid out for the
+    C ABI: (counts int32 [R], rle_off int32 [M+1]).  Host-side data generation only."""
+    m = np.asarray(masks, bool)
+    M, h, w = m.shape
+    flat = m.transpose(0, 2, 1).reshape(M, h * w)
+    counts, off = [], [0]
+    for i in range(M):
+        change = np.nonzero(flat[i, 1:] ^ flat[i, :-1])[0] + 1
+        c = np.diff(np.concatenate([[0], change, [h * w]]))
+        if flat[i, 0]:
+            c = np.concatenate([[0], c])
+        counts.append(c.astype(np.int32))
+        off.append(off[-1] + c.size)
+    return (np.concatenate(counts) if counts else np.zeros(0, np.int32)), np.asarray(off, np.int32)
+
+
+def masks_to_rle_device(masks):
+    """The same on a torch device tensor bool [M,H,W] (benchmark-sized batches): returns (counts int32 [R], rle_off int32 [M+1])."""
+    import torch
+    M, h, w = masks.shape
+    counts, lens = [], []
+    for s in range(0, M, 64):                                                           # chunked: keeps temporaries small
+        flat = masks[s:s + 64].permute(0, 2, 1).reshape(-1, h * w)
+        n = flat.shape[0]
+        first = flat[:, :1]
+        # a run starts at position 0 (the leading zeros run, length 0 when the first pixel is set) and wherever the value changes
+        chg = torch.cat([torch.ones_like(first), flat[:, 1:] ^ flat[:, :-1]], dim=1)
+        mi, pos = chg.nonzero(as_tuple=True)
+        lead = first[:, 0]                                                               # masks that need the extra leading 0
+        per = torch.bincount(mi, minlength=n) + lead.long()
+        nxt = torch.cat([pos[1:], pos.new_zeros(1)])
+        last = torch.cat([mi[1:] != mi[:-1], mi.new_ones(1, dtype=torch.bool)])
+        run = torch.where(last, h * w - pos, nxt - pos)
+        # splice the leading zero counts in: output slot of every run = its rank + number of leads of masks <= its own
+        lead_before = torch.cumsum(lead.long(), 0)
+        slot = torch.arange(pos.numel(), device=masks.device) + lead_before[mi]
+        out = torch.zeros(int(per.sum()), dtype=torch.int32, device=masks.device)
+        out[slot] = run.to(torch.int32)
+        counts.append(out); lens.append(per)
+    lens = torch.cat(lens)
+    off = torch.zeros(M + 1, dtype=torch.int64, device=masks.device)
+    off[1:] = torch.cumsum(lens, 0)
+    return torch.cat(counts), off.to(torch.int32)
+
+
 def make_target(rng: np.random.Generator, masks: np.ndarray) -> np.ndarray:
     """Ground truth = one proposal shifted by a few pixels so that IoU is neither 0 nor 1."""
     k = int(rng.integers(0, masks.shape[0]))

@@ -169,6 +169,21 @@ HGL_API int hgl_iou(const uint8_t* masks, const uint8_t* target, const int64_t* 
             const int32_t* mask_off, const int32_t* expr_off, int B, int M, int E, int H, int W,
             int64_t* iu, int64_t* cum, void* stream);
 
+/* The same with the prediction read from the packed masks (bits u32 [M,H,ceil(W/32)], hgl_pack_masks / hgl_rle_to_bits)
+ * instead of byte masks; identical integers. */
+HGL_API int hgl_iou_bits(const uint32_t* bits, const uint8_t* target, const int64_t* idx_hybrid, const int64_t* idx_final,
+            const int32_t* mask_off, const int32_t* expr_off, int B, int M, int E, int H, int W,
+            int64_t* iu, int64_t* cum, void* stream);
+
+/* ---- SAM run-length proposals -> packed masks --------------------------------------------------------
+ * Replaces rle_to_mask third_party/segment-anything/segment_anything/utils/amg.py:138-149 (+ the torch.stack / .to(device)
+ * of Hybridgl_main.py:86-87) for proposals kept in SAM's uncompressed RLE form (amg.py:107-135 mask_to_rle_pytorch;
+ * SamAutomaticMaskGenerator(output_mode="uncompressed_rle")): column-major runs, the first run counts zeros.
+ * counts int32 [R] = the `counts` lists of all M proposals back to back; rle_off int32 [M+1] = their boundaries in `counts`
+ * (every proposal's counts sum to H*W; positions past H*W are ignored); bits u32 [M,H,ceil(W/32)] (overwritten) = exactly
+ * what hgl_pack_masks writes for the expanded masks. */
+HGL_API int hgl_rle_to_bits(const int32_t* counts, const int32_t* rle_off, int M, int H, int W, uint32_t* bits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,6 +390,45 @@ def mask_pool_tokens(weights: np.ndarray, tokens: np.ndarray, normalize: bool = 
 # --------------------------------------------------------------------------------------------------
 # (a13) IoU accounting -- utils.py:365-384, Hybridgl_main.py:240-247
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# SAM run-length proposals (third_party/segment-anything/segment_anything/utils/amg.py)
+# --------------------------------------------------------------------------------------------------
+def mask_to_rle(mask: np.ndarray) -> dict:
+    """amg.py:107-135 mask_to_rle_pytorch for one mask: column-major (Fortran) runs, first run counts zeros
+    (a leading 0 is emitted when the first pixel is set, amg.py:132)."""
+    h, w = mask.shape
+    flat = np.asarray(mask, bool).T.reshape(-1)                      # amg.py:114 permute(0,2,1).flatten(1)
+    change = np.nonzero(flat[1:] ^ flat[:-1])[0] + 1                  # amg.py:117-118, :126
+    edges = np.concatenate([[0], change, [h * w]])                   # amg.py:123-129
+    counts = np.diff(edges).tolist()                                 # amg.py:130
+    if flat[0]:
+        counts = [0] + counts                                        # amg.py:131
+    return {"size": [h, w], "counts": counts}
+
+
+def rle_to_mask(rle: dict) -> np.ndarray:
+    """amg.py:138-149: fill alternating runs into a flat column-major buffer, reshape (w,h), transpose."""
+    h, w = rle["size"]
+    counts = np.asarray(rle["counts"], np.int64)
+    parity = (np.arange(counts.size) & 1).astype(bool)               # amg.py:143-148
+    flat = np.repeat(parity, counts)[: h * w]
+    if flat.size < h * w:                                            # np.empty tail of a short RLE: define it as zeros
+        flat = np.concatenate([flat, np.zeros(h * w - flat.size, bool)])
+    return flat.reshape(w, h).T                                      # amg.py:148-149
+
+
+def pack_bits(masks: np.ndarray) -> np.ndarray:
+    """The packed-mask format of libhgl: uint32 [M,H,ceil(W/32)], bit i of word w = pixel 32*w+i (no reference
+    counterpart -- a storage format; defined here so that tests can state it independently of the kernels)."""
+    m = np.asarray(masks).astype(bool)
+    M, H, W = m.shape
+    WW = (W + 31) // 32
+    pad = np.zeros((M, H, WW * 32), bool)
+    pad[:, :, :W] = m
+    by = np.packbits(pad.reshape(M, H, WW, 32), axis=-1, bitorder="little")      # [M,H,WW,4] bytes, little endian
+    return by.view("<u4").reshape(M, H, WW)
+
+
 def compute_iou(pred: np.ndarray, target: np.ndarray):
     """utils.py:365-384: integer I, U and this_iou = I/U (0 when U == 0)."""
     p = np.asarray(pred).astype(bool); t = np.asarray(target).astype(bool)

@@ -15,8 +15,8 @@ timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; e
 cat $out/${tag}_bench.json
 # launch list (cold-cache, serialised: shares only)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$KRE" -c 72 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+    python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline --serial-steps 0 --rle-steps 0 > $out/${tag}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 # full sections for one step of our kernels (second pass over the path: skip the first step's launches)
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-12} -o $out/${tag}_prof -f \
-    python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --serial-steps 0 --rle-steps 0 > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $out | tail -12

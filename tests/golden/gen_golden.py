@@ -250,9 +250,38 @@ def gen_misc(ref_utils):
     print("misc", len(rows))
 
 
+def gen_rle():
+    """SAM's own RLE codec (third_party/segment-anything/segment_anything/utils/amg.py:107-149), imported in place."""
+    sys.path.insert(0, os.path.join(REF, "third_party/segment-anything"))
+    from segment_anything.utils.amg import mask_to_rle_pytorch, rle_to_mask
+    out = {}
+    rng = np.random.default_rng(31)
+    cases = []
+    for ci, (h, w, n) in enumerate(((48, 64, 6), (37, 45, 5), (64, 33, 4), (5, 3, 3), (96, 160, 4))):
+        m = synth.make_masks(rng, n, h, w, min_area=20)
+        m[0] = False; m[0, 0, 0] = True                     # first pixel set -> leading zero count
+        m[1] = True                                          # full frame: one run spanning every column
+        if n > 2:
+            m[2] = rng.random((h, w)) < 0.5                  # noise: thousands of 1-pixel runs
+        if n > 3:
+            m[3] = False                                     # empty mask: a single run of zeros
+        cases.append(m)
+        rles = mask_to_rle_pytorch(torch.from_numpy(m))
+        counts = np.concatenate([np.asarray(r["counts"], np.int32) for r in rles])
+        off = np.cumsum([0] + [len(r["counts"]) for r in rles]).astype(np.int32)
+        back = np.stack([rle_to_mask(r) for r in rles])
+        assert np.array_equal(back, m)
+        out[f"c{ci}_masks"] = m; out[f"c{ci}_counts"] = counts; out[f"c{ci}_off"] = off; out[f"c{ci}_decoded"] = back
+        print("rle", ci, (h, w, n), "runs", counts.size)
+    out["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "rle.npz"), **out)
+
+
 if __name__ == "__main__":
     CLIP, CLIPViTFM, ref_utils = load_reference()
-    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc"]
+    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc", "rle"]
+    if "rle" in which:
+        gen_rle()
     with torch.no_grad():
         if "prep" in which:
             gen_prep(ref_utils)

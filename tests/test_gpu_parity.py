@@ -360,3 +360,87 @@ def test_pipeline_token_features_vs_oracle(ops):
             ei = b * e + j
             sc = O.calculate_score(feats[b * n:(b + 1) * n], (0.5 * batch["sent"][ei] + 0.5 * batch["noun"][ei]).cpu().numpy()[None], 100.0)[:, 0]
             np.testing.assert_allclose(res["score_clip"][ei, :n].cpu().numpy(), sc, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ SAM RLE proposals
+def test_rle_to_bits_matches_sam_golden(ops, golden):
+    """hgl_rle_to_bits on SAM's own RLE output (amg.py mask_to_rle_pytorch, recorded by gen_golden.py) == packed rle_to_mask."""
+    g = golden("rle")
+    for ci in range(int(g["n_cases"])):
+        masks = g[f"c{ci}_masks"]
+        h, w = masks.shape[1:]
+        bits = ops.rle_to_bits(cu(g[f"c{ci}_counts"]), cu(g[f"c{ci}_off"]), h, w)
+        assert np.array_equal(bits.cpu().numpy().view(np.uint32), O.pack_bits(g[f"c{ci}_decoded"]))
+        assert torch.equal(bits, ops.pack_masks(cu(masks)))
+
+
+@pytest.mark.parametrize("h,w,n,seed", [(480, 640, 40, 50), (333, 500, 9, 51), (97, 131, 6, 52), (600, 800, 12, 53), (512, 512, 5, 54),
+                                        (1080, 1920, 3, 55), (1500, 2100, 2, 56), (1, 7, 2, 57), (40, 1, 2, 58)])
+def test_rle_to_bits_vs_oracle(ops, h, w, n, seed):
+    """Frame sizes around the word / strip boundaries (1080x1920 and larger do not fit one strip of shared memory)."""
+    rng = np.random.default_rng(seed)
+    m = synth.make_masks(rng, n, h, w, min_area=4)
+    m[0] = rng.random((h, w)) < 0.5
+    m[-1] = True
+    counts, off = synth.masks_to_rle(m)
+    want = np.stack([O.rle_to_mask(O.mask_to_rle(x)) for x in m])
+    assert np.array_equal(want, m)
+    bits = ops.rle_to_bits(cu(counts), cu(off), h, w)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), O.pack_bits(want))
+
+
+def test_rle_edge_cases(ops):
+    h, w = 48, 64
+    # zero-length runs in the middle, a trailing zero-length run, an all-zero mask given as one run, and no masks at all
+    rles = [[10, 0, 0, 5, h * w - 15], [0, h * w, 0], [h * w], [0, 1, h * w - 1]]
+    counts = np.concatenate([np.asarray(r, np.int32) for r in rles])
+    off = np.cumsum([0] + [len(r) for r in rles]).astype(np.int32)
+    want = np.stack([O.rle_to_mask({"size": [h, w], "counts": r}) for r in rles])
+    bits = ops.rle_to_bits(cu(counts), cu(off), h, w)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), O.pack_bits(want))
+    empty = ops.rle_to_bits(torch.zeros(0, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV), h, w)
+    assert tuple(empty.shape) == (0, h, 2)
+    with pytest.raises(TypeError):
+        ops.rle_to_bits(cu(counts).to(torch.int64), cu(off), h, w)
+
+
+@pytest.mark.parametrize("h,w", [(480, 640), (97, 131), (33, 20)])
+def test_iou_from_packed_masks_bit_exact(ops, h, w):
+    rng = np.random.default_rng(h)
+    B, n, E = 2, 5, 3
+    m = np.concatenate([synth.make_masks(rng, n, h, w, min_area=20) for _ in range(B)])
+    tgt = np.stack([np.roll(m[2], 3, axis=1), np.roll(m[n + 1], -2, axis=0)]).astype(np.uint8) * 255      # any non-zero byte counts
+    ih = rng.integers(0, n, B * E); jf = rng.integers(0, n, B * E)
+    moff = cu(np.array([0, n, 2 * n], np.int32)); eoff = cu(np.array([0, E, 2 * E], np.int32))
+    cum_a = torch.zeros(4, dtype=torch.int64, device=DEV); cum_b = torch.zeros_like(cum_a)
+    bits = ops.pack_masks(cu(m))
+    iu_b = ops.iou_accumulate(bits, cu(tgt), cu(ih), cu(jf), cum_b, moff, eoff).cpu().numpy()
+    iu_a = ops.iou_accumulate(cu(m), cu(tgt), cu(ih), cu(jf), cum_a, moff, eoff).cpu().numpy()
+    want = []
+    for e in range(B * E):
+        b = e // E
+        i0, u0, _ = O.compute_iou(m[b * n + ih[e]], tgt[b]); i1, u1, _ = O.compute_iou(m[b * n + jf[e]], tgt[b])
+        want.append([i0, u0, i1, u1])
+    want = np.asarray(want, np.int64)
+    assert np.array_equal(iu_b, want) and np.array_equal(iu_a, want)
+    assert cum_b.cpu().numpy().tolist() == want.sum(0).tolist() == cum_a.cpu().numpy().tolist()
+
+
+def test_pipeline_rle_input_equals_byte_mask_input(ops):
+    """ScoringPath fed SAM RLE proposals gives bit-identical results to the same proposals fed as byte masks."""
+    from hybridgl_b200.pipeline import OUTPUT_KEYS, ScoringPath
+    batch = synth.make_batch_device(77, 3, 120, 160, 12, 2, 64, device=DEV, grid=4)
+    counts, off = synth.masks_to_rle_device(batch["masks"])
+    c_np, o_np = synth.masks_to_rle(batch["masks"].cpu().numpy())
+    assert np.array_equal(counts.cpu().numpy(), c_np) and np.array_equal(off.cpu().numpy(), o_np)
+    res = {}
+    for mode in ("bytes", "rle"):
+        path = ScoringPath(size=32, grid=4, prep_dtype=torch.float32, feature_source="tokens")
+        b = dict(batch)
+        if mode == "rle":
+            del b["masks"]
+            b["rle_counts"], b["rle_off"] = counts, off
+        res[mode] = path.run(b, 12)
+        res[mode]["cum"] = path.cum.clone()
+    for k in OUTPUT_KEYS + ("local_imgs", "global_imgs", "grid", "area", "bits", "cum"):
+        assert torch.equal(res["bytes"][k], res["rle"][k]), k

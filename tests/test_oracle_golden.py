@@ -142,3 +142,26 @@ def test_token_space_pooling_equals_pixel_space_pooling():
     # normalised rows have unit length
     pn = O.mask_pool_tokens(weights, F, normalize=True)
     np.testing.assert_allclose(np.linalg.norm(pn.astype(np.float64), axis=1), 1.0, rtol=1e-6)
+
+
+def test_rle_codec_matches_sam(golden):
+    """oracle mask_to_rle / rle_to_mask against SAM's own codec (amg.py:107-149) recorded by gen_golden.py::gen_rle."""
+    g = golden("rle")
+    for ci in range(int(g["n_cases"])):
+        masks, counts, off = g[f"c{ci}_masks"], g[f"c{ci}_counts"], g[f"c{ci}_off"]
+        c2, off2 = synth.masks_to_rle(masks)
+        assert np.array_equal(c2, counts) and np.array_equal(off2, off)
+        for i in range(masks.shape[0]):
+            r = O.mask_to_rle(masks[i])
+            assert r["counts"] == counts[off[i]:off[i + 1]].tolist() and r["size"] == list(masks.shape[1:])
+            assert np.array_equal(O.rle_to_mask(r), g[f"c{ci}_decoded"][i])
+
+
+def test_pack_bits_layout():
+    rng = np.random.default_rng(3)
+    m = rng.random((3, 5, 70)) < 0.4
+    b = O.pack_bits(m)
+    assert b.shape == (3, 5, 3) and b.dtype == np.uint32
+    for (n, y, x) in [(0, 0, 0), (1, 2, 31), (2, 4, 32), (2, 3, 69)]:
+        assert bool((b[n, y, x // 32] >> (x % 32)) & 1) == bool(m[n, y, x])
+    assert (b[:, :, 2] >> 6).max() == 0            # bits past W are zero
