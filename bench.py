@@ -119,7 +119,8 @@ def _oracle_one_image(args):
     feats = O.mask_pool_tokens(grid.reshape(grid.shape[0], -1), tokens)            # dense tokens pooled under every soft grid mask
     cum = np.zeros(4, np.int64)
     for ex in it.expressions:
-        sg = O.gem_pool(O.condition_heatmap(ex.heatmap, ex.dirflag), it.masks, O.black_for(ex.relaflag))
+        heat = O.resize_bilinear_aa(ex.heat_raw[None], cfg["h"], cfg["w"])[0]           # T.Resize((H,W), antialias=True), :201
+        sg = O.gem_pool(O.condition_heatmap(heat, ex.dirflag), it.masks, O.black_for(ex.relaflag))
         r = O.score_and_select(feats, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag, score_gem=sg)
         i0, u0, _ = O.compute_iou(it.masks[r["idx_hybrid"]], it.target)
         i1, u1, _ = O.compute_iou(it.masks[r["idx_final"]], it.target)
@@ -192,9 +193,13 @@ def algorithmic_bytes(cfg, B, prep_bytes):
     return {
         "blur": 2 * B * H * W * 3,
         "pack": M * H * W + M * H * ((W + 31) // 32) * 4,
-        "prep": M * H * ((W + 31) // 32) * 4 + 2 * B * H * W * 3 + 2 * M * 3 * S * S * prep_bytes,
-        # one pass over the packed masks (grid + pooling) + the heat-maps once (+ their row-prefix tables written once)
-        "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + 2 * ET * H * W * 4 + ET * N * 4,
+        # per-image half: frames in, 12 answer planes + 24 tap bytes per output pixel out
+        "prep_setup": 2 * B * H * W * 3 + B * S * S * (12 * prep_bytes + 24),
+        # per-mask half: packed masks + answer planes in, 2 x [M,3,S,S] out
+        "prep": M * H * ((W + 31) // 32) * 4 + B * S * S * 12 * prep_bytes + 2 * M * 3 * S * S * prep_bytes,
+        # one pass over the packed masks (grid + pooling) + the raw GEM maps (28 x 37, resized on the fly) + the row-prefix
+        # tables of the frame-sized conditioned maps written once
+        "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + ET * 28 * 37 * 4 + ET * H * W * 4 + ET * N * 4,
         # tensor-core pooling of the dense tokens: soft masks f32 + tokens bf16 in, pooled rows bf16 out (flops: MASK_POOL_FLOPS)
         "mask_pool": M * cfg["g"] ** 2 * 4 + B * cfg["g"] ** 2 * De * 2 + M * De * 2,
         "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
@@ -222,7 +227,7 @@ def run_ours(args, cfg):
     path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap)
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
     batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
-                                         grid=cfg["g"])
+                                         grid=cfg["g"], raw_heat=True)
                for i in range(2)]
     max_n = cfg["n_masks"]
     torch.cuda.synchronize()

@@ -110,19 +110,53 @@ static HeatWs heat_carve(void* ws, int E, int H, int W) {
 // One warp per (expression, row), 128 pixels per round: a lane owns 4 adjacent pixels (one 16-byte load, one 16-byte store),
 // scans them in registers, the 32 lane totals go through one shuffle scan, and a running carry links the rounds.  Row 0's
 // warp also emits the ramp prefix.  The ramp row is evaluated once per CTA (shared memory).
+//
+// kLR: `heat` is the RAW GEM map [E,hh,hw] and the frame-sized map of Hybridgl_main.py:201, T.Resize((H,W), antialias=True),
+// is evaluated on the fly (ATen _upsample_bilinear2d_aa, separable: horizontal pass, then vertical pass; for an up-sampler
+// the triangle filter has <= 3 taps per axis).  The x taps are built once per CTA in shared memory, the y taps once per warp;
+// the raw map (a few KB per expression) is read through L1.  The frame-sized heat-map then never exists in HBM.
+template <bool kLR>
 __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag,
-                                                                      int H, int W, int Wp, float* __restrict__ cr, float* __restrict__ rp,
-                                                                      float* __restrict__ rowstat) {
-  extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]
+                                                                      int H, int W, int Wp, int hh, int hw, float* __restrict__ cr,
+                                                                      float* __restrict__ rp, float* __restrict__ rowstat) {
+  extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]  (+ kLR: x taps, see below)
   const int e = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W128 = (W + 127) & ~127;
   const int dir = dirflag[e];
-  for (int x = threadIdx.x; x < W128; x += blockDim.x) ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
+  float* wxt = ramp + W128;                               // kLR: [W128][3] horizontal filter weights
+  int* xtap = reinterpret_cast<int*>(wxt + 3 * W128);     // kLR: [W128]    xmin | xsize << 16
+  for (int x = threadIdx.x; x < W128; x += blockDim.x) {
+    ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
+    if (kLR && x < W) {
+      int xm, xs;
+      aa_fill(x, hw, W, 3, &xm, &xs, wxt + 3 * x);
+      xtap[x] = xm | (xs << 16);
+    }
+  }
   __syncthreads();
   const int y = blockIdx.x * kPrefWarps + warp;
   if (y >= H) return;                               // whole warp; no block-level barrier below
-  const float* A = heat + ((size_t)e * H + y) * W;
-  const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
+  const float* A = kLR ? heat + (size_t)e * hh * hw : heat + ((size_t)e * H + y) * W;
+  const bool vec = !kLR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
+  int ymin = 0, ysize = 0;
+  float wy[3] = {0.f, 0.f, 0.f};
+  if (kLR) aa_fill(y, hh, H, 3, &ymin, &ysize, wy);
+  auto lr_pixel = [&](int x) -> float {              // one pixel of T.Resize((H,W), antialias=True)(raw map)
+    const int xt = xtap[x], xm = xt & 0xffff, xs = xt >> 16;
+    float o = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if (ky < ysize) {
+        const float* r = A + (size_t)(ymin + ky) * hw + xm;
+        float t = 0.f;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          if (kx < xs) t = __fadd_rn(t, __fmul_rn(__ldg(r + kx), wxt[3 * x + kx]));
+        o = __fadd_rn(o, __fmul_rn(t, wy[ky]));
+      }
+    }
+    return o;
+  };
   for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
     float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
     float mn = INFINITY, mx = -INFINITY, carry = 0.f;
@@ -133,7 +167,10 @@ __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const floa
       if (pass == 0) { a[0] = r4.x; a[1] = r4.y; a[2] = r4.z; a[3] = r4.w; }
       else {
         float h4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vec && x + 3 < W) { const float4 v = __ldg(reinterpret_cast<const float4*>(A + x)); h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w; }
+        if (kLR) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = lr_pixel(x + q);
+        } else if (vec && x + 3 < W) { const float4 v = __ldg(reinterpret_cast<const float4*>(A + x)); h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w; }
         else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = __ldg(A + x + q);
@@ -199,6 +236,46 @@ __global__ void __launch_bounds__(128) heat_consts_kernel(const float* __restric
     const double kk = 1.0 / (range * mean);
     float* o = consts + (size_t)e * 4;
     o[0] = lo; o[1] = (float)kk; o[2] = (float)(kk * (s1 - (double)lo * s0)); o[3] = 0.f;
+  }
+}
+
+// T.Resize((H,W), antialias=True) of the raw GEM maps as a tensor (Hybridgl_main.py:201; the drop-in form, any scale):
+// one thread per output pixel, separable triangle filter with ATen's index / weight arithmetic, horizontal pass then vertical.
+struct AaTap { float scale, support, invscale, center, total; int xmin, xsize; };
+__device__ __forceinline__ float aa_raw_weight(const AaTap& t, int j) {
+  const float v = fabsf((float)(((double)__fsub_rn((float)(j + t.xmin), t.center) + 0.5) * (double)t.invscale));
+  return (v < 1.f) ? __fsub_rn(1.f, v) : 0.f;
+}
+__device__ __forceinline__ AaTap aa_tap(int i, int in_size, int out_size) {
+  AaTap t;
+  t.scale = __fdiv_rn((float)in_size, (float)out_size);
+  if (t.scale >= 1.f) { t.support = t.scale; t.invscale = __fdiv_rn(1.f, t.scale); } else { t.support = 1.f; t.invscale = 1.f; }
+  t.center = (float)((double)t.scale * ((double)i + 0.5));
+  t.xmin = max((int)((double)__fsub_rn(t.center, t.support) + 0.5), 0);
+  t.xsize = max(min((int)((double)__fadd_rn(t.center, t.support) + 0.5), in_size) - t.xmin, 0);
+  t.total = 0.f;
+  for (int j = 0; j < t.xsize; ++j) t.total = __fadd_rn(t.total, aa_raw_weight(t, j));
+  return t;
+}
+__device__ __forceinline__ float aa_weight(const AaTap& t, int j) {
+  const float w = aa_raw_weight(t, j);
+  return (t.total != 0.f) ? __fdiv_rn(w, t.total) : w;
+}
+__global__ void __launch_bounds__(256) heat_resize_aa_kernel(const float* __restrict__ src, int E, int hh, int hw, int H, int W,
+                                                             float* __restrict__ out) {
+  const size_t total = (size_t)E * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), e = (int)(i / ((size_t)W * H));
+    const AaTap tx = aa_tap(x, hw, W), ty = aa_tap(y, hh, H);
+    const float* s = src + (size_t)e * hh * hw;
+    float o = 0.f;
+    for (int ky = 0; ky < ty.xsize; ++ky) {
+      const float* r = s + (size_t)(ty.xmin + ky) * hw + tx.xmin;
+      float t = 0.f;
+      for (int kx = 0; kx < tx.xsize; ++kx) t = __fadd_rn(t, __fmul_rn(__ldg(r + kx), aa_weight(tx, kx)));
+      o = __fadd_rn(o, __fmul_rn(t, aa_weight(ty, ky)));
+    }
+    out[i] = o;
   }
 }
 
@@ -548,12 +625,25 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
   return go(mask_rows_kernel<false, true>);
 }
 
-static int launch_heat_tables(const float* heat, const int32_t* dirflag, int E, int H, int W, const HeatWs& ws, cudaStream_t st) {
-  const size_t smem = (size_t)((W + 127) & ~127) * 4;
+// hh > 0: `heat` is the raw map [E,hh,hw] (resized on the fly when both axes are up-sampled, else materialised in `full`)
+static int launch_heat_tables(const float* heat, int hh, int hw, float* full, const int32_t* dirflag, int E, int H, int W, const HeatWs& ws,
+                              cudaStream_t st) {
+  bool lr = hh > 0;
+  if (lr && (aa_maxk(hh, H) > 3 || aa_maxk(hw, W) > 3)) {          // a down-sampling axis: wide filters, resize as a tensor first
+    HGL_REQUIRE(full, "hgl_heat_pool: internal: no room for the resized heat-map");
+    const int blocks = (int)std::min<size_t>(((size_t)E * H * W + 255) / 256, (size_t)sm_count() * 16);
+    heat_resize_aa_kernel<<<blocks, 256, 0, st>>>(heat, E, hh, hw, H, W, full);
+    int rc = launch_status("hgl_heat_pool(resize)");
+    if (rc != HGL_OK) return rc;
+    heat = full; lr = false;
+  }
+  const size_t w128 = (size_t)((W + 127) & ~127);
+  const size_t smem = lr ? w128 * 4 * 5 : w128 * 4;
   HGL_REQUIRE(smem <= 200 * 1024, "hgl_heat_pool: W=%d too wide", W);
-  cudaError_t e = cudaFuncSetAttribute(heat_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = lr ? heat_prefix_kernel<true> : heat_prefix_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
-  heat_prefix_kernel<<<dim3(ceil_div(H, kPrefWarps), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, ws.cr, ws.rp, ws.rowstat);
+  kern<<<dim3(ceil_div(H, kPrefWarps), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, hh, hw, ws.cr, ws.rp, ws.rowstat);
   int rc = launch_status("hgl_heat_pool(prefix)");
   if (rc != HGL_OK) return rc;
   heat_consts_kernel<<<E, 128, 0, st>>>(ws.rowstat, ws.rp, H, W, ws.Wp, ws.consts);
@@ -614,21 +704,30 @@ extern "C" int64_t hgl_heat_pool_workspace_bytes(int B, int M, int E, int H, int
   return hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, 0, max_n);
 }
 
-// shared argument checks + table build of the two pooling entry points
-static int hgl_heat_common(const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, const uint32_t* bits,
-                           const int32_t* mask_off, int B, int M, int E, int H, int W, int max_n, float* score_gem, void* workspace,
-                           hgl::HeatWs* ws, void** scratch, cudaStream_t st) {
+// bytes of the frame-sized heat-maps that the raw-map entry point must materialise (only when an axis is down-sampled)
+static size_t lr_full_bytes(int E, int H, int W, int hh, int hw) {
+  if (hh <= 0 || (hgl::aa_maxk(hh, H) <= 3 && hgl::aa_maxk(hw, W) <= 3)) return 0;
+  return ((size_t)E * H * W * 4 + 255) & ~size_t(255);
+}
+
+// shared argument checks + table build of the pooling entry points (hh > 0: heat is the raw map [E,hh,hw])
+static int hgl_heat_common(const float* heat, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black,
+                           const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W, int max_n, float* score_gem,
+                           void* workspace, hgl::HeatWs* ws, void** scratch, cudaStream_t st) {
   using namespace hgl;
   HGL_REQUIRE(heat && dirflag && black && bits && score_gem && workspace, "hgl_heat_pool: null pointer");
   HGL_REQUIRE(B >= 1 && M >= 0 && E >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_heat_pool: bad shape");
+  HGL_REQUIRE(hh >= 0 && hw >= 0 && hw <= 65535 && (hh > 0) == (hw > 0), "hgl_heat_pool: bad raw heat-map shape %dx%d", hh, hw);
   HGL_REQUIRE((mask_off && expr_off) || B == 1, "hgl_heat_pool: mask_off/expr_off required when B > 1");
   HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hgl_heat_pool: workspace must be 16-byte aligned");
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   *ws = heat_carve(base, E, H, W);
-  *scratch = base + ws->bytes;
+  const size_t fb = lr_full_bytes(E, H, W, hh, hw);
+  float* full = fb ? reinterpret_cast<float*>(base + ws->bytes) : nullptr;
+  *scratch = base + ws->bytes + fb;
   cudaError_t e = cudaMemsetAsync(score_gem, 0, (size_t)E * max_n * 4, st);    // rows of images with fewer than max_n masks
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
-  return launch_heat_tables(heat, dirflag, E, H, W, *ws, st);
+  return launch_heat_tables(heat, hh, hw, full, dirflag, E, H, W, *ws, st);
 }
 
 static void hgl_fill_heat(hgl::RowsParams& p, const hgl::HeatWs& ws, const float* black, const int32_t* mask_off, const int32_t* expr_off,
@@ -645,7 +744,7 @@ extern "C" int hgl_heat_pool(const float* heat, const int32_t* expr_off, const i
   cudaStream_t st = (cudaStream_t)stream;
   HeatWs ws;
   void* scratch = nullptr;
-  int rc = hgl_heat_common(heat, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  int rc = hgl_heat_common(heat, 0, 0, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
   if (rc != HGL_OK) return rc;
   RowsParams p = {};
   p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
@@ -653,10 +752,26 @@ extern "C" int hgl_heat_pool(const float* heat, const int32_t* expr_off, const i
   return launch_rows(p, false, true, scratch, st);
 }
 
-extern "C" int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
-                                  float* grid, int32_t* area,
-                                  const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
-                                  int max_n, float* score_gem, void* workspace, void* stream) {
+extern "C" int hgl_heat_resize_aa(const float* heat_raw, int E, int hh, int hw, int H, int W, float* out, void* stream) {
+  using namespace hgl;
+  if (E == 0) return HGL_OK;
+  HGL_REQUIRE(heat_raw && out, "hgl_heat_resize_aa: null pointer");
+  HGL_REQUIRE(E > 0 && hh >= 1 && hw >= 1 && H >= 1 && W >= 1, "hgl_heat_resize_aa: bad shape");
+  const int blocks = (int)std::min<size_t>(((size_t)E * H * W + 255) / 256, (size_t)sm_count() * 16);
+  heat_resize_aa_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(heat_raw, E, hh, hw, H, W, out);
+  return launch_status("hgl_heat_resize_aa");
+}
+
+extern "C" int64_t hgl_grid_heat_pool_raw_workspace_bytes(int B, int M, int E, int H, int W, int g, int max_n, int hh, int hw) {
+  const int64_t base = hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, g, max_n);
+  if (base < 0 || hh < 1 || hw < 1) return -1;
+  return base + (int64_t)lr_full_bytes(E, H, W, hh, hw);
+}
+
+// the body of hgl_grid_heat_pool / hgl_grid_heat_pool_raw (hh == 0: heat is frame-sized)
+static int grid_heat_pool_impl(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g, float* grid, int32_t* area,
+                               const float* heat, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
+                               int max_n, float* score_gem, void* workspace, void* stream) {
   using namespace hgl;
   if (M == 0) return HGL_OK;
   if (E == 0) return hgl_mask_grid(bits, M, H, W, g, 1, grid, area, workspace, stream);
@@ -665,11 +780,28 @@ extern "C" int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off,
   cudaStream_t st = (cudaStream_t)stream;
   HeatWs ws;
   void* scratch = nullptr;
-  int rc = hgl_heat_common(heat, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  int rc = hgl_heat_common(heat, hh, hw, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
   if (rc != HGL_OK) return rc;
   RowsParams p = {};
   p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
   p.g = g; p.maxky = aa_maxk(H, g); p.maxkx = aa_maxk(W, g); p.grid = grid; p.area = area;
   hgl_fill_heat(p, ws, black, mask_off, expr_off, B, E, max_n, score_gem);
   return launch_rows(p, true, true, scratch, st);
+}
+
+extern "C" int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                                  float* grid, int32_t* area,
+                                  const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
+                                  int max_n, float* score_gem, void* workspace, void* stream) {
+  return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, heat, 0, 0, expr_off, dirflag, black, E, max_n, score_gem, workspace, stream);
+}
+
+extern "C" int hgl_grid_heat_pool_raw(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                                      float* grid, int32_t* area,
+                                      const float* heat_raw, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag,
+                                      const float* black, int E, int max_n, float* score_gem, void* workspace, void* stream) {
+  using namespace hgl;
+  HGL_REQUIRE(hh >= 1 && hw >= 1, "hgl_grid_heat_pool_raw: bad raw heat-map shape %dx%d", hh, hw);
+  return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, heat_raw, hh, hw, expr_off, dirflag, black, E, max_n, score_gem, workspace,
+                             stream);
 }

@@ -558,21 +558,18 @@ extern "C" int64_t hgl_prep_workspace_bytes(int B, int S, int out_dtype) {
   return (int64_t)hgl::prep_carve(nullptr, B, S, out_dtype).bytes;
 }
 
-extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off,
-                        int B, int M, int max_n, int H, int W, int S, int bg_mode, int out_dtype,
-                        void* local_out, void* global_out, void* workspace, void* stream) {
+// per-image half: needs the frames only, not the masks -- a caller may enqueue it while the masks are still being packed
+extern "C" int hgl_prep_setup(const uint8_t* image, const uint8_t* blur, int B, int H, int W, int S, int bg_mode, int out_dtype,
+                              void* workspace, void* stream) {
   using namespace hgl;
-  if (M == 0 && B >= 1) return HGL_OK;   // nothing to do (empty tensors have null data pointers)
-  HGL_REQUIRE(image && bits && local_out && global_out && workspace, "hgl_prep: null pointer");
+  HGL_REQUIRE(image && workspace, "hgl_prep: null pointer");
   HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK, "hgl_prep: bg_mode %d", bg_mode);
   HGL_REQUIRE(bg_mode != HGL_BG_BLUR || blur, "hgl_prep: blur frame required for HGL_BG_BLUR");
   HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep: out_dtype %d", out_dtype);
-  HGL_REQUIRE(B >= 1 && M >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_prep: bad shape B=%d M=%d H=%d W=%d max_n=%d", B, M, H, W, max_n);
+  HGL_REQUIRE(B >= 1 && H >= 1 && W >= 1, "hgl_prep: bad shape B=%d H=%d W=%d", B, H, W);
   HGL_REQUIRE(S >= 4 && S % 4 == 0 && S <= 1024, "hgl_prep: S=%d must be a multiple of 4 in [4,1024]", S);
-  HGL_REQUIRE(mask_off || B == 1, "hgl_prep: mask_off required when B > 1");
   HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hgl_prep: workspace must be 256-byte aligned");
-  HGL_REQUIRE(((reinterpret_cast<uintptr_t>(local_out) | reinterpret_cast<uintptr_t>(global_out)) & 15) == 0,
-              "hgl_prep: outputs must be 16-byte aligned");
+  HGL_REQUIRE(B <= 65535, "hgl_prep: batch too large for one launch (B=%d)", B);
   cudaStream_t st = (cudaStream_t)stream;
   const int SS = S * S;
   PrepWs ws = prep_carve(workspace, B, S, out_dtype);
@@ -581,8 +578,33 @@ extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_
     prep_setup_kernel<true><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps, ws.lut);
   else
     prep_setup_kernel<false><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps, ws.lut);
-  int rc = launch_status("hgl_prep(setup)");
+  return launch_status("hgl_prep(setup)");
+}
+
+extern "C" int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off,
+                        int B, int M, int max_n, int H, int W, int S, int bg_mode, int out_dtype,
+                        void* local_out, void* global_out, void* workspace, void* stream) {
+  if (M == 0 && B >= 1) return HGL_OK;   // nothing to do (empty tensors have null data pointers)
+  int rc = hgl_prep_setup(image, blur, B, H, W, S, bg_mode, out_dtype, workspace, stream);
   if (rc != HGL_OK) return rc;
+  return hgl_prep_main(bits, mask_off, B, M, max_n, H, W, S, out_dtype, local_out, global_out, workspace, stream);
+}
+
+// per-mask half: streams the packed masks over the answer planes hgl_prep_setup left in `workspace`
+extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int B, int M, int max_n, int H, int W, int S, int out_dtype,
+                             void* local_out, void* global_out, void* workspace, void* stream) {
+  using namespace hgl;
+  if (M == 0 && B >= 1) return HGL_OK;
+  HGL_REQUIRE(bits && local_out && global_out && workspace, "hgl_prep: null pointer");
+  HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep: out_dtype %d", out_dtype);
+  HGL_REQUIRE(B >= 1 && M >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_prep: bad shape B=%d M=%d H=%d W=%d max_n=%d", B, M, H, W, max_n);
+  HGL_REQUIRE(S >= 4 && S % 4 == 0 && S <= 1024, "hgl_prep: S=%d must be a multiple of 4 in [4,1024]", S);
+  HGL_REQUIRE(mask_off || B == 1, "hgl_prep: mask_off required when B > 1");
+  HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hgl_prep: workspace must be 256-byte aligned");
+  HGL_REQUIRE(((reinterpret_cast<uintptr_t>(local_out) | reinterpret_cast<uintptr_t>(global_out)) & 15) == 0,
+              "hgl_prep: outputs must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepWs ws = prep_carve(workspace, B, S, out_dtype);
 
   PrepParams p;
   p.bits = bits; p.mask_off = mask_off; p.planes = ws.planes; p.taps = ws.taps; p.lut = ws.lut;

@@ -118,20 +118,9 @@ def _bits(masks_or_bits: torch.Tensor, W: Optional[int] = None) -> torch.Tensor:
     return pack_masks(masks_or_bits)
 
 
-def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks: torch.Tensor, size: int,
-                        mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None, background: str = "blur",
-                        dtype: torch.dtype = torch.float32,
-                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                        workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S].
-    `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks()."""
+def _prep_frames(image: torch.Tensor, blur: Optional[torch.Tensor], background: str):
     img = image[None] if image.dim() == 3 else image
     _req(img, torch.uint8, "image", 4)
-    B, H, W, _ = img.shape
-    bits = _bits(masks)
-    M = bits.shape[0]
-    if tuple(bits.shape[1:]) != (H, (W + 31) // 32):
-        raise ValueError(f"masks {tuple(masks.shape)} do not match the frame {H}x{W}")
     bg = {"blur": HGL_BG_BLUR, "black": HGL_BG_BLACK}[background]
     bl = None
     if bg == HGL_BG_BLUR:
@@ -141,6 +130,70 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
         _req(bl, torch.uint8, "blur", 4)
         if bl.shape != img.shape:
             raise ValueError("blur must have the shape of image")
+    return img, bl, bg
+
+
+def _prep_workspace(B: int, size: int, dtype: torch.dtype, device, workspace: Optional[torch.Tensor]) -> torch.Tensor:
+    need = _lib.load().hgl_prep_workspace_bytes(B, size, _dt(dtype))
+    if need < 0:
+        raise ValueError(f"prep: unsupported size {size}")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=device)
+    return workspace
+
+
+def prep_setup(image: torch.Tensor, blur: Optional[torch.Tensor], size: int, background: str = "blur",
+               dtype: torch.dtype = torch.float32, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-image half of the prep loop (hgl_prep_setup): needs the frames only, so a caller can enqueue it while the masks are
+    still being packed on another stream.  Returns the workspace prep_main() consumes."""
+    img, bl, bg = _prep_frames(image, blur, background)
+    B, H, W, _ = img.shape
+    workspace = _prep_workspace(B, size, dtype, img.device, workspace)
+    check(_lib.load().hgl_prep_setup(img.data_ptr(), _ptr(bl), B, H, W, size, bg, _dt(dtype), workspace.data_ptr(), _stream()),
+          "hgl_prep_setup")
+    return workspace
+
+
+def prep_main(masks: torch.Tensor, frame_shape, size: int, workspace: torch.Tensor, mask_off: Optional[torch.Tensor] = None,
+              max_n: Optional[int] = None, dtype: torch.dtype = torch.float32,
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-mask half of the prep loop (hgl_prep_main) over the workspace prep_setup() filled.  frame_shape = (B, H, W)."""
+    B, H, W = (int(v) for v in frame_shape)
+    bits = _bits(masks)
+    M = bits.shape[0]
+    if tuple(bits.shape[1:]) != (H, (W + 31) // 32):
+        raise ValueError(f"masks {tuple(masks.shape)} do not match the frame {H}x{W}")
+    off = _offsets(mask_off, B, "mask_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    if out is None:
+        local = torch.empty((M, 3, size, size), dtype=dtype, device=bits.device)
+        glob = torch.empty_like(local)
+    else:
+        local, glob = out
+    _req(workspace, torch.uint8, "workspace", 1)
+    if workspace.numel() < _lib.load().hgl_prep_workspace_bytes(B, size, _dt(dtype)):
+        raise ValueError("prep_main: workspace smaller than hgl_prep_workspace_bytes()")
+    check(_lib.load().hgl_prep_main(bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, _dt(dtype), local.data_ptr(), glob.data_ptr(),
+                                    workspace.data_ptr(), _stream()), "hgl_prep_main")
+    return local, glob
+
+
+def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks: torch.Tensor, size: int,
+                        mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None, background: str = "blur",
+                        dtype: torch.dtype = torch.float32,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                        workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S].
+    `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks()."""
+    img, bl, bg = _prep_frames(image, blur, background)
+    B, H, W, _ = img.shape
+    bits = _bits(masks)
+    M = bits.shape[0]
+    if tuple(bits.shape[1:]) != (H, (W + 31) // 32):
+        raise ValueError(f"masks {tuple(masks.shape)} do not match the frame {H}x{W}")
     off = _offsets(mask_off, B, "mask_off")
     if max_n is None:
         if B != 1:
@@ -151,14 +204,9 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
         glob = torch.empty_like(local)
     else:
         local, glob = out
-    lib = _lib.load()
-    need = lib.hgl_prep_workspace_bytes(B, size, _dt(dtype))
-    if need < 0:
-        raise ValueError(f"prep: unsupported size {size}")
-    if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=img.device)
-    check(lib.hgl_prep(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, bg, _dt(dtype),
-                       local.data_ptr(), glob.data_ptr(), workspace.data_ptr(), _stream()), "hgl_prep")
+    workspace = _prep_workspace(B, size, dtype, img.device, workspace)
+    check(_lib.load().hgl_prep(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, bg, _dt(dtype),
+                               local.data_ptr(), glob.data_ptr(), workspace.data_ptr(), _stream()), "hgl_prep")
     return local, glob
 
 
@@ -242,6 +290,17 @@ def dir_mask(dirflag: str, height: int, width: int, device=None) -> torch.Tensor
     return out
 
 
+def heat_resize_aa(heat_raw: torch.Tensor, height: int, width: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T.Resize((H,W), antialias=True)(gem(...)[0]) Hybridgl_main.py:201: raw GEM maps f32 [E,h,w] -> f32 [E,H,W]."""
+    _req(heat_raw, torch.float32, "heat_raw", 3)
+    E, hh, hw = heat_raw.shape
+    if out is None:
+        out = torch.empty((E, height, width), dtype=torch.float32, device=heat_raw.device)
+    _req(out, torch.float32, "out", 3)
+    check(_lib.load().hgl_heat_resize_aa(heat_raw.data_ptr(), E, hh, hw, height, width, out.data_ptr(), _stream()), "hgl_heat_resize_aa")
+    return out
+
+
 def heat_pool(heat: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor, masks: torch.Tensor,
               mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -280,8 +339,9 @@ def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, d
     _req(heat, torch.float32, "heat", 3)
     M, H, W = bits.shape[0], bits.shape[1], int(width)
     E = heat.shape[0]
-    if bits.shape[2] != (W + 31) // 32 or tuple(heat.shape[1:]) != (H, W):
-        raise ValueError("packed masks, width and heat-map frames disagree")
+    if bits.shape[2] != (W + 31) // 32:
+        raise ValueError("packed masks and width disagree")
+    raw = tuple(heat.shape[1:]) != (H, W)     # the GEM map before T.Resize((H,W), antialias=True), Hybridgl_main.py:201
     _req(dirflag, torch.int32, "dirflag", 1)
     _req(black, torch.float32, "black", 1)
     B = 1 if mask_off is None else mask_off.numel() - 1
@@ -292,12 +352,19 @@ def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, d
             raise ValueError("max_n is required for batched calls")
         max_n = max(M, 1)
     lib = _lib.load()
-    need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, g, max_n)
+    hh, hw = int(heat.shape[1]), int(heat.shape[2])
+    need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, E, H, W, g, max_n, hh, hw) if raw
+            else lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, g, max_n))
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=bits.device)
     grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
     area = torch.empty((M,), dtype=torch.int32, device=bits.device)
     out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
+    if raw:
+        check(lib.hgl_grid_heat_pool_raw(bits.data_ptr(), _ptr(moff), B, M, H, W, g, grid.data_ptr(), area.data_ptr(),
+                                         heat.data_ptr(), hh, hw, _ptr(eoff), dirflag.data_ptr(), black.data_ptr(), E, max_n,
+                                         out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_grid_heat_pool_raw")
+        return grid, area, out
     check(lib.hgl_grid_heat_pool(bits.data_ptr(), _ptr(moff), B, M, H, W, g, grid.data_ptr(), area.data_ptr(),
                                  heat.data_ptr(), _ptr(eoff), dirflag.data_ptr(), black.data_ptr(), E, max_n,
                                  out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_grid_heat_pool")

@@ -120,25 +120,32 @@ class ScoringPath:
         local = self._get("local", (M, 3, self.size, self.size), self.prep_dtype)
         glob = self._get("global", (M, 3, self.size, self.size), self.prep_dtype)
         pws = self._get("prep_ws", (max(lib.hgl_prep_workspace_bytes(B, self.size, ops._dt(self.prep_dtype)), 1),), torch.uint8)
+        # the per-image half of prep (answer planes) needs the frames only: it runs while the side stream still packs the masks
+        with self._span("prep_setup"):
+            ops.prep_setup(img, blur, self.size, background=self.background, dtype=self.prep_dtype, workspace=pws)
         if ev_pack is not None:
             main.wait_event(ev_pack)
         with self._span("prep"):
-            ops.prep_visual_prompts(img, blur, bits, self.size, mask_off=moff, max_n=max_n, background=self.background,
-                                    dtype=self.prep_dtype, out=(local, glob), workspace=pws)
+            ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
             feats = features if features is not None else batch.get("features")
             E = batch["sent"].shape[0]
-            need = lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n)
+            heat = batch["heat"]       # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
+            raw = tuple(heat.shape[1:]) != (H, W)
+            need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, E, H, W, self.grid, max_n, heat.shape[1], heat.shape[2]) if raw
+                    else lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n))
             ws = self._get("heat_ws", (need,), torch.uint8)
             with self._span("grid_heat_pool"):
                 if self.antialias:     # mask grid + heat-map pooling share one pass over the packed masks
-                    grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, batch["heat"], batch["dirflag"], batch["black"],
+                    grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, heat, batch["dirflag"], batch["black"],
                                                                moff, eoff, max_n, workspace=ws)
                 else:
+                    if raw:
+                        heat = ops.heat_resize_aa(heat, H, W, out=self._get("heat_full", (E, H, W), torch.float32))
                     grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
-                    score_gem = ops.heat_pool(batch["heat"], batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
+                    score_gem = ops.heat_pool(heat, batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
             if self.feature_source == "tokens" and features is None:
                 mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
                 with self._span("mask_pool"):

@@ -28,6 +28,8 @@ class Expression:
     dirflag: str                         # extract_dir_phrase                          Hybridgl_main.py:143
     relaflag: str                        # extract_rela_word                           Hybridgl_main.py:177
     heatmap: np.ndarray                  # f32 [H,W]  GEM map after T.Resize           Hybridgl_main.py:200-201
+    heat_raw: Optional[np.ndarray] = None   # f32 [h',w'] the map as the GEM model returns it (before T.Resize, :200); an
+    #                                         alternative input: resize_bilinear_aa(heat_raw) replaces `heatmap` when the raw path is used
 
 
 @dataclasses.dataclass
@@ -191,7 +193,7 @@ def make_expression(rng: np.random.Generator, h: int, w: int, de: int,
           + coarse[y1][:, x0] * fy * (1 - fx) + coarse[y1][:, x1] * fy * fx).astype(np.float32)
     if bf16:
         sent, noun, other = bf16_round(sent), bf16_round(noun), bf16_round(other)
-    return Expression(sent, noun, other.reshape(n_other, de), dirflag, relaflag, hm)
+    return Expression(sent, noun, other.reshape(n_other, de), dirflag, relaflag, hm, coarse)
 
 
 def make_item(seed: int, h: int = 480, w: int = 640, n_masks: int = 64, n_expr: int = 1,
@@ -232,7 +234,7 @@ CONFIGS = {
 # device-side generator for benchmark-sized batches (same shapes / statistics, torch RNG on the GPU)
 # --------------------------------------------------------------------------------------------------
 def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_expr: int, de: int,
-                      device="cuda", n_other: int = 2, pinned_host: bool = False, grid: int = 14):
+                      device="cuda", n_other: int = 2, pinned_host: bool = False, grid: int = 14, raw_heat: bool = False):
     """RefCOCO-shaped batch laid out for the batched C ABI (ragged offsets, here uniform).
     Returns a dict of tensors on `device` (or pinned host tensors when pinned_host=True)."""
     import torch
@@ -277,7 +279,11 @@ def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_
     noun = (0.6 * sent + 0.8 * torch.randn((ET, de), generator=gen, device=device) + 1.5 * anchor).to(torch.bfloat16).float()
     others = torch.randn((ET * n_other, de), generator=gen, device=device).to(torch.bfloat16).float()
     other_off = (torch.arange(ET + 1, device=device) * n_other).to(torch.int32)
-    heat = torch.nn.functional.interpolate(rand(ET, 1, 28, 37), size=(h, w), mode="bilinear", align_corners=False)[:, 0].contiguous()
+    # GEM map: 448-short-side input, patch 16 -> 28 x 37.  raw_heat: hand the path the map as the model returns it
+    # (the T.Resize((H,W), antialias=True) of Hybridgl_main.py:201 then runs on the device); else a frame-sized map.
+    heat = rand(ET, 1, 28, 37)
+    heat = (heat[:, 0].contiguous() if raw_heat else
+            torch.nn.functional.interpolate(heat, size=(h, w), mode="bilinear", align_corners=False)[:, 0].contiguous())
     dirflag = torch.randint(0, 6, (ET,), generator=gen, device=device).to(torch.int32)
     relaflag = torch.randint(0, 8, (ET,), generator=gen, device=device).to(torch.int32)
     black = torch.where(relaflag == 5, 1.95, torch.where(relaflag == 6, 1.5, 1.8)).to(torch.float32)

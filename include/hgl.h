@@ -76,6 +76,15 @@ HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* 
              int B, int M, int max_n, int H, int W, int S, int bg_mode, int out_dtype,
              void* local_out, void* global_out, void* workspace, void* stream);
 
+/* hgl_prep in its two halves, for callers that overlap stages: hgl_prep_setup needs only the frames (per image: the
+ * "all taps inside" / "all taps outside" answer planes and the tap bytes, left in `workspace`) and may be enqueued while
+ * the masks are still being packed; hgl_prep_main streams the packed masks over them.  hgl_prep == setup then main on
+ * one stream; same arguments, same workspace. */
+HGL_API int hgl_prep_setup(const uint8_t* image, const uint8_t* blur, int B, int H, int W, int S, int bg_mode, int out_dtype,
+                   void* workspace, void* stream);
+HGL_API int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int B, int M, int max_n, int H, int W, int S, int out_dtype,
+                  void* local_out, void* global_out, void* workspace, void* stream);
+
 /* cv2.GaussianBlur(img,(15,15),0) on uint8, BORDER_REFLECT_101, OpenCV's Q8 fixed-point taps
  * (Hybridgl_main.py:99).  image/out u8 [B,H,W,3]. */
 HGL_API int hgl_gaussian_blur15(const uint8_t* image, uint8_t* out, int B, int H, int W, void* stream);
@@ -127,6 +136,20 @@ HGL_API int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, in
                        float* grid, int32_t* area,
                        const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
                        int max_n, float* score_gem, void* workspace, void* stream);
+
+/* (a10), first step: imgattn = T.Resize((H,W), antialias=True)(gem(...)[0]) (Hybridgl_main.py:201) -- ATen
+ * _upsample_bilinear2d_aa (separable triangle filter, horizontal pass then vertical pass), any scale.
+ * heat_raw f32 [E,hh,hw] (the GEM map as the model returns it) -> out f32 [E,H,W]. */
+HGL_API int hgl_heat_resize_aa(const float* heat_raw, int E, int hh, int hw, int H, int W, float* out, void* stream);
+/* hgl_grid_heat_pool on the RAW GEM maps: heat_raw f32 [E,hh,hw]; the resize of Hybridgl_main.py:201 is evaluated inside the
+ * prefix pass (the frame-sized heat-map never exists in HBM) when both axes are up-sampled, else materialised in the
+ * workspace first.  Same results as hgl_heat_resize_aa followed by hgl_grid_heat_pool.
+ * workspace: hgl_grid_heat_pool_raw_workspace_bytes(...) bytes. */
+HGL_API int64_t hgl_grid_heat_pool_raw_workspace_bytes(int B, int M, int E, int H, int W, int g, int max_n, int hh, int hw);
+HGL_API int hgl_grid_heat_pool_raw(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                           float* grid, int32_t* area,
+                           const float* heat_raw, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag,
+                           const float* black, int E, int max_n, float* score_gem, void* workspace, void* stream);
 
 /* ---- (b3') token-space mask pooling + L2 normalisation (tensor cores) ---------------------------------
  * The masks x tokens x D contraction of the north star; token-space form of the pooling loop Hybridgl_main.py:218-223

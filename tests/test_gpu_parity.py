@@ -309,6 +309,58 @@ def test_full_size_properties(ops):
     assert torch.all(grid[0] > 0.999999)
 
 
+# ------------------------------------------------------------------------------------------------ raw GEM map -> frame (a10, first step)
+def test_heat_resize_aa_matches_reference_golden(ops, golden):
+    """T.Resize((H,W), antialias=True)(gem(...)[0]) Hybridgl_main.py:201: device kernel vs the reference's own output."""
+    g = golden("scoring")
+    seen = 0
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        if "heat_resized" not in c:
+            continue
+        got = ops.heat_resize_aa(cu(c["heat_raw"]), c["h"], c["w"]).cpu().numpy()[0]
+        np.testing.assert_allclose(got, c["heat_resized"], rtol=0, atol=2e-7, err_msg=f"case {ci}")
+        assert np.array_equal(got, O.resize_bilinear_aa(c["heat_raw"], c["h"], c["w"])[0]), ci      # same op order as the oracle
+        seen += 1
+    assert seen >= 10
+
+
+@pytest.mark.parametrize("hh,hw,h,w", [(28, 37, 480, 640), (14, 14, 97, 131), (37, 28, 33, 20), (64, 80, 48, 200), (30, 40, 30, 40),
+                                       (448, 597, 480, 640), (3, 5, 600, 800), (1, 1, 17, 9)])
+def test_heat_resize_aa_vs_oracle_any_scale(ops, hh, hw, h, w):
+    rng = np.random.default_rng(hh * 1000 + hw)
+    raw = rng.random((3, hh, hw), dtype=np.float32)
+    got = ops.heat_resize_aa(cu(raw), h, w).cpu().numpy()
+    np.testing.assert_allclose(got, O.resize_bilinear_aa(raw, h, w), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("hh,hw,h,w", [(28, 37, 480, 640), (14, 19, 97, 131), (64, 80, 48, 200), (7, 40, 33, 20)])
+def test_grid_heat_pool_on_raw_maps_equals_resize_then_pool(ops, hh, hw, h, w):
+    """hgl_grid_heat_pool_raw (resize inside the prefix pass, or materialised when an axis is down-sampled) gives the very
+    same numbers as hgl_heat_resize_aa followed by hgl_grid_heat_pool, and matches the oracle chain resize -> condition -> pool."""
+    from hybridgl_b200._lib import DIR_CODES
+    rng = np.random.default_rng(h + w)
+    spec = [(5, 2), (3, 3), (8, 1)]
+    g = 4 if h < 100 else 14
+    masks = np.concatenate([synth.make_masks(rng, n, h, w) for n, _ in spec])
+    moff = np.cumsum([0] + [n for n, _ in spec]).astype(np.int32); eoff = np.cumsum([0] + [e for _, e in spec]).astype(np.int32)
+    E, max_n = int(eoff[-1]), max(n for n, _ in spec)
+    raw = rng.random((E, hh, hw), dtype=np.float32)
+    dirs = np.array([synth.DIRFLAGS[i % len(synth.DIRFLAGS)] for i in range(E)])
+    black = np.array([1.8, 1.95, 1.5, 1.8, 1.8, 1.5], np.float32)[:E]
+    bits = ops.pack_masks(cu(masks))
+    dd, db, dmo, deo = cu(np.array([DIR_CODES[d] for d in dirs], np.int32)), cu(black), cu(moff), cu(eoff)
+    g1, a1, s1 = ops.grid_heat_pool(bits, w, g, cu(raw), dd, db, dmo, deo, max_n)
+    full = ops.heat_resize_aa(cu(raw), h, w)
+    g2, a2, s2 = ops.grid_heat_pool(bits, w, g, full, dd, db, dmo, deo, max_n)
+    assert torch.equal(g1, g2) and torch.equal(a1, a2) and torch.equal(s1, s2)
+    ref_full = O.resize_bilinear_aa(raw, h, w)
+    for b, (n, e_cnt) in enumerate(spec):
+        for e in range(eoff[b], eoff[b + 1]):
+            ref = O.gem_pool(O.condition_heatmap(ref_full[e], str(dirs[e])), masks[moff[b]:moff[b + 1]], float(black[e]))
+            np.testing.assert_allclose(s1.cpu().numpy()[e, :n], ref, rtol=1e-3, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core mask pooling
 @pytest.mark.parametrize("B,n,L,D,dtype", [(1, 100, 196, 768, torch.float32), (2, 37, 196, 512, torch.float32), (1, 200, 576, 1024, torch.float32),
                                            (3, 130, 49, 64, torch.float32), (1, 5, 16, 32, torch.bfloat16), (2, 150, 196, 768, torch.bfloat16)])
@@ -444,3 +496,33 @@ def test_pipeline_rle_input_equals_byte_mask_input(ops):
         res[mode]["cum"] = path.cum.clone()
     for k in OUTPUT_KEYS + ("local_imgs", "global_imgs", "grid", "area", "bits", "cum"):
         assert torch.equal(res["bytes"][k], res["rle"][k]), k
+
+
+def test_pipeline_raw_heat_equals_resized_heat_and_overlap_is_invisible(ops):
+    """ScoringPath fed the raw GEM maps (resized inside the prefix pass) == the same maps resized first (hgl_heat_resize_aa);
+    the two-stream stage graph (overlap=True: prep_setup under the pack, side-stream chain) == the serial launch order."""
+    from hybridgl_b200.pipeline import OUTPUT_KEYS, ScoringPath
+    batch = synth.make_batch_device(91, 3, 120, 160, 12, 2, 64, device=DEV, grid=4, raw_heat=True)
+    assert tuple(batch["heat"].shape[1:]) == (28, 37)
+    res = {}
+    for mode in ("raw", "resized", "serial"):
+        path = ScoringPath(size=32, grid=4, prep_dtype=torch.float32, feature_source="tokens", overlap=(mode != "serial"))
+        b = dict(batch)
+        if mode == "resized":
+            b["heat"] = ops.heat_resize_aa(batch["heat"], 120, 160)
+        res[mode] = path.run(b, 12)
+        res[mode]["cum"] = path.cum.clone()
+    for k in OUTPUT_KEYS + ("local_imgs", "global_imgs", "grid", "area", "cum"):
+        assert torch.equal(res["raw"][k], res["resized"][k]), k
+        assert torch.equal(res["raw"][k], res["serial"][k]), k
+
+
+def test_prep_two_halves_equal_one_call(ops):
+    it = synth.make_item(61, 96, 128, 7, 0, with_features=False)
+    img, masks = cu(it.image), cu(it.masks)
+    blur = ops.gaussian_blur15(img)
+    for dt in (torch.float32, torch.bfloat16):
+        l1, g1 = ops.prep_visual_prompts(img, blur, masks, 32, dtype=dt)
+        ws = ops.prep_setup(img, blur, 32, dtype=dt)
+        l2, g2 = ops.prep_main(ops.pack_masks(masks), (1, 96, 128), 32, ws, dtype=dt)
+        assert torch.equal(l1, l2) and torch.equal(g1, g2)
