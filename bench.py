@@ -197,9 +197,11 @@ def algorithmic_bytes(cfg, B, prep_bytes):
         "prep_setup": 2 * B * H * W * 3 + B * S * S * (12 * prep_bytes + 24),
         # per-mask half: packed masks + answer planes in, 2 x [M,3,S,S] out
         "prep": M * H * ((W + 31) // 32) * 4 + B * S * S * 12 * prep_bytes + 2 * M * 3 * S * S * prep_bytes,
-        # one pass over the packed masks (grid + pooling) + the raw GEM maps (28 x 37, resized on the fly) + the row-prefix
-        # tables of the frame-sized conditioned maps written once
-        "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + ET * 28 * 37 * 4 + ET * H * W * 4 + ET * N * 4,
+        # heat-map tables (Hybridgl_main.py:201-209): raw GEM maps (28 x 37, resized on the fly) in, row-prefix tables of the
+        # frame-sized conditioned maps out, written once
+        "heat_tables": ET * 28 * 37 * 4 + ET * H * W * 4,
+        # one pass over the packed masks (mask grid + heat-map pooling): packed masks in, grid + pooled scores out
+        "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + ET * N * 4,
         # tensor-core pooling of the dense tokens: soft masks f32 + tokens bf16 in, pooled rows bf16 out (flops: MASK_POOL_FLOPS)
         "mask_pool": M * cfg["g"] ** 2 * 4 + B * cfg["g"] ** 2 * De * 2 + M * De * 2,
         "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
@@ -423,7 +425,8 @@ def run_ours(args, cfg):
                            f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
                            **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
-                "streams": ("2 (prep chain on the caller's stream, post-pack chain on a high-priority side stream)" if path.overlap else "1"),
+                "streams": ("2 (heat-map tables, blur and prep on the caller's stream; pack and the post-pack chain on a high-priority side stream)"
+                            if path.overlap else "1"),
                 "ms_per_step_serial": ms_serial,
                 "roofline": roofline, "kernels": kernels, "rle_input": rle_info, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],

@@ -28,6 +28,7 @@ constexpr int kMaxG = 32;          // grid side limit (14 for ViT-B/16, 24 for V
 constexpr int kRowsThreads = 256;  // one thread per bit row of a 256-row tile
 constexpr int kEB = 4;             // expressions pooled per pass over a mask
 constexpr int kPrefWarps = 8;
+constexpr int kPrefRows = 32;       // heat-map rows per CTA of heat_prefix_kernel
 
 // ---- shared with heat conditioning -----------------------------------------------------------------------------------
 __device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {  // ATen linspace (float): both-ends evaluation
@@ -109,104 +110,114 @@ static HeatWs heat_carve(void* ws, int E, int H, int W) {
 
 // One warp per (expression, row), 128 pixels per round: a lane owns 4 adjacent pixels (one 16-byte load, one 16-byte store),
 // scans them in registers, the 32 lane totals go through one shuffle scan, and a running carry links the rounds.  Row 0's
-// warp also emits the ramp prefix.  The ramp row is evaluated once per CTA (shared memory).
+// warp also emits the ramp prefix.  A CTA covers kPrefRows consecutive rows (kPrefRows / kPrefWarps per warp), so the
+// per-CTA tables (ramp row, and for kLR the horizontal pass below) are built once per 32 rows.
 //
 // kLR: `heat` is the RAW GEM map [E,hh,hw] and the frame-sized map of Hybridgl_main.py:201, T.Resize((H,W), antialias=True),
 // is evaluated on the fly (ATen _upsample_bilinear2d_aa, separable: horizontal pass, then vertical pass; for an up-sampler
-// the triangle filter has <= 3 taps per axis).  The x taps are built once per CTA in shared memory, the y taps once per warp;
-// the raw map (a few KB per expression) is read through L1.  The frame-sized heat-map then never exists in HBM.
+// the triangle filter has <= 3 taps per axis).  The 32 output rows of a CTA only see a handful of raw rows (kPrefRows*hh/H + 3),
+// so the CTA first runs the HORIZONTAL pass for those raw rows into shared memory (exactly ATen's intermediate tensor,
+// same tap order), and a pixel is then three shared-memory reads and the vertical taps.  The raw map (a few KB per
+// expression) is read through L1; the frame-sized heat-map never exists in HBM.
 template <bool kLR>
 __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag,
-                                                                      int H, int W, int Wp, int hh, int hw, float* __restrict__ cr,
+                                                                      int H, int W, int Wp, int hh, int hw, int nr_max, float* __restrict__ cr,
                                                                       float* __restrict__ rp, float* __restrict__ rowstat) {
-  extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]  (+ kLR: x taps, see below)
+  extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]  (+ kLR: hrow [nr_max][W128])
   const int e = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W128 = (W + 127) & ~127;
   const int dir = dirflag[e];
-  float* wxt = ramp + W128;                               // kLR: [W128][3] horizontal filter weights
-  int* xtap = reinterpret_cast<int*>(wxt + 3 * W128);     // kLR: [W128]    xmin | xsize << 16
+  const int y_first = blockIdx.x * kPrefRows, y_last = min(H, y_first + kPrefRows) - 1;
+  float* hrow = ramp + W128;                              // kLR: horizontal pass of raw rows [ry0, ry0 + nr)
+  int ry0 = 0, nr = 0;
+  if (kLR) {
+    int ym, ys;
+    float wtmp[3];
+    aa_fill(y_first, hh, H, 3, &ry0, &ys, wtmp);
+    aa_fill(y_last, hh, H, 3, &ym, &ys, wtmp);
+    nr = min(ym + ys - ry0, nr_max);
+  }
   for (int x = threadIdx.x; x < W128; x += blockDim.x) {
     ramp[x] = (x < W) ? ramp_at(dir, x, W) : 0.f;
-    if (kLR && x < W) {
-      int xm, xs;
-      aa_fill(x, hw, W, 3, &xm, &xs, wxt + 3 * x);
-      xtap[x] = xm | (xs << 16);
-    }
-  }
-  __syncthreads();
-  const int y = blockIdx.x * kPrefWarps + warp;
-  if (y >= H) return;                               // whole warp; no block-level barrier below
-  const float* A = kLR ? heat + (size_t)e * hh * hw : heat + ((size_t)e * H + y) * W;
-  const bool vec = !kLR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
-  int ymin = 0, ysize = 0;
-  float wy[3] = {0.f, 0.f, 0.f};
-  if (kLR) aa_fill(y, hh, H, 3, &ymin, &ysize, wy);
-  auto lr_pixel = [&](int x) -> float {              // one pixel of T.Resize((H,W), antialias=True)(raw map)
-    const int xt = xtap[x], xm = xt & 0xffff, xs = xt >> 16;
-    float o = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      if (ky < ysize) {
-        const float* r = A + (size_t)(ymin + ky) * hw + xm;
+    if (kLR) {
+      int xm = 0, xs = 0;
+      float wx[3] = {0.f, 0.f, 0.f};
+      if (x < W) aa_fill(x, hw, W, 3, &xm, &xs, wx);
+      const float* A0 = heat + ((size_t)e * hh + ry0) * hw + xm;
+      for (int r = 0; r < nr; ++r) {
         float t = 0.f;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
-          if (kx < xs) t = __fadd_rn(t, __fmul_rn(__ldg(r + kx), wxt[3 * x + kx]));
-        o = __fadd_rn(o, __fmul_rn(t, wy[ky]));
+          if (kx < xs) t = __fadd_rn(t, __fmul_rn(__ldg(A0 + (size_t)r * hw + kx), wx[kx]));
+        hrow[r * W128 + x] = t;
       }
     }
-    return o;
-  };
-  for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
-    float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
-    float mn = INFINITY, mx = -INFINITY, carry = 0.f;
-    for (int x0 = 0; x0 < W; x0 += 128) {
-      const int x = x0 + 4 * lane;
-      const float4 r4 = *reinterpret_cast<const float4*>(ramp + x);
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pass == 0) { a[0] = r4.x; a[1] = r4.y; a[2] = r4.z; a[3] = r4.w; }
-      else {
-        float h4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (kLR) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = lr_pixel(x + q);
-        } else if (vec && x + 3 < W) { const float4 v = __ldg(reinterpret_cast<const float4*>(A + x)); h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w; }
+  }
+  __syncthreads();
+  for (int y = y_first + warp; y <= y_last; y += kPrefWarps) {      // whole warps; no block-level barrier below
+    const float* A = heat + ((size_t)e * H + y) * W;                // !kLR only
+    const bool vec = !kLR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
+    int ymin = 0, ysize = 0;
+    float wy[3] = {0.f, 0.f, 0.f};
+    if (kLR) aa_fill(y, hh, H, 3, &ymin, &ysize, wy);
+    const float* hr = hrow + (ymin - ry0) * W128;
+    for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
+      float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
+      float mn = INFINITY, mx = -INFINITY, carry = 0.f;
+      for (int x0 = 0; x0 < W; x0 += 128) {
+        const int x = x0 + 4 * lane;
+        const float4 r4 = *reinterpret_cast<const float4*>(ramp + x);
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pass == 0) { a[0] = r4.x; a[1] = r4.y; a[2] = r4.z; a[3] = r4.w; }
         else {
+          float h4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (kLR) {                                         // vertical pass: o = sum_ky hrow[ymin+ky][x] * wy[ky], ascending ky
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = __ldg(A + x + q);
+            for (int ky = 0; ky < 3; ++ky) {
+              if (ky < ysize) {
+                const float4 t4 = *reinterpret_cast<const float4*>(hr + ky * W128 + x);
+                h4[0] = __fadd_rn(h4[0], __fmul_rn(t4.x, wy[ky])); h4[1] = __fadd_rn(h4[1], __fmul_rn(t4.y, wy[ky]));
+                h4[2] = __fadd_rn(h4[2], __fmul_rn(t4.z, wy[ky])); h4[3] = __fadd_rn(h4[3], __fmul_rn(t4.w, wy[ky]));
+              }
+            }
+          } else if (vec && x + 3 < W) { const float4 v = __ldg(reinterpret_cast<const float4*>(A + x)); h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w; }
+          else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (x + q < W) h4[q] = __ldg(A + x + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (x + q < W) { mn = fminf(mn, h4[q]); mx = fmaxf(mx, h4[q]); }
+          a[0] = __fmul_rn(h4[0], r4.x); a[1] = __fmul_rn(h4[1], r4.y); a[2] = __fmul_rn(h4[2], r4.z); a[3] = __fmul_rn(h4[3], r4.w);
         }
+        const float p0 = a[0], p1 = __fadd_rn(p0, a[1]), p2 = __fadd_rn(p1, a[2]), p3 = __fadd_rn(p2, a[3]);
+        float incl = p3;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (x + q < W) { mn = fminf(mn, h4[q]); mx = fmaxf(mx, h4[q]); }
-        a[0] = __fmul_rn(h4[0], r4.x); a[1] = __fmul_rn(h4[1], r4.y); a[2] = __fmul_rn(h4[2], r4.z); a[3] = __fmul_rn(h4[3], r4.w);
-      }
-      const float p0 = a[0], p1 = __fadd_rn(p0, a[1]), p2 = __fadd_rn(p1, a[2]), p3 = __fadd_rn(p2, a[3]);
-      float incl = p3;
+        for (int o = 1; o < 32; o <<= 1) {
+          const float nb = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl = __fadd_rn(incl, nb);
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);            // sum of the lanes before this one (exact, no subtraction)
+        if (lane == 0) excl = 0.f;
+        const float base = __fadd_rn(carry, excl);                     // exclusive prefix of this lane's first pixel
+        const float4 o4 = make_float4(base, __fadd_rn(base, p0), __fadd_rn(base, p1), __fadd_rn(base, p2));
+        if (x + 3 < Wp) *reinterpret_cast<float4*>(dst + x) = o4;      // entries beyond W inside the padded row are never read
+        else {
+          const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float nb = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl = __fadd_rn(incl, nb);
+          for (int q = 0; q < 4; ++q) if (x + q < Wp) dst[x + q] = ov[q];
+        }
+        carry = __fadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
       }
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);            // sum of the lanes before this one (exact, no subtraction)
-      if (lane == 0) excl = 0.f;
-      const float base = __fadd_rn(carry, excl);                     // exclusive prefix of this lane's first pixel
-      const float4 o4 = make_float4(base, __fadd_rn(base, p0), __fadd_rn(base, p1), __fadd_rn(base, p2));
-      if (x + 3 < Wp) *reinterpret_cast<float4*>(dst + x) = o4;      // entries beyond W inside the padded row are never read
-      else {
-        const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (x + q < Wp) dst[x + q] = ov[q];
+      if (lane == 0 && (W & 127) == 0) dst[W] = carry;              // otherwise the lane that owns index W wrote it above
+      if (pass == 1) {
+        mn = warp_min(mn); mx = warp_max(mx);
+        if (lane == 0) {
+          float* o = rowstat + ((size_t)e * H + y) * 4;
+          o[0] = mn; o[1] = mx; o[2] = carry; o[3] = 0.f;
+        }
       }
-      carry = __fadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
+      __syncwarp();
     }
-    if (lane == 0 && (W & 127) == 0) dst[W] = carry;              // otherwise the lane that owns index W wrote it above
-    if (pass == 1) {
-      mn = warp_min(mn); mx = warp_max(mx);
-      if (lane == 0) {
-        float* o = rowstat + ((size_t)e * H + y) * 4;
-        o[0] = mn; o[1] = mx; o[2] = carry; o[3] = 0.f;
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -638,12 +649,13 @@ static int launch_heat_tables(const float* heat, int hh, int hw, float* full, co
     heat = full; lr = false;
   }
   const size_t w128 = (size_t)((W + 127) & ~127);
-  const size_t smem = lr ? w128 * 4 * 5 : w128 * 4;
+  const int nr_max = lr ? (int)((double)kPrefRows * hh / H) + 4 : 0;       // raw rows behind the kPrefRows output rows of a CTA
+  const size_t smem = w128 * 4 * (1 + (size_t)nr_max);
   HGL_REQUIRE(smem <= 200 * 1024, "hgl_heat_pool: W=%d too wide", W);
   auto kern = lr ? heat_prefix_kernel<true> : heat_prefix_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
-  kern<<<dim3(ceil_div(H, kPrefWarps), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, hh, hw, ws.cr, ws.rp, ws.rowstat);
+  kern<<<dim3(ceil_div(H, kPrefRows), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, hh, hw, nr_max, ws.cr, ws.rp, ws.rowstat);
   int rc = launch_status("hgl_heat_pool(prefix)");
   if (rc != HGL_OK) return rc;
   heat_consts_kernel<<<E, 128, 0, st>>>(ws.rowstat, ws.rp, H, W, ws.Wp, ws.consts);
@@ -710,24 +722,49 @@ static size_t lr_full_bytes(int E, int H, int W, int hh, int hw) {
   return ((size_t)E * H * W * 4 + 255) & ~size_t(255);
 }
 
-// shared argument checks + table build of the pooling entry points (hh > 0: heat is the raw map [E,hh,hw])
-static int hgl_heat_common(const float* heat, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black,
-                           const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W, int max_n, float* score_gem,
-                           void* workspace, hgl::HeatWs* ws, void** scratch, cudaStream_t st) {
+// workspace carve-up shared by the table pass and the mask pass (hh > 0: heat is the raw map [E,hh,hw])
+static int hgl_heat_carve(void* workspace, int E, int H, int W, int hh, int hw, hgl::HeatWs* ws, float** full, void** scratch) {
   using namespace hgl;
-  HGL_REQUIRE(heat && dirflag && black && bits && score_gem && workspace, "hgl_heat_pool: null pointer");
-  HGL_REQUIRE(B >= 1 && M >= 0 && E >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_heat_pool: bad shape");
+  HGL_REQUIRE(workspace, "hgl_heat_pool: null pointer");
+  HGL_REQUIRE(E >= 0 && H >= 1 && W >= 1, "hgl_heat_pool: bad shape");
   HGL_REQUIRE(hh >= 0 && hw >= 0 && hw <= 65535 && (hh > 0) == (hw > 0), "hgl_heat_pool: bad raw heat-map shape %dx%d", hh, hw);
-  HGL_REQUIRE((mask_off && expr_off) || B == 1, "hgl_heat_pool: mask_off/expr_off required when B > 1");
   HGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hgl_heat_pool: workspace must be 16-byte aligned");
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   *ws = heat_carve(base, E, H, W);
   const size_t fb = lr_full_bytes(E, H, W, hh, hw);
-  float* full = fb ? reinterpret_cast<float*>(base + ws->bytes) : nullptr;
+  *full = fb ? reinterpret_cast<float*>(base + ws->bytes) : nullptr;
   *scratch = base + ws->bytes + fb;
+  return HGL_OK;
+}
+
+// the half of the pooling entry points that needs the heat-maps only (not the masks): prefix tables + per-expression constants
+extern "C" int hgl_heat_tables(const float* heat, int hh, int hw, const int32_t* dirflag, int E, int H, int W, void* workspace, void* stream) {
+  using namespace hgl;
+  if (E == 0) return HGL_OK;
+  HGL_REQUIRE(heat && dirflag, "hgl_heat_tables: null pointer");
+  HeatWs ws;
+  float* full = nullptr;
+  void* scratch = nullptr;
+  int rc = hgl_heat_carve(workspace, E, H, W, hh, hw, &ws, &full, &scratch);
+  if (rc != HGL_OK) return rc;
+  return launch_heat_tables(heat, hh, hw, full, dirflag, E, H, W, ws, (cudaStream_t)stream);
+}
+
+// argument checks of the mask pass + zeroing of its output rows; tables = 1: also build the tables here (one-call entry points)
+static int hgl_heat_common(const float* heat, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black,
+                           const uint32_t* bits, const int32_t* mask_off, int B, int M, int E, int H, int W, int max_n, float* score_gem,
+                           void* workspace, hgl::HeatWs* ws, void** scratch, int tables, cudaStream_t st) {
+  using namespace hgl;
+  HGL_REQUIRE(black && bits && score_gem && workspace, "hgl_heat_pool: null pointer");
+  HGL_REQUIRE(!tables || (heat && dirflag), "hgl_heat_pool: null pointer");
+  HGL_REQUIRE(B >= 1 && M >= 0 && E >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_heat_pool: bad shape");
+  HGL_REQUIRE((mask_off && expr_off) || B == 1, "hgl_heat_pool: mask_off/expr_off required when B > 1");
+  float* full = nullptr;
+  int rc = hgl_heat_carve(workspace, E, H, W, hh, hw, ws, &full, scratch);
+  if (rc != HGL_OK) return rc;
   cudaError_t e = cudaMemsetAsync(score_gem, 0, (size_t)E * max_n * 4, st);    // rows of images with fewer than max_n masks
   if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
-  return launch_heat_tables(heat, hh, hw, full, dirflag, E, H, W, *ws, st);
+  return tables ? launch_heat_tables(heat, hh, hw, full, dirflag, E, H, W, *ws, st) : HGL_OK;
 }
 
 static void hgl_fill_heat(hgl::RowsParams& p, const hgl::HeatWs& ws, const float* black, const int32_t* mask_off, const int32_t* expr_off,
@@ -744,7 +781,7 @@ extern "C" int hgl_heat_pool(const float* heat, const int32_t* expr_off, const i
   cudaStream_t st = (cudaStream_t)stream;
   HeatWs ws;
   void* scratch = nullptr;
-  int rc = hgl_heat_common(heat, 0, 0, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  int rc = hgl_heat_common(heat, 0, 0, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, 1, st);
   if (rc != HGL_OK) return rc;
   RowsParams p = {};
   p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
@@ -768,10 +805,11 @@ extern "C" int64_t hgl_grid_heat_pool_raw_workspace_bytes(int B, int M, int E, i
   return base + (int64_t)lr_full_bytes(E, H, W, hh, hw);
 }
 
-// the body of hgl_grid_heat_pool / hgl_grid_heat_pool_raw (hh == 0: heat is frame-sized)
+// the body of hgl_grid_heat_pool / hgl_grid_heat_pool_raw / hgl_grid_heat_pool_rows (hh == 0: heat is frame-sized;
+// tables == 0: hgl_heat_tables already ran on this workspace)
 static int grid_heat_pool_impl(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g, float* grid, int32_t* area,
                                const float* heat, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
-                               int max_n, float* score_gem, void* workspace, void* stream) {
+                               int max_n, float* score_gem, void* workspace, int tables, void* stream) {
   using namespace hgl;
   if (M == 0) return HGL_OK;
   if (E == 0) return hgl_mask_grid(bits, M, H, W, g, 1, grid, area, workspace, stream);
@@ -780,7 +818,8 @@ static int grid_heat_pool_impl(const uint32_t* bits, const int32_t* mask_off, in
   cudaStream_t st = (cudaStream_t)stream;
   HeatWs ws;
   void* scratch = nullptr;
-  int rc = hgl_heat_common(heat, hh, hw, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch, st);
+  int rc = hgl_heat_common(heat, hh, hw, expr_off, dirflag, black, bits, mask_off, B, M, E, H, W, max_n, score_gem, workspace, &ws, &scratch,
+                           tables, st);
   if (rc != HGL_OK) return rc;
   RowsParams p = {};
   p.bits = bits; p.M = M; p.H = H; p.W = W; p.WW = (W + 31) >> 5;
@@ -789,11 +828,19 @@ static int grid_heat_pool_impl(const uint32_t* bits, const int32_t* mask_off, in
   return launch_rows(p, true, true, scratch, st);
 }
 
+// the mask half after hgl_heat_tables(heat, hh, hw, ...) on the same workspace (hh = hw = 0 for frame-sized maps)
+extern "C" int hgl_grid_heat_pool_rows(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                                       float* grid, int32_t* area, int hh, int hw, const int32_t* expr_off, const float* black, int E,
+                                       int max_n, float* score_gem, void* workspace, void* stream) {
+  return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, nullptr, hh, hw, expr_off, nullptr, black, E, max_n, score_gem, workspace,
+                             0, stream);
+}
+
 extern "C" int hgl_grid_heat_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
                                   float* grid, int32_t* area,
                                   const float* heat, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
                                   int max_n, float* score_gem, void* workspace, void* stream) {
-  return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, heat, 0, 0, expr_off, dirflag, black, E, max_n, score_gem, workspace, stream);
+  return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, heat, 0, 0, expr_off, dirflag, black, E, max_n, score_gem, workspace, 1, stream);
 }
 
 extern "C" int hgl_grid_heat_pool_raw(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
@@ -803,5 +850,5 @@ extern "C" int hgl_grid_heat_pool_raw(const uint32_t* bits, const int32_t* mask_
   using namespace hgl;
   HGL_REQUIRE(hh >= 1 && hw >= 1, "hgl_grid_heat_pool_raw: bad raw heat-map shape %dx%d", hh, hw);
   return grid_heat_pool_impl(bits, mask_off, B, M, H, W, g, grid, area, heat_raw, hh, hw, expr_off, dirflag, black, E, max_n, score_gem, workspace,
-                             stream);
+                             1, stream);
 }

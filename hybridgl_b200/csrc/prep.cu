@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t half_of(const uint4 v) {   // 16 mask bytes 
 // W % 32 == 0 and 16-byte aligned base: the masks are one flat byte stream, word w = pixels [32w, 32w+32).
 // lane loads 16 B (fully coalesced 512 B per warp), neighbours pair up through one shuffle, even lanes store.
 __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __restrict__ src, size_t n16, uint32_t* __restrict__ bits) {
-  constexpr int kU = 4;   // independent 16-byte loads in flight per thread
+  constexpr int kU = 8;   // independent 16-byte loads in flight per thread
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + (kU - 1) * stride < n16; i += kU * stride) {
@@ -201,8 +201,8 @@ struct PrepParams {
   int B, M, H, W, S, WW;
   int stage_words;            // ring pitch of the shared-memory bit-row stages (words)
   int sub;                    // masks per stage
-  int gw, gh, cw, nbx;        // thread -> pixel map (PrepGeom)
-  int debug;                  // profiling only (HGL_PREP_DEBUG): 1 = skip the fix-up pass, 2 = skip the stores of P1
+  int gw, gh, cw, nbx, strip; // thread -> pixel map (PrepGeom)
+  int debug;                  // profiling only (HGL_PREP_DEBUG): 1 = skip the exact outline pixels, 2 = skip the stores
   int narrow;                 // 1 if the 8 taps of 4 adjacent pixels always fit one 32-bit window
 };
 
@@ -234,9 +234,9 @@ struct Pack {
 };
 
 // boundary pixel: exact per-tap evaluation (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel).
-// Only pixels whose taps straddle the mask outline come here, through the dense fix-up pass of each stage.
+// Only pixels whose taps straddle the mask outline come here, through the dense per-warp resolve step of prep_main_kernel.
 // lut: tables (built by prep_setup_kernel, L1-resident) of the two per-byte maps, [0..255] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255)
-// -- the same correctly-rounded divisions as to_unit / to_norm, evaluated once per CTA instead of 27 times per pixel.
+// -- the same correctly-rounded divisions as to_unit / to_norm, evaluated once per image batch instead of 27 times per pixel.
 __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__ taps, size_t tap0, int SS, uint32_t code,
                                                     float wx0, float wx1, float wy0, float wy1, const float* __restrict__ lut,
                                                     float* __restrict__ out6) {
@@ -263,9 +263,11 @@ __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__
   }
 }
 
-constexpr int kPrepQueue = 3072;    // boundary pixels a CTA can defer per stage (entry = k << 16 | local pixel << 4 | tap code)
 constexpr int kPrepStages = 3;      // shared-memory ring of bit-row stages
-constexpr int kPrepSubDefault = 8;  // masks per stage (PrepParams::sub; HGL_PREP_SUB overrides for tuning)
+constexpr int kPrepSubDefault = 4;  // masks per stage (PrepParams::sub; HGL_PREP_SUB overrides for tuning)
+constexpr int kPrepWq = 512;        // per-warp list of outline pixels waiting for their exact value (>= 32 lanes x 8 pixels)
+constexpr int kPrepMaxSub = 16;     // masks per stage, at most
+constexpr int kPrepWarpBytes = kPrepWq * 4;
 
 // Thread -> pixel map.  A lane owns PX adjacent output pixels (one 16-byte store per plane); the 32 lanes of a warp form a
 // 2-D patch of gw groups x gh rows (gw * gh = 32) and the cw warps of a CTA sit side by side, so a CTA covers a band of gh
@@ -273,8 +275,15 @@ constexpr int kPrepSubDefault = 8;  // masks per stage (PrepParams::sub; HGL_PRE
 // (longer) mixed-group path runs for ~10 % of the warp iterations instead of ~30 %.
 struct PrepGeom {
   int gw, gh, cw, nbx;     // groups per patch row, rows per patch, warps (patches) per CTA, CTAs per band
+  int strip;               // > 0: strip mode, = groups per output row (see hgl_prep_main)
 };
 __device__ __forceinline__ void prep_pixel_of(const PrepGeom& gm, int bxi, int byi, int t, int PX, int& i, int& j0) {
+  if (gm.strip) {          // the band's groups in row-major order: a warp = 32 consecutive groups = one contiguous run of the plane
+    const int r = t / gm.strip;
+    i = byi * gm.gh + r;
+    j0 = (t - r * gm.strip) * PX;
+    return;
+  }
   const int warp = t >> 5, lane = t & 31;
   const int gr = lane / gm.gw, gc = lane - gr * gm.gw;
   i = byi * gm.gh + gr;
@@ -282,31 +291,34 @@ __device__ __forceinline__ void prep_pixel_of(const PrepGeom& gm, int bxi, int b
 }
 
 // One CTA = a band tile of one image x a span of masks (blockIdx.z-th share of the image's masks), processed as a pipeline
-// of stages of kPrepSub masks:
-//   fill   the bit rows the band touches, for the masks of a stage, land in shared memory.  kTMA: one thread issues a 1-D
-//          bulk async copy (cp.async.bulk, SASS UBLKCP) per mask onto the stage's mbarrier, kPrepStages stages ahead of the
-//          consumer, so the load latency is hidden behind the stores of earlier stages; !kTMA (rows not 16-byte aligned):
-//          cooperative coalesced loads, one exposed latency per stage.
-//   P1     per mask: window from shared memory, FG/BG decision for the whole group, 6 streaming stores.  No global load in
-//          the loop; the FG/BG answers sit in registers for the CTA's whole span.  Groups cut by the outline are merged
-//          with two AND/compare per pixel; pixels whose own four taps straddle the outline get a placeholder and are queued.
-//   P2     dense fix-up per stage: one thread per queued pixel evaluates the exact formula and patches the freshly written
-//          line (L2 hit); a full queue makes the owning thread patch its pixel itself right after its store
-template <bool kBF16, int PX, bool kTMA>
+// of stages of kPrepSub masks with NO CTA-wide barrier in the steady state:
+//   producer  (kTMA) one extra warp: its lane 0 keeps the ring of bit-row stages full: it waits for a slot to be released
+//             (`empty` mbarrier, one arrival per consumer warp) and refills it -- one 1-D bulk async copy (cp.async.bulk, SASS
+//             UBLKCP) per mask onto the slot's `full` mbarrier.  !kTMA (rows not 16-byte aligned): cooperative loads between
+//             two __syncthreads per stage.
+//   consumers per mask: window from shared memory, then two warp votes.  A warp whose 32 groups lie entirely inside or
+//             entirely outside the mask (the common case) is six 16-byte streaming stores straight from the FG or BG answer
+//             registers -- no select, no per-pixel work, no global load; the answers sit in registers for the CTA's whole
+//             span.  Otherwise FG/BG are merged per pixel with bit masks; pixels whose own four taps straddle the outline get
+//             the BG value as a placeholder and are filed in the WARP's list (one shuffle scan).
+//   flush     at the end of a stage (or when the list is full) the warp evaluates its listed pixels exactly, one lane per
+//             pixel side by side (dense; ATen's op order), and patches the freshly written lines (L2).  Warps never wait for
+//             each other: they drift apart by up to kPrepStages stages, so a warp that crosses many outlines does not hold
+//             the others up.
+template <bool kBF16, int PX, bool kTMA, bool kNarrow>
 __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepParams p) {
   extern __shared__ __align__(128) uint8_t sm_prep[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages] (64 bytes reserved)
-  uint32_t* queue = reinterpret_cast<uint32_t*>(sm_prep + 64);                 // [kPrepQueue]
-  uint32_t* stage_base = queue + kPrepQueue;                                   // [kPrepStages][kPrepSub][stage_rows * WW], 16-byte aligned
-  __shared__ int q_count[2];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages]  (64 bytes reserved for both)
+  uint64_t* empty = full + kPrepStages;                                        // [kPrepStages]
   const float* lut = p.lut;
-  const int nthreads = blockDim.x;
 
   const int H = p.H, W = p.W, S = p.S, WW = p.WW;
   const int SS = S * S;
-  const PrepGeom gm = {p.gw, p.gh, p.cw, p.nbx};
+  const PrepGeom gm = {p.gw, p.gh, p.cw, p.nbx, p.strip};
+  const int ncons = 32 * gm.cw;                                                // consumer threads (the producer warp comes after them)
+  uint32_t* stage_base = reinterpret_cast<uint32_t*>(sm_prep + 64 + (size_t)gm.cw * kPrepWarpBytes);   // [kPrepStages][kPrepSub][rows * WW] + 16 B
   const int bxi = blockIdx.x % gm.nbx, byi = blockIdx.x / gm.nbx;
-  const int b = blockIdx.y, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int n_lo = 0, n_hi = p.M;
   if (p.mask_off) { n_lo = p.mask_off[b]; n_hi = p.mask_off[b + 1]; }
   {
@@ -328,29 +340,33 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const int stage_words = p.stage_words;                             // ring pitch (host: kPrepSub * max rows * WW)
   const uint32_t* src0 = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW;
 
-  // stage fill: masks [c*kPrepSub, ...) of the span into ring slot c % kPrepStages
-  auto issue = [&](int c) {                                          // kTMA: called by one thread
-    const int c0 = c * kPrepSub, cn = min(kPrepSub, cnt - c0);
-    uint32_t* dst = stage_base + (size_t)(c % kPrepStages) * stage_words;
-    uint64_t* bar = bars + (c % kPrepStages);
-    mbar_expect_tx(bar, (uint32_t)(cn * per_mask * 4));
-    for (int k = 0; k < cn; ++k) bulk_g2s(dst + k * per_mask, src0 + (size_t)(c0 + k) * mask_words, (uint32_t)(per_mask * 4), bar);
-  };
   if (kTMA) {
     if (tid == 0) {
-      for (int s = 0; s < kPrepStages; ++s) mbar_init(bars + s, 1);
+      for (int s = 0; s < kPrepStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (uint32_t)gm.cw); }
       mbar_fence_init();
     }
+    __syncthreads();
+    if (warp == gm.cw) {                                             // ---- producer warp
+      if (lane == 0 && !(p.debug & 4)) {
+        for (int c = 0; c < nst; ++c) {
+          const int slot = c % kPrepStages;
+          if (c >= kPrepStages) mbar_wait(empty + slot, (uint32_t)((c / kPrepStages - 1) & 1));
+          const int c0 = c * kPrepSub, cn = min(kPrepSub, cnt - c0);
+          uint32_t* dst = stage_base + (size_t)slot * stage_words;
+          mbar_expect_tx(full + slot, (uint32_t)(cn * per_mask * 4));
+          for (int k = 0; k < cn; ++k) bulk_g2s(dst + k * per_mask, src0 + (size_t)(c0 + k) * mask_words, (uint32_t)(per_mask * 4), full + slot);
+        }
+      }
+      return;
+    }
   }
-  if (tid == 0) { q_count[0] = 0; q_count[1] = 0; }
-  __syncthreads();
-  if (kTMA && tid == 0)
-    for (int c = 0; c < min(kPrepStages, nst); ++c) issue(c);
 
+  // ---- consumers
+  uint32_t* wq = reinterpret_cast<uint32_t*>(sm_prep + 64 + (size_t)warp * kPrepWarpBytes);   // [kPrepWq] mask << 16 | owner pixel << 4 | tap code
   int i, j0;
   prep_pixel_of(gm, bxi, byi, tid, PX, i, j0);
-  const bool live = i < S;                                           // partial last band
-  if (!live) { i = S - 1; }
+  const bool live = i <= row_last && j0 < S;                         // partial last band / idle lanes of the last warp (strip mode)
+  if (!live) { i = row_last; j0 = 0; }
   const Taps ty = make_taps(i, H, S);
   const int bx = make_taps(j0, W, S).i0;
   uint32_t tapmask = 0;
@@ -358,14 +374,13 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
 #pragma unroll
   for (int q = 0; q < PX; ++q) {
     tm[q] = 0;
-    if (p.narrow) {
+    if (kNarrow) {
       const Taps tx = make_taps(j0 + q, W, S);
       tm[q] = (1u << (tx.i0 - bx)) | (1u << (tx.i0 + tx.d - bx));
       tapmask |= tm[q];
     }
   }
-  const int wi = bx >> 5, sh = bx & 31;
-  const int wi1 = min(wi + 1, WW - 1);                               // clamped: bits beyond the row are never selected
+  const int wi = bx >> 5, sh = bx & 31;                              // the word after the window's first is always readable (see host)
   Pack<kBF16, PX> ans[12];
   const size_t px0 = (size_t)i * S + j0;
 #pragma unroll
@@ -373,143 +388,159 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
 
   constexpr size_t kElem = kBF16 ? 2 : 4;
   const size_t plane_bytes = (size_t)SS * kElem;
-  uint8_t* lp = reinterpret_cast<uint8_t*>(p.local_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
-  uint8_t* gp = reinterpret_cast<uint8_t*>(p.global_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
+  uint8_t* lp0 = reinterpret_cast<uint8_t*>(p.local_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;    // planes of mask n_lo
+  uint8_t* gp0 = reinterpret_cast<uint8_t*>(p.global_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
   const int row_off0 = (ty.i0 - ylo) * WW, row_off1 = row_off0 + ty.d * WW;
+  const size_t tap_base = (size_t)b * 6 * SS;
 
-  // exact value of one pixel whose taps straddle the outline of mask n_lo + kk; overwrites the placeholder
-  auto patch = [&](int kk, int pi, int pj, uint32_t code) {
-    const int gpx = pi * S + pj;
-    const Taps tyy = make_taps(pi, H, S), txx = make_taps(pj, W, S);
-    float o6[6];
-    prep_boundary_pixel(p.taps, (size_t)b * 6 * SS + gpx, SS, code, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
-    const size_t o = ((size_t)(n_lo + kk) * 3) * SS + gpx;
+  // exact values of the listed outline pixels (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel), one lane
+  // per pixel; overwrites the placeholders this warp stored earlier (ordered by the __syncwarp)
+  int wcount = 0;                                                    // entries in wq (warp-uniform)
+  auto flush = [&]() {
+    __syncwarp();
+    for (int t = lane; t < wcount; t += 32) {
+      const uint32_t ent = wq[t];
+      const int lpx = (int)((ent >> 4) & 0xfffu), ol_ = lpx / PX, oq = lpx - ol_ * PX;      // owner lane, pixel of its group
+      int pi, pj0;
+      prep_pixel_of(gm, bxi, byi, (warp << 5) | ol_, PX, pi, pj0);
+      const int pj = pj0 + oq, gpx = pi * S + pj;
+      const Taps tyy = make_taps(pi, H, S), txx = make_taps(pj, W, S);
+      float o6[6];
+      prep_boundary_pixel(p.taps, tap_base + gpx, SS, ent & 15u, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
+      const size_t o = ((size_t)(n_lo + (int)(ent >> 16)) * 3) * SS + gpx;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      if (kBF16) {
-        reinterpret_cast<__nv_bfloat16*>(p.local_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[ch]);
-        reinterpret_cast<__nv_bfloat16*>(p.global_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[3 + ch]);
-      } else {
-        reinterpret_cast<float*>(p.local_out)[o + (size_t)ch * SS] = o6[ch];
-        reinterpret_cast<float*>(p.global_out)[o + (size_t)ch * SS] = o6[3 + ch];
+      for (int ch = 0; ch < 3; ++ch) {
+        if (kBF16) {
+          reinterpret_cast<__nv_bfloat16*>(p.local_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[ch]);
+          reinterpret_cast<__nv_bfloat16*>(p.global_out)[o + (size_t)ch * SS] = __float2bfloat16_rn(o6[3 + ch]);
+        } else {
+          reinterpret_cast<float*>(p.local_out)[o + (size_t)ch * SS] = o6[ch];
+          reinterpret_cast<float*>(p.global_out)[o + (size_t)ch * SS] = o6[3 + ch];
+        }
       }
     }
+    __syncwarp();
+    wcount = 0;
   };
 
+  uint8_t* lp = lp0;
+  uint8_t* gp = gp0;
   for (int c = 0; c < nst; ++c) {
     const int c0 = c * kPrepSub, cn = min(kPrepSub, cnt - c0);
-    uint32_t* stage = stage_base + (size_t)(c % kPrepStages) * stage_words;
-    int* qc = &q_count[c & 1];
+    const int slot = c % kPrepStages;
+    uint32_t* stage = stage_base + (size_t)slot * stage_words;
     if (kTMA) {
-      mbar_wait(bars + (c % kPrepStages), (uint32_t)((c / kPrepStages) & 1));
+      if (!(p.debug & 4)) mbar_wait(full + slot, (uint32_t)((c / kPrepStages) & 1));
     } else {
+      __syncthreads();                                               // everybody is done with the previous stage
       const uint32_t* src = src0 + (size_t)c0 * mask_words;
-      for (int t = tid; t < cn * per_mask; t += nthreads) {
+      for (int t = tid; t < cn * per_mask; t += ncons) {
         const int k = t / per_mask, o = t - k * per_mask;
         stage[t] = __ldg(src + (size_t)k * mask_words + o);
       }
       __syncthreads();
     }
 
-    // ---- P1
+    // Every lane runs the loop (idle lanes only skip their stores): the warp-level steps use full-warp votes and shuffles.
     const uint32_t* s0 = stage + row_off0;                           // tap rows inside the stage of mask 0
     const uint32_t* s1 = stage + row_off1;
-    for (int k = 0; live && k < cn; ++k, s0 += per_mask, s1 += per_mask) {
-      Pack<kBF16, PX> ol[3], og[3];
-      bool uniform = false, inside = false;
-      uint32_t X = 0, Y = 0, overflow_any = 0;
-      if (p.narrow) {
-        const uint32_t a0 = __funnelshift_r(s0[wi], s0[wi1], sh);
-        const uint32_t a1 = __funnelshift_r(s1[wi], s1[wi1], sh);
-        X = a0 & a1; Y = a0 | a1;                                    // bit set: column inside on both / on either tap row
-        inside = (X & tapmask) == tapmask;
-        uniform = inside || ((Y & tapmask) == 0u);
-      }
-      if (uniform) {
+    for (int k = 0; k < cn; ++k, s0 += per_mask, s1 += per_mask, lp += 3 * plane_bytes, gp += 3 * plane_bytes) {
+      uint32_t a0 = 0, a1 = 0, in_bits = 0, bnd_bits = 0, codes = 0;   // bit q: pixel q fully inside / ON the outline; !kNarrow: 4-bit tap codes
+      if (kNarrow) {
+        if (!(p.debug & 8)) {
+          a0 = __funnelshift_r(s0[wi], s0[wi + 1], sh);
+          a1 = __funnelshift_r(s1[wi], s1[wi + 1], sh);
+        }
+        const uint32_t X = a0 & a1, Y = a0 | a1;                     // bit set: column inside on both / on either tap row
+        const bool all_in = __all_sync(0xffffffffu, (X & tapmask) == tapmask);
+        const bool all_out = __all_sync(0xffffffffu, (Y & tapmask) == 0u);
+        if (all_in || all_out) {                                     // all 32 groups on one side of the outline (warp-uniform)
+          if (live && !(p.debug & 2)) {
+            if (all_in) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
+              for (int ch = 0; ch < 3; ++ch) { ans[0 + ch].store(lp + (size_t)ch * plane_bytes); ans[3 + ch].store(gp + (size_t)ch * plane_bytes); }
+            } else {
 #pragma unroll
-          for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
-            ol[ch].w[w] = inside ? ans[0 + ch].w[w] : ans[6 + ch].w[w];
-            og[ch].w[w] = inside ? ans[3 + ch].w[w] : ans[9 + ch].w[w];
+              for (int ch = 0; ch < 3; ++ch) { ans[6 + ch].store(lp + (size_t)ch * plane_bytes); ans[9 + ch].store(gp + (size_t)ch * plane_bytes); }
+            }
           }
+          continue;
+        }
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          const bool in_q = (X & tm[q]) == tm[q];
+          in_bits |= (in_q ? 1u : 0u) << q;
+          bnd_bits |= ((!in_q && (Y & tm[q]) != 0u) ? 1u : 0u) << q;
         }
       } else {
-        // mixed group: per-pixel FG/BG merge with bit masks; pixels whose own taps straddle the outline keep the BG
-        // placeholder and are queued with their 4-bit tap code
-        uint32_t in_bits = 0;               // bit q: pixel q fully inside
 #pragma unroll
         for (int q = 0; q < PX; ++q) {
-          bool in_q, bnd_q;
-          if (p.narrow) {
-            in_q = (X & tm[q]) == tm[q];
-            bnd_q = !in_q && (Y & tm[q]) != 0u;
-          } else {
-            const Taps tx = make_taps(j0 + q, W, S);
-            const int xa = tx.i0, xb = tx.i0 + tx.d;
-            const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
-                                  (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
-            in_q = code == 15u; bnd_q = code != 15u && code != 0u;
-          }
-          in_bits |= (in_q ? 1u : 0u) << q;
-          if (bnd_q) {                                               // rare: a pixel ON the outline
-            const Taps tx = make_taps(j0 + q, W, S);
-            const int xa = tx.i0, xb = tx.i0 + tx.d;
-            const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
-                                  (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
-            const int slot = atomicAdd(qc, 1);
-            if (slot < kPrepQueue) queue[slot] = ((uint32_t)k << 16) | ((uint32_t)(tid * PX + q) << 4) | code;
-            else overflow_any |= 1u << q;                                  // queue full: this thread patches the pixel itself below
-          }
-        }
-#pragma unroll
-        for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
-          uint32_t m;                        // all-ones in the lanes of pixels that are fully inside
-          if (kBF16) m = (((in_bits >> (2 * w)) & 1u) ? 0x0000ffffu : 0u) | (((in_bits >> (2 * w + 1)) & 1u) ? 0xffff0000u : 0u);
-          else m = ((in_bits >> w) & 1u) ? 0xffffffffu : 0u;
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            ol[ch].w[w] = (ans[0 + ch].w[w] & m) | (ans[6 + ch].w[w] & ~m);
-            og[ch].w[w] = (ans[3 + ch].w[w] & m) | (ans[9 + ch].w[w] & ~m);
-          }
-        }
-      }
-      if (!(p.debug & 2)) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          ol[ch].store(lp + (size_t)ch * plane_bytes);
-          og[ch].store(gp + (size_t)ch * plane_bytes);
-        }
-      } else if (ol[0].w[0] == 0x12345u && og[2].w[1] == 0x54321u) {
-        ol[0].store(lp);
-      }
-      if (overflow_any) {                                            // queue full (pathological outlines): same thread, program order
-        for (int q = 0; q < PX; ++q) {
-          if (!((overflow_any >> q) & 1u)) continue;
           const Taps tx = make_taps(j0 + q, W, S);
           const int xa = tx.i0, xb = tx.i0 + tx.d;
           const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
                                 (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
-          patch(c0 + k, i, j0 + q, code);
+          in_bits |= (code == 15u ? 1u : 0u) << q;
+          bnd_bits |= ((code != 15u && code != 0u) ? 1u : 0u) << q;
+          codes |= code << (4 * q);
         }
       }
-      lp += 3 * plane_bytes; gp += 3 * plane_bytes;
+      // groups cut by the outline: per-pixel FG/BG merge with bit masks; outline pixels keep the BG value as a placeholder
+      Pack<kBF16, PX> ol[3], og[3];
+#pragma unroll
+      for (int w = 0; w < Pack<kBF16, PX>::NW; ++w) {
+        uint32_t m;                        // all-ones in the lanes of pixels that are fully inside
+        if (kBF16) m = (((in_bits >> (2 * w)) & 1u) ? 0x0000ffffu : 0u) | (((in_bits >> (2 * w + 1)) & 1u) ? 0xffff0000u : 0u);
+        else m = ((in_bits >> w) & 1u) ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          ol[ch].w[w] = (ans[0 + ch].w[w] & m) | (ans[6 + ch].w[w] & ~m);
+          og[ch].w[w] = (ans[3 + ch].w[w] & m) | (ans[9 + ch].w[w] & ~m);
+        }
+      }
+      if (live) {
+        if (!(p.debug & 2)) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            ol[ch].store(lp + (size_t)ch * plane_bytes);
+            og[ch].store(gp + (size_t)ch * plane_bytes);
+          }
+        } else if (ol[0].w[0] == 0x12345u && og[2].w[1] == 0x54321u) {
+          ol[0].store(lp);
+        }
+      }
+      if (!live || (p.debug & 1)) bnd_bits = 0;
+      // file the outline pixels.  Tap code: bit t = tap t inside; taps ordered (row0,x0) (row0,x1) (row1,x0) (row1,x1).
+      if (__any_sync(0xffffffffu, bnd_bits != 0u)) {
+        const uint32_t mine = __popc(bnd_bits);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += nb;
+        }
+        const int total = (int)__shfl_sync(0xffffffffu, incl, 31);   // <= 32 * PX <= kPrepWq
+        if (wcount + total > kPrepWq) flush();                        // earlier masks only: their placeholders are stored
+        int slot_w = wcount + (int)(incl - mine);
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {                                 // unrolled: tm[] stays in registers
+          if (!((bnd_bits >> q) & 1u)) continue;
+          uint32_t code;
+          if (kNarrow) {
+            const int pa = __ffs(tm[q]) - 1, pb = 31 - __clz(tm[q]);   // window bits of the pixel's two tap columns
+            code = ((a0 >> pa) & 1u) | (((a0 >> pb) & 1u) << 1) | (((a1 >> pa) & 1u) << 2) | (((a1 >> pb) & 1u) << 3);
+          } else {
+            code = (codes >> (4 * q)) & 15u;
+          }
+          wq[slot_w++] = ((uint32_t)(c0 + k) << 16) | ((uint32_t)(lane * PX + q) << 4) | code;
+        }
+        wcount += total;
+      }
     }
-    // ---- P2: dense fix-up of the queued boundary pixels of this stage.  (A barrier per stage measured faster than
-    //      barrier-free ring slots with one fix-up pass per CTA: it keeps the CTA's warps writing the same lines together
-    //      and the patched lines are still in L2.)
-    __syncthreads();
-    const int nq = (p.debug & 1) ? 0 : min(*qc, kPrepQueue);
-    for (int e = tid; e < nq; e += nthreads) {
-      const uint32_t ent = queue[e];
-      const int lpx = (ent >> 4) & 0xfff;
-      int pi, pj0;
-      prep_pixel_of(gm, bxi, byi, lpx / PX, PX, pi, pj0);
-      patch(c0 + (int)(ent >> 16), pi, pj0 + lpx % PX, ent & 15u);
+    if (wcount) flush();
+    if (kTMA) {                                                       // this warp is done with the slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
     }
-    if (tid == 0) q_count[(c + 1) & 1] = 0;            // the other counter: nobody touches it between the two barriers
-    __syncthreads();                                   // stage slot and queue are free again
-    if (kTMA && tid == 0 && c + kPrepStages < nst) issue(c + kPrepStages);
   }
 }
 
@@ -543,7 +574,12 @@ extern "C" int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_
   cudaStream_t st = (cudaStream_t)stream;
   if ((W & 31) == 0 && (reinterpret_cast<uintptr_t>(masks) & 15) == 0) {
     const size_t n16 = rows * W / 16;
-    const int blocks = (int)std::min<size_t>((n16 + 256 * 4 - 1) / (256 * 4), (size_t)sm_count() * 8);
+    // persistent grid-stride CTAs.  HBM is saturated by the bytes in flight (8 x 16 B per thread), not by the thread count, so
+    // the kernel only takes a quarter of every SM's thread slots (measured fastest alone, too): kernels of a concurrent stream (blur, prep setup, heat-map
+    // tables in the batched pipeline) then run beside it instead of queueing behind a grid that fills the machine.
+    int per_sm = 2;
+    if (const char* pv = getenv("HGL_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(pv)));     // tuning hook
+    const int blocks = (int)std::min<size_t>((n16 + 256 * 8 - 1) / (256 * 8), (size_t)sm_count() * per_sm);
     pack_masks_flat_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const uint4*>(masks), n16, bits);
   } else {
     const size_t total = rows * ((W + 31) >> 5);
@@ -619,25 +655,42 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   int gw = 1;
   while (gw < 8 && G % (gw * 2) == 0) gw *= 2;
   const int gh = 32 / gw, ppr = G / gw;
+  // 1-D bulk copies need 16-byte aligned rows: WW % 4 == 0 and an aligned base; otherwise cooperative loads
+  const bool tma = (p.WW % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
   int cw = 1;
-  for (int d = 1; d <= 8; ++d) if (ppr % d == 0) cw = d;
-  p.gw = gw; p.gh = gh; p.cw = cw; p.nbx = ppr / cw;
-  const int nby = ceil_div(S, gh);
-  const int threads = 32 * cw;
+  for (int d = 1; d <= (tma ? 7 : 8); ++d) if (ppr % d == 0) cw = d;        // kTMA: one more warp (the producer) joins the CTA
+  p.gw = gw; p.gh = gh; p.cw = cw; p.nbx = ppr / cw; p.strip = 0;
+  // strip mode (default whenever a row's groups fit one CTA): a CTA owns R whole output rows and its lanes walk the band's
+  // groups in row-major order, so every warp-wide store is one contiguous, 128-byte aligned 512-byte run of a plane (full
+  // lines; measured 6.2 TB/s of pure stores against 5.1 TB/s for 2-D patches of 64-byte row pieces).  The last warp may
+  // have idle lanes when R * G is not a multiple of 32.
+  const int max_cons = tma ? kPrepThreads - 32 : kPrepThreads;
+  if (G <= max_cons && !getenv("HGL_PREP_PATCH")) {
+    const int R = max_cons / G;
+    p.strip = G; p.gh = R; p.cw = ceil_div(R * G, 32); p.nbx = 1; p.gw = 1;
+  }
+  const int gh_ = p.gh; cw = p.cw;
+  const int nby = ceil_div(S, gh_);
+  const int threads = 32 * cw + (tma ? 32 : 0);
   // the 2*px tap columns of a lane must fit one 32-bit window for the fast path
   // grid: (band tiles, images, z) -- z splits an image's masks so that the launch fills whole waves of resident CTAs
   const int gx = p.nbx * nby;
   const int per_image = (B == 1) ? M : std::min(max_n, M);
   const double sy = (double)H / (double)S;
-  const int stage_rows = std::min(H, (int)(gh * sy) + 3);                    // source rows behind a band
+  const int stage_rows = std::min(H, (int)(gh_ * sy) + 3);                    // source rows behind a band
   const size_t per_mask_bytes = (size_t)stage_rows * p.WW * 4;
+  // barriers | per-warp scratch | stages (+ the word after the last row)
+  const size_t fixed_smem = 64 + (size_t)cw * kPrepWarpBytes + 16;
+  const size_t stage_budget = fixed_smem + 24 * 1024 <= 112 * 1024 ? 112 * 1024 - fixed_smem      // two CTAs per SM
+                                                                     : (fixed_smem < 200 * 1024 ? 224 * 1024 - fixed_smem : 0);
   int kPrepSub = kPrepSubDefault;
-  if (const char* sv = getenv("HGL_PREP_SUB")) kPrepSub = std::max(1, std::min(32, atoi(sv)));
-  while (kPrepSub > 1 && (size_t)kPrepStages * kPrepSub * per_mask_bytes > 96 * 1024) kPrepSub /= 2;
+  if (const char* sv = getenv("HGL_PREP_SUB")) kPrepSub = std::max(1, std::min(kPrepMaxSub, atoi(sv)));
+  while (kPrepSub > 1 && (size_t)kPrepStages * kPrepSub * per_mask_bytes > std::min<size_t>(stage_budget, 96 * 1024)) kPrepSub /= 2;
   p.sub = kPrepSub;
-  HGL_REQUIRE((size_t)kPrepStages * kPrepSub * per_mask_bytes <= 160 * 1024, "hgl_prep: frame %dx%d too large for the bit-row stages", H, W);
+  HGL_REQUIRE((size_t)kPrepStages * kPrepSub * per_mask_bytes <= stage_budget, "hgl_prep: frame %dx%d (S=%d) too large for the shared-memory stages",
+              H, W, S);
   p.stage_words = (int)(kPrepSub * per_mask_bytes / 4);
-  const size_t smem = 64 + (size_t)kPrepQueue * 4 + (size_t)kPrepStages * kPrepSub * per_mask_bytes;
+  const size_t smem = fixed_smem + (size_t)kPrepStages * kPrepSub * per_mask_bytes;
   const int resident = std::max(1, std::min(std::min(2 * kPrepThreads / threads, (int)((220 * 1024) / smem)), 65536 / (threads * 128)));
   const long slots = (long)sm_count() * resident;
   int gz = 1;
@@ -655,17 +708,19 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   if (const char* dv = getenv("HGL_PREP_DEBUG")) p.debug = atoi(dv);              // profiling only: results are wrong when set
   dim3 grid(gx, B, gz);
   HGL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "hgl_prep: batch too large for one launch (B=%d, max_n=%d)", B, max_n);
-  // 1-D bulk copies need 16-byte aligned rows: WW % 4 == 0 and an aligned base; otherwise cooperative loads
-  const bool tma = (p.WW % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, threads, smem, st>>>(p);
   };
+  HGL_REQUIRE(per_image <= 65535 * gz, "hgl_prep: more than 65535 masks of one image per CTA span");
+  const bool nw = p.narrow != 0;
   if (out_dtype == HGL_BF16) {
-    if (px == 8) { if (tma) launch(prep_main_kernel<true, 8, true>); else launch(prep_main_kernel<true, 8, false>); }
-    else { if (tma) launch(prep_main_kernel<true, kPrepPx, true>); else launch(prep_main_kernel<true, kPrepPx, false>); }
+    if (px == 8) { if (tma) launch(prep_main_kernel<true, 8, true, true>); else launch(prep_main_kernel<true, 8, false, true>); }
+    else if (nw) { if (tma) launch(prep_main_kernel<true, kPrepPx, true, true>); else launch(prep_main_kernel<true, kPrepPx, false, true>); }
+    else { if (tma) launch(prep_main_kernel<true, kPrepPx, true, false>); else launch(prep_main_kernel<true, kPrepPx, false, false>); }
   } else {
-    if (tma) launch(prep_main_kernel<false, kPrepPx, true>); else launch(prep_main_kernel<false, kPrepPx, false>);
+    if (nw) { if (tma) launch(prep_main_kernel<false, kPrepPx, true, true>); else launch(prep_main_kernel<false, kPrepPx, false, true>); }
+    else { if (tma) launch(prep_main_kernel<false, kPrepPx, true, false>); else launch(prep_main_kernel<false, kPrepPx, false, false>); }
   }
   return launch_status("hgl_prep(main)");
 }

@@ -371,6 +371,39 @@ def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, d
     return grid, area, out
 
 
+def heat_tables(heat: torch.Tensor, dirflag: torch.Tensor, H: int, W: int, workspace: torch.Tensor) -> None:
+    """First half of grid_heat_pool: the heat-map tables (Hybridgl_main.py:201-209).  Needs the heat-maps only, so a caller can
+    enqueue it while the masks are still being packed.  heat f32 [E,H,W], or the raw GEM map [E,hh,hw]."""
+    _req(heat, torch.float32, "heat", 3)
+    _req(dirflag, torch.int32, "dirflag", 1)
+    raw = tuple(heat.shape[1:]) != (int(H), int(W))
+    hh, hw = (int(heat.shape[1]), int(heat.shape[2])) if raw else (0, 0)
+    check(_lib.load().hgl_heat_tables(heat.data_ptr(), hh, hw, dirflag.data_ptr(), heat.shape[0], int(H), int(W), workspace.data_ptr(),
+                                      _stream()), "hgl_heat_tables")
+
+
+def grid_heat_pool_rows(bits: torch.Tensor, width: int, g: int, heat_shape, black: torch.Tensor, mask_off: Optional[torch.Tensor],
+                        expr_off: Optional[torch.Tensor], max_n: int, workspace: torch.Tensor):
+    """Second half of grid_heat_pool: the pass over the packed masks, after heat_tables(...) on the same workspace.
+    heat_shape = heat.shape of the tensor given to heat_tables.  Returns (grid, area, score_gem) like grid_heat_pool."""
+    _req(bits, torch.int32, "bits", 3)
+    _req(black, torch.float32, "black", 1)
+    M, H, W = bits.shape[0], bits.shape[1], int(width)
+    E = int(heat_shape[0])
+    raw = tuple(heat_shape[1:]) != (H, W)
+    hh, hw = (int(heat_shape[1]), int(heat_shape[2])) if raw else (0, 0)
+    B = 1 if mask_off is None else mask_off.numel() - 1
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
+    area = torch.empty((M,), dtype=torch.int32, device=bits.device)
+    out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
+    check(_lib.load().hgl_grid_heat_pool_rows(bits.data_ptr(), _ptr(moff), B, M, H, W, g, grid.data_ptr(), area.data_ptr(), hh, hw,
+                                              _ptr(eoff), black.data_ptr(), E, max_n, out.data_ptr(), workspace.data_ptr(), _stream()),
+          "hgl_grid_heat_pool_rows")
+    return grid, area, out
+
+
 # ---- (b3') --------------------------------------------------------------------------------------------
 def mask_pool(weights: torch.Tensor, tokens: torch.Tensor, mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
               normalize: bool = True, dtype: torch.dtype = torch.float32, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:

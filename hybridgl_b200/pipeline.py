@@ -48,6 +48,8 @@ class ScoringPath:
         self.events = None            # optional per-stage CUDA event pairs (bench.py): [(stage, start, end)]
         self.overlap = overlap        # fork the post-pack chain onto a high-priority side stream (see run())
         self._side: Optional[torch.cuda.Stream] = None
+        self._pre: Optional[torch.cuda.Stream] = None
+        self._tab: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype) -> torch.Tensor:
@@ -81,10 +83,14 @@ class ScoringPath:
         """One pass over a device-resident batch.  Returns device tensors (see OUTPUT_KEYS) plus the prep
         outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M].
 
-        Stage graph (self.overlap=True): the bandwidth-bound chain  blur -> prep  stays on the caller's stream; the chain
-        pack (or RLE decode) -> mask grid + heat-map pooling -> [mask pooling] -> score/select -> IoU  (small, latency-bound kernels after
-        the pack) is forked onto a high-priority side stream, so it runs in the shadow of the prep writes.  Both chains are
-        joined before run() returns; with overlap=False every stage is launched in order on the caller's stream."""
+        Stage graph (self.overlap=True), four streams forked from / joined to the caller's stream:
+            side  pack (or RLE decode) ---------+--> mask grid + heat-map pooling -> [mask pooling] -> score/select -> IoU
+            pre   blur -> prep setup ------+    |         ^
+            tab   heat-map tables ---------|----|---------+
+            main  (caller's stream)        +----+--> prep main (the bandwidth-bound bulk)
+        The pack runs with a small SM footprint, so the frame-only and heat-map-only kernels run beside it; the small,
+        latency-bound kernels after the pack run at high priority in the shadow of the prep writes.  With overlap=False every
+        stage is launched in order on the caller's stream."""
         img = batch["image"]
         B, H, W, _ = img.shape
         rle = "rle_counts" in batch          # proposals as SAM uncompressed RLE instead of byte masks
@@ -93,12 +99,15 @@ class ScoringPath:
         moff, eoff = batch["mask_off"], batch["expr_off"]
         lib = ops._lib.load()
         main = torch.cuda.current_stream()
-        side = main
+        side = pre = tab = main
         if self.overlap:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device, priority=-1)
-            side = self._side
-            side.wait_stream(main)
+                self._pre = torch.cuda.Stream(device=self.device, priority=-1)
+                self._tab = torch.cuda.Stream(device=self.device, priority=-1)
+            side, pre, tab = self._side, self._pre, self._tab
+            for s_ in (side, pre, tab):
+                s_.wait_stream(main)
 
         # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
         with torch.cuda.stream(side):
@@ -114,31 +123,53 @@ class ScoringPath:
                 ev_pack = torch.cuda.Event()
                 ev_pack.record()
 
-        # ---- chain P (caller's stream): blur -> prep
-        with self._span("blur"):
-            blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
+        # ---- chain F (frames only): blur -> per-image half of prep (answer planes).  Runs beside the mask pack.
         local = self._get("local", (M, 3, self.size, self.size), self.prep_dtype)
         glob = self._get("global", (M, 3, self.size, self.size), self.prep_dtype)
         pws = self._get("prep_ws", (max(lib.hgl_prep_workspace_bytes(B, self.size, ops._dt(self.prep_dtype)), 1),), torch.uint8)
-        # the per-image half of prep (answer planes) needs the frames only: it runs while the side stream still packs the masks
-        with self._span("prep_setup"):
-            ops.prep_setup(img, blur, self.size, background=self.background, dtype=self.prep_dtype, workspace=pws)
+        with torch.cuda.stream(pre):
+            with self._span("blur"):
+                blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
+            with self._span("prep_setup"):
+                ops.prep_setup(img, blur, self.size, background=self.background, dtype=self.prep_dtype, workspace=pws)
+            ev_setup = None
+            if self.overlap:
+                ev_setup = torch.cuda.Event()
+                ev_setup.record()
+
+        # ---- chain T (heat-maps only): the table half of the pooling pass, also beside the mask pack
+        heat = batch["heat"]           # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
+        E = batch["sent"].shape[0]
+        raw = tuple(heat.shape[1:]) != (H, W)
+        need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, E, H, W, self.grid, max_n, heat.shape[1], heat.shape[2]) if raw
+                else lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n))
+        ws = self._get("heat_ws", (need,), torch.uint8)
+        split = self.antialias and E > 0 and M > 0
+        ev_tables = None
+        if split:
+            with torch.cuda.stream(tab):
+                with self._span("heat_tables"):
+                    ops.heat_tables(heat, batch["dirflag"], H, W, ws)
+                if self.overlap:
+                    ev_tables = torch.cuda.Event()
+                    ev_tables.record()
+
+        # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
         if ev_pack is not None:
             main.wait_event(ev_pack)
+            main.wait_event(ev_setup)
         with self._span("prep"):
             ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
             feats = features if features is not None else batch.get("features")
-            E = batch["sent"].shape[0]
-            heat = batch["heat"]       # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
-            raw = tuple(heat.shape[1:]) != (H, W)
-            need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, E, H, W, self.grid, max_n, heat.shape[1], heat.shape[2]) if raw
-                    else lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n))
-            ws = self._get("heat_ws", (need,), torch.uint8)
+            if ev_tables is not None:
+                side.wait_event(ev_tables)
             with self._span("grid_heat_pool"):
-                if self.antialias:     # mask grid + heat-map pooling share one pass over the packed masks
+                if split:              # mask grid + heat-map pooling share one pass over the packed masks
+                    grid, area, score_gem = ops.grid_heat_pool_rows(bits, W, self.grid, heat.shape, batch["black"], moff, eoff, max_n, ws)
+                elif self.antialias:
                     grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, heat, batch["dirflag"], batch["black"],
                                                                moff, eoff, max_n, workspace=ws)
                 else:
@@ -159,6 +190,7 @@ class ScoringPath:
                 iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
         if self.overlap:
             main.wait_stream(side)
+            main.wait_stream(tab)          # (already ordered before the mask pass; keeps the join explicit when split is off)
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
 

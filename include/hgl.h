@@ -151,6 +151,17 @@ HGL_API int hgl_grid_heat_pool_raw(const uint32_t* bits, const int32_t* mask_off
                            const float* heat_raw, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag,
                            const float* black, int E, int max_n, float* score_gem, void* workspace, void* stream);
 
+/* hgl_grid_heat_pool{,_raw} in two halves, so that a caller can build the heat-map tables (needs the heat-maps only;
+ * Hybridgl_main.py:201-209) while the masks are still being packed, and run the mask pass (Hybridgl_main.py:211-223 +
+ * model/backbone.py:160) afterwards:
+ *   hgl_heat_tables(heat, hh, hw, ...)       heat f32 [E,H,W] with hh = hw = 0, or the raw map [E,hh,hw]
+ *   hgl_grid_heat_pool_rows(..., hh, hw, ...) same workspace, same hh / hw; results identical to the one-call forms.
+ * workspace: hgl_grid_heat_pool_raw_workspace_bytes(...) (raw maps) or hgl_grid_heat_pool_workspace_bytes(...) bytes. */
+HGL_API int hgl_heat_tables(const float* heat, int hh, int hw, const int32_t* dirflag, int E, int H, int W, void* workspace, void* stream);
+HGL_API int hgl_grid_heat_pool_rows(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W, int g,
+                            float* grid, int32_t* area, int hh, int hw, const int32_t* expr_off, const float* black, int E,
+                            int max_n, float* score_gem, void* workspace, void* stream);
+
 /* ---- (b3') token-space mask pooling + L2 normalisation (tensor cores) ---------------------------------
  * The masks x tokens x D contraction of the north star; token-space form of the pooling loop Hybridgl_main.py:218-223
  * (S_in = (M~ . F^) . t) with the normalisation of model/backbone.py:79 fused:
