@@ -4,7 +4,7 @@
 # Outputs land in gpurun_out/<tag>_*; summaries are copied into profiles/ by profiles/summarize.py (run here, no GPU).
 tag=${1:-run}
 out=gpurun_out
-KRE='prep_main|prep_setup|pack_masks|blur15|mask_grid|mask_area|mask_rows|heat_prefix|heat_consts|score_select|score_text|iou_kernel|iou_zero|mask_pool|token_mask|attn_'
+KRE='prep_main|prep_setup|pack_masks|blur15|mask_grid|mask_area|mask_rows|heat_prefix|heat_consts|heat_resize|score_select|score_text|iou_kernel|iou_zero|mask_pool|token_mask|attn_|rle_'
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,memory.total --format=csv > $out/${tag}_gpu.csv 2>&1
 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
