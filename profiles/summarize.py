@@ -22,7 +22,7 @@ PROF = os.path.join(ROOT, "profiles")
 
 # bench.py stage name -> kernels that belong to it
 STAGES = {
-    "blur": ["blur15"], "pack": ["pack_masks"], "prep_setup": ["prep_setup"], "prep": ["prep_main"], "grid_heat_pool": ["mask_rows", "heat_prefix", "heat_consts", "mask_grid", "mask_area"], "score_select": ["score_select", "score_text"], "iou": ["iou_zero", "iou_kernel"],
+    "blur": ["blur15"], "pack": ["pack_masks"], "prep_setup": ["prep_setup"], "prep": ["prep_main"], "heat_tables": ["heat_prefix", "heat_consts", "heat_resize"], "grid_heat_pool": ["mask_rows", "mask_grid", "mask_area"], "score_select": ["score_select", "score_text"], "iou": ["iou_zero", "iou_kernel"],
     "mask_pool": ["mask_pool"], "token_mask_fuse": ["token_mask_fuse"],
 }
 

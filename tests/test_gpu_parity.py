@@ -526,3 +526,70 @@ def test_prep_two_halves_equal_one_call(ops):
         ws = ops.prep_setup(img, blur, 32, dtype=dt)
         l2, g2 = ops.prep_main(ops.pack_masks(masks), (1, 96, 128), 32, ws, dtype=dt)
         assert torch.equal(l1, l2) and torch.equal(g1, g2)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs as parity cases
+def _batch_from_items(items, raw_heat=False):
+    """Device batch dict (pipeline.INPUT_KEYS) of a list of synth Items, ragged offsets included."""
+    from hybridgl_b200._lib import DIR_CODES, REL_CODES
+    exprs = [ex for it in items for ex in it.expressions]
+    de = items[0].features.shape[1]
+    ooff = np.cumsum([0] + [ex.other_feats.shape[0] for ex in exprs]).astype(np.int32)
+    others = np.concatenate([ex.other_feats for ex in exprs]) if ooff[-1] else np.zeros((0, de), np.float32)
+    rels = [ex.relaflag for ex in exprs]
+    return dict(
+        image=cu(np.stack([it.image for it in items])), masks=cu(np.concatenate([it.masks for it in items])),
+        boxes=cu(np.concatenate([it.boxes for it in items])), target=cu(np.stack([it.target for it in items]).astype(np.uint8)),
+        features=cu(np.concatenate([it.features for it in items])),
+        sent=cu(np.stack([ex.sentence_feat for ex in exprs])), noun=cu(np.stack([ex.noun_feat for ex in exprs])),
+        others=cu(others), other_off=cu(ooff),
+        heat=cu(np.stack([ex.heat_raw if raw_heat else ex.heatmap for ex in exprs])),
+        dirflag=cu(np.array([DIR_CODES[ex.dirflag] for ex in exprs], np.int32)),
+        relaflag=cu(np.array([REL_CODES[r] for r in rels], np.int32)),
+        black=cu(np.array([O.black_for(r) for r in rels], np.float32)),
+        mask_off=cu(np.cumsum([0] + [it.n_masks for it in items]).astype(np.int32)),
+        expr_off=cu(np.cumsum([0] + [len(it.expressions) for it in items]).astype(np.int32)))
+
+
+@pytest.mark.parametrize("cfg_id", [1, 3, 4, 5])
+def test_named_config_shapes_pipeline_vs_oracle(ops, cfg_id):
+    """BASELINE.json configs[0], [2], [3], [4] at their full per-image shapes (64 / 150 / 200 / 200 proposals; ViT-L/14@336
+    geometry S=336 g=24 De=768 for configs[3]; 600x800 frames for configs[4]): one image through ScoringPath, every stage
+    against the oracle.  (configs[1] is the bench workload: test_full_size_properties + the golden-vector tests.)"""
+    from hybridgl_b200.pipeline import ScoringPath
+    cfg = synth.CONFIGS[cfg_id]
+    it = synth.make_item(4000 + cfg_id, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], de=cfg["De"], n_other=cfg.get("n_other"))
+    n = it.n_masks
+    batch = _batch_from_items([it], raw_heat=True)
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=torch.float32, feature_source="supplied")
+    res = path.run(batch, n)
+    torch.cuda.synchronize()
+    # a1: three proposals element-wise (the full-size property test covers the rest), bit-exact f32
+    blur = O.gaussian_blur_u8(it.image)
+    pick = [0, n // 2, n - 1]
+    ol, og = O.prep(it.image, blur, it.masks[pick], cfg["S"])
+    assert np.array_equal(res["local_imgs"][pick].cpu().numpy(), ol) and np.array_equal(res["global_imgs"][pick].cpu().numpy(), og)
+    # a2: soft grid masks + areas
+    ref_grid = O.mask_to_grid(it.masks, cfg["g"], antialias=True)
+    np.testing.assert_allclose(res["grid"].cpu().numpy(), ref_grid, rtol=0, atol=1e-6)
+    assert np.array_equal(res["grid"].cpu().numpy() == 0, ref_grid == 0)
+    assert np.array_equal(res["area"].cpu().numpy(), it.masks.reshape(n, -1).sum(1))
+    # a6-a13 per expression
+    tot = np.zeros(4, np.int64)
+    for e, ex in enumerate(it.expressions):
+        heat = O.resize_bilinear_aa(ex.heat_raw[None], cfg["h"], cfg["w"])[0]                  # Hybridgl_main.py:201
+        ref_sg = O.gem_pool(O.condition_heatmap(heat, ex.dirflag), it.masks, O.black_for(ex.relaflag))
+        np.testing.assert_allclose(res["score_gem"][e, :n].cpu().numpy(), ref_sg, rtol=1e-3, atol=1e-4)
+        r = O.score_and_select(it.features, ex.sentence_feat, ex.noun_feat, ex.other_feats, it.boxes, ex.relaflag, score_gem=ref_sg)
+        np.testing.assert_allclose(res["score_clip"][e, :n].cpu().numpy(), r["score_clip"], rtol=1e-3, atol=1e-4)
+        top2 = np.sort(r["score_clip"])[-2:]
+        if top2[1] - top2[0] > 1e-3 * abs(top2[1]):
+            assert int(res["idx_hybrid"][e]) == r["idx_hybrid"]
+        b2 = np.sort(r["blended"])[-2:]
+        if b2[1] - b2[0] > 1e-3 * max(abs(b2[1]), 1e-3):
+            assert int(res["idx_final"][e]) == r["idx_final"]
+        i0, u0, _ = O.compute_iou(it.masks[int(res["idx_hybrid"][e])], it.target)
+        i1, u1, _ = O.compute_iou(it.masks[int(res["idx_final"][e])], it.target)
+        assert res["iu"][e].cpu().numpy().tolist() == [i0, u0, i1, u1]                          # integers: bit-exact
+        tot += np.array([i0, u0, i1, u1])
+    assert path.cum.cpu().numpy().tolist() == tot.tolist()
