@@ -186,6 +186,24 @@ def workload_name(cfg):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(gpu_index: int):
+    """One process per GPU: pin the process (and therefore its pinned host buffers, by first touch) to the CPU cores NVML
+    reports as local to the GPU, so that the e2e H2D copies of 8 ranks do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cores local to GPU {gpu_index}"
+    except Exception as e:      # no NVML / not permitted: keep the default placement
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def algorithmic_bytes(cfg, B, prep_bytes):
     """Per-launch algorithmic HBM bytes of each kernel (stated in DESIGN.md)."""
     H, W, N, E, S, De = cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["S"], cfg["De"]
@@ -221,8 +239,10 @@ def run_ours(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)       # before any pinned allocation: first-touch puts the host buffers next to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
@@ -246,14 +266,18 @@ def run_ours(args, cfg):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    stage_events = []
+    # timed region: only the dominant stage (prep) is bracketed with events -- two records per step instead of twenty, which
+    # cost ~3 % of the step when every stage is bracketed (profiles/host_overhead.py)
+    top_events = []
+    path.events_only = {"prep"}
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
     for s in range(args.steps):
         path.events = []
         path.run(batches[s % 2], max_n)
-        stage_events.append(path.events)
+        top_events.append(path.events)
     path.events = None
+    path.events_only = None
     cum = path.cum.clone()
     if world > 1:
         dist.all_reduce(cum)              # the path's only collective: IoU accumulators (64 bytes)
@@ -267,15 +291,25 @@ def run_ours(args, cfg):
     expr_per_step = world * B * cfg["n_expr"]
     value = expr_per_step * args.steps / (ms_total / 1e3)
 
-    # per-stage durations from the event pairs recorded inside the timed region, each pair on the stream its stage runs on
-    # (the post-pack chain runs concurrently with prep on a side stream, so these are durations UNDER that overlap)
+    # per-stage durations from event pairs, each pair on the stream its stage runs on
     def stage_avg(all_events):
         dur = {}
         for evs in all_events:
             for name, e0, e1 in evs:
                 dur.setdefault(name, []).append(e0.elapsed_time(e1))
         return {k: sum(v) / len(v) for k, v in dur.items()}
+    top_ms = stage_avg(top_events)
+    # every stage bracketed, same overlapped stage graph, right after the timed region (durations UNDER the overlap: the
+    # helper-stream chains run concurrently with prep)
+    stage_events = []
+    for s in range(min(args.steps, 50)):
+        path.events = []
+        path.run(batches[s % 2], max_n)
+        stage_events.append(path.events)
+    path.events = None
+    barrier()
     avg_ms = stage_avg(stage_events)
+    avg_ms.update(top_ms)                # the dominant stage: the timed region's own measurement
     # the same stages launched back to back on one stream (no overlap): each kernel timed ALONE, after the timed region
     serial_events = []
     ms_serial = None
@@ -325,10 +359,11 @@ def run_ours(args, cfg):
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         kernels["mask_pool"].update({"algorithmic_flop": flop, "achieved_tflops": round(tf, 2), "frac_tensor": round(tf / peak_tf, 5),
                                      "tensor_peak_tflops": peak_tf})
-    top = max(kernels, key=lambda k: kernels[k]["ms"])
+    top = "prep" if "prep" in kernels else max(kernels, key=lambda k: kernels[k]["ms"])      # the bandwidth-bound bulk of the step
     roofline = {"kernel": f"hgl_{top}", "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak_hbm, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src,
-                "timing": ("CUDA events around the stage on its own stream inside the timed region" +
+                "timing": ("CUDA events around the stage on its own stream inside the timed region (the other stages are bracketed in "
+                           "a second pass right after it: kernels{})" +
                            ("; the side-stream chain (pack, mask grid + heat-map pooling, mask pooling, score/select, IoU) runs "
                             "concurrently with prep, so `frac` is prep's share of HBM while sharing it; `frac_alone` is the same "
                             "kernel timed alone in the serial pass" if path.overlap else "")),
@@ -424,7 +459,7 @@ def run_ours(args, cfg):
                 "config": {"workload": workload_name(cfg), "l2": "two alternating batches, masks alone are "
                            f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
                            **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
+                "clocks": clocks, "host_affinity": numa, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
                 "streams": ("2 (heat-map tables, blur and prep on the caller's stream; pack and the post-pack chain on a high-priority side stream)"
                             if path.overlap else "1"),
                 "ms_per_step_serial": ms_serial,

@@ -46,6 +46,7 @@ class ScoringPath:
         self._dev_in: Dict[str, torch.Tensor] = {}
         self._host_out: Dict[str, torch.Tensor] = {}
         self.events = None            # optional per-stage CUDA event pairs (bench.py): [(stage, start, end)]
+        self.events_only = None       # optional set of stage names to bracket (None = every stage)
         self.overlap = overlap        # fork the post-pack chain onto a high-priority side stream (see run())
         self._side: Optional[torch.cuda.Stream] = None
         self._pre: Optional[torch.cuda.Stream] = None
@@ -64,13 +65,17 @@ class ScoringPath:
         def __init__(self, path, name):
             self.path, self.name = path, name
 
+        def _on(self):
+            p = self.path
+            return p.events is not None and (p.events_only is None or self.name in p.events_only)
+
         def __enter__(self):
-            if self.path.events is not None:
+            if self._on():
                 self.e0 = torch.cuda.Event(enable_timing=True)
                 self.e0.record()
 
         def __exit__(self, *exc):
-            if self.path.events is not None:
+            if self._on():
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()
                 self.path.events.append((self.name, self.e0, e1))
