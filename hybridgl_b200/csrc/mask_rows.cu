@@ -78,6 +78,36 @@ __device__ void aa_fill(int i, int in_size, int out_size, int maxk, int* xmin_ou
   *xmin_out = xmin; *xsize_out = xsize;
 }
 
+// The same table built by a whole warp: the weights (double-precision index arithmetic, the expensive part) are evaluated one
+// per lane; the normalising total stays a sequential float sum in tap order (one lane), so every value is bit-identical to
+// aa_fill.  `w` is shared memory.
+__device__ void aa_fill_warp(int i, int in_size, int out_size, int maxk, int* xmin_out, int* xsize_out, float* w, int lane) {
+  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+  float support, invscale;
+  if (scale >= 1.f) { support = scale; invscale = __fdiv_rn(1.f, scale); } else { support = 1.f; invscale = 1.f; }
+  const float center = (float)((double)scale * ((double)i + 0.5));
+  int xmin = (int)((double)__fsub_rn(center, support) + 0.5);
+  xmin = max(xmin, 0);
+  int xsize = min((int)((double)__fadd_rn(center, support) + 0.5), in_size) - xmin;
+  xsize = max(min(xsize, maxk), 0);
+  for (int j = lane; j < xsize; j += 32) {
+    float t = (float)(((double)__fsub_rn((float)(j + xmin), center) + 0.5) * (double)invscale);
+    t = fabsf(t);
+    w[j] = (t < 1.f) ? __fsub_rn(1.f, t) : 0.f;
+  }
+  __syncwarp();
+  float total = 0.f;
+  if (lane == 0)
+    for (int j = 0; j < xsize; ++j) total = __fadd_rn(total, w[j]);
+  total = __shfl_sync(0xffffffffu, total, 0);
+  for (int j = lane; j < maxk; j += 32) {
+    if (j >= xsize) w[j] = 0.f;
+    else if (total != 0.f) w[j] = __fdiv_rn(w[j], total);
+  }
+  __syncwarp();
+  if (lane == 0) { *xmin_out = xmin; *xsize_out = xsize; }
+}
+
 static int aa_maxk(int in_size, int out_size) {
   const float scale = (float)in_size / (float)out_size;
   const float support = scale >= 1.f ? scale : 1.f;
@@ -331,7 +361,7 @@ struct RowsParams {
 };
 
 template <bool kGrid, bool kHeat>
-__global__ void __launch_bounds__(kRowsThreads) mask_rows_kernel(const RowsParams p) {
+__global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   int* ymin = reinterpret_cast<int*>(smem);
   int* ysize = ymin + kMaxG;
@@ -348,15 +378,19 @@ __global__ void __launch_bounds__(kRowsThreads) mask_rows_kernel(const RowsParam
   const int pk = p.maxkx + 1;
   float inv_sx = 0.f;
   if (kGrid) {
-    if (tid < g) aa_fill(tid, H, g, p.maxky, &ymin[tid], &ysize[tid], wy + tid * p.maxky);
-    else if (tid >= 32 && tid < 32 + g) {
-      const int i = tid - 32;
-      int xm, xs;
-      aa_fill(i, W, g, p.maxkx, &xm, &xs, wx + i * p.maxkx);
-      xlo[i] = xm; xhi[i] = xm + xs;
-      double run = 0.0;
-      psum[i * pk] = 0.0;
-      for (int k = 0; k < p.maxkx; ++k) { run += (double)wx[i * p.maxkx + k]; psum[i * pk + k + 1] = run; }
+    for (int t = warp; t < 2 * g; t += kRowsThreads / 32) {       // one warp per table (28 for g = 14), instead of one thread
+      if (t < g) {
+        aa_fill_warp(t, H, g, p.maxky, &ymin[t], &ysize[t], wy + t * p.maxky, lane);
+      } else {
+        const int i = t - g;
+        aa_fill_warp(i, W, g, p.maxkx, &xlo[i], &xhi[i], wx + i * p.maxkx, lane);       // xhi holds the size for a moment
+        if (lane == 0) {
+          xhi[i] += xlo[i];
+          double run = 0.0;
+          psum[i * pk] = 0.0;
+          for (int k = 0; k < p.maxkx; ++k) { run += (double)wx[i * p.maxkx + k]; psum[i * pk + k + 1] = run; }
+        }
+      }
     }
     inv_sx = (float)g / (float)W;
     __syncthreads();

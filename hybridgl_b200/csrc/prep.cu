@@ -202,6 +202,7 @@ struct PrepParams {
   int stage_words;            // ring pitch of the shared-memory bit-row stages (words)
   int sub;                    // masks per stage
   int gw, gh, cw, nbx, strip; // thread -> pixel map (PrepGeom)
+  int flush_every;            // masks between two flushes of a warp's outline list (<= sub)
   int debug;                  // profiling only (HGL_PREP_DEBUG): 1 = skip the exact outline pixels, 2 = skip the stores
   int narrow;                 // 1 if the 8 taps of 4 adjacent pixels always fit one 32-bit window
 };
@@ -535,8 +536,9 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
         }
         wcount += total;
       }
+      if (wcount && ((k + 1) % p.flush_every) == 0) flush();          // early enough for the patched lines to be in L2 still
     }
-    if (wcount) flush();
+    if (wcount && (p.flush_every <= kPrepSub || c == nst - 1)) flush();
     if (kTMA) {                                                       // this warp is done with the slot
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + slot);
@@ -705,6 +707,8 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   }
   if (const char* ov = getenv("HGL_PREP_GZ")) gz = std::max(1, atoi(ov));         // tuning hook
   p.debug = 0;
+  p.flush_every = kPrepSub;
+  if (const char* fv = getenv("HGL_PREP_FLUSH")) p.flush_every = std::max(1, atoi(fv));                 // tuning hook
   if (const char* dv = getenv("HGL_PREP_DEBUG")) p.debug = atoi(dv);              // profiling only: results are wrong when set
   dim3 grid(gx, B, gz);
   HGL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "hgl_prep: batch too large for one launch (B=%d, max_n=%d)", B, max_n);

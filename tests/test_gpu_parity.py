@@ -593,3 +593,30 @@ def test_named_config_shapes_pipeline_vs_oracle(ops, cfg_id):
         assert res["iu"][e].cpu().numpy().tolist() == [i0, u0, i1, u1]                          # integers: bit-exact
         tot += np.array([i0, u0, i1, u1])
     assert path.cum.cpu().numpy().tolist() == tot.tolist()
+
+
+@pytest.mark.parametrize("raw", [True, False])
+def test_grid_heat_pool_two_halves_equal_one_call(ops, raw):
+    """hgl_heat_tables + hgl_grid_heat_pool_rows (what the pipeline launches on two streams) == hgl_grid_heat_pool{,_raw}, bit for bit;
+    a down-sampling axis (raw map larger than the frame) goes through the materialised resize inside the table half."""
+    h, w, g, n, e = 97, 131, 6, 7, 3
+    it = synth.make_item(611, h, w, n, e, de=32)
+    rng = np.random.default_rng(5)
+    shapes = [(14, 19), (120, 40)] if raw else [(h, w)]
+    bits = ops.pack_masks(cu(it.masks))
+    dirs = cu(np.array([1, 3, 0], np.int32)); black = cu(np.array([1.8, 1.95, 1.5], np.float32))
+    lib = ops._lib.load()
+    for hh, hw in shapes:
+        heat = cu(rng.random((e, hh, hw), dtype=np.float32))
+        g1, a1, s1 = ops.grid_heat_pool(bits, w, g, heat, dirs, black)
+        need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(1, n, e, h, w, g, n, hh, hw) if raw
+                else lib.hgl_grid_heat_pool_workspace_bytes(1, n, e, h, w, g, n))
+        ws = torch.empty((need,), dtype=torch.uint8, device=DEV)
+        ops.heat_tables(heat, dirs, h, w, ws)
+        g2, a2, s2 = ops.grid_heat_pool_rows(bits, w, g, heat.shape, black, None, None, n, ws)
+        assert torch.equal(g1, g2) and torch.equal(a1, a2) and torch.equal(s1, s2)
+        # and against the oracle chain (resize -> condition -> pool)
+        for j in range(e):
+            full = O.resize_bilinear_aa(heat[j].cpu().numpy()[None], h, w)[0] if raw else heat[j].cpu().numpy()
+            ref = O.gem_pool(O.condition_heatmap(full, synth.DIRFLAGS[int(dirs[j])]), it.masks, float(black[j]))
+            np.testing.assert_allclose(s2[j, :n].cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
