@@ -693,7 +693,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
               H, W, S);
   p.stage_words = (int)(kPrepSub * per_mask_bytes / 4);
   const size_t smem = fixed_smem + (size_t)kPrepStages * kPrepSub * per_mask_bytes;
-  const int resident = std::max(1, std::min(std::min(2 * kPrepThreads / threads, (int)((220 * 1024) / smem)), 65536 / (threads * 128)));
+  const int resident = std::max(1, std::min(std::min(2 * kPrepThreads / threads, (int)((220 * 1024) / (smem + 1024))), 65536 / (threads * 128)));
   const long slots = (long)sm_count() * resident;
   int gz = 1;
   {

@@ -51,6 +51,7 @@ class ScoringPath:
         self._side: Optional[torch.cuda.Stream] = None
         self._pre: Optional[torch.cuda.Stream] = None
         self._tab: Optional[torch.cuda.Stream] = None
+        self._capturing = False
 
     # ------------------------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype) -> torch.Tensor:
@@ -71,12 +72,13 @@ class ScoringPath:
 
         def __enter__(self):
             if self._on():
-                self.e0 = torch.cuda.Event(enable_timing=True)
+                # inside a graph capture the pair becomes two event-record NODES (external events), re-stamped by every replay
+                self.e0 = torch.cuda.Event(enable_timing=True, external=self.path._capturing)
                 self.e0.record()
 
         def __exit__(self, *exc):
             if self._on():
-                e1 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True, external=self.path._capturing)
                 e1.record()
                 self.path.events.append((self.name, self.e0, e1))
             return False
@@ -199,6 +201,32 @@ class ScoringPath:
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
 
+    def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None) -> "GraphStep":
+        """One step as a CUDA graph: the whole stage graph of run() (four streams, ~12 kernels, memsets, fork / join events) is
+        captured once for THESE device buffers and replayed with a single launch; the per-launch host work of run() (~0.3 ms
+        of ctypes / torch calls per step, profiles/host_overhead.py) disappears from the step.  `batch` must stay alive and keep
+        its addresses (run_host's device buffers do; a sweep captures one graph per ring buffer).  time_stages: stage names
+        to bracket with event-record nodes (GraphStep.events: re-stamped by every replay).
+        Returns a GraphStep; GraphStep.replay() enqueues the step on the current stream and returns the (static) result dict."""
+        saved = (self.events, self.events_only)
+        self.events, self.events_only = None, None
+        cum0 = self.cum.clone()
+        self.run(batch, max_n)                 # eager once: sizes every workspace, creates the streams, sets kernel attributes
+        torch.cuda.current_stream().synchronize()
+        self.cum.copy_(cum0)                   # the warm-up step must not count
+        graph = torch.cuda.CUDAGraph()
+        events = []
+        if time_stages:
+            self.events, self.events_only = events, set(time_stages)
+        self._capturing = True
+        try:
+            with torch.cuda.graph(graph):
+                res = self.run(batch, max_n)
+        finally:
+            self._capturing = False
+            self.events, self.events_only = saved
+        return GraphStep(graph, res, events, batch)
+
     # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), score_select 2 (text, score+select), iou 2
     LAUNCHES_PER_RUN = 11      # + 1 (mask_pool) with feature_source="tokens"
 
@@ -242,6 +270,17 @@ class ScoringPath:
 
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._host_out.values())
+
+
+class GraphStep:
+    """A captured step (ScoringPath.capture).  `res` are static device tensors, overwritten by every replay."""
+
+    def __init__(self, graph, res, events, batch):
+        self.graph, self.res, self.events, self._batch = graph, res, events, batch
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        self.graph.replay()
+        return self.res
 
 
 def report(cum: torch.Tensor, ious_hybrid, ious_final):

@@ -620,3 +620,25 @@ def test_grid_heat_pool_two_halves_equal_one_call(ops, raw):
             full = O.resize_bilinear_aa(heat[j].cpu().numpy()[None], h, w)[0] if raw else heat[j].cpu().numpy()
             ref = O.gem_pool(O.condition_heatmap(full, synth.DIRFLAGS[int(dirs[j])]), it.masks, float(black[j]))
             np.testing.assert_allclose(s2[j, :n].cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
+
+
+def test_captured_step_equals_eager_step(ops):
+    """ScoringPath.capture: the step replayed from a CUDA graph writes the same bits as the eager step, accumulates the IoU
+    counters once per replay, and its event-record nodes time a stage."""
+    from hybridgl_b200.pipeline import ScoringPath
+    B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
+    batch = synth.make_batch_device(78, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True)
+    eager = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    ref = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in eager.run(batch, n).items()}
+    torch.cuda.synchronize()
+    path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    step = path.capture(batch, n, time_stages=("prep",))
+    assert path.cum.tolist() == [0, 0, 0, 0]                         # neither the warm-up nor the capture counts
+    for r in range(3):
+        res = step.replay()
+    torch.cuda.synchronize()
+    for k in ("local_imgs", "global_imgs", "grid", "area", "score_clip", "score_gem", "idx_hybrid", "idx_final", "top_idx", "iu", "features"):
+        assert torch.equal(res[k], ref[k]), k
+    assert path.cum.tolist() == [3 * v for v in eager.cum.tolist()]
+    (name, e0, e1), = step.events
+    assert name == "prep" and e0.elapsed_time(e1) > 0.0
