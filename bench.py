@@ -135,7 +135,7 @@ def cpu_baseline_sample(cfg, budget_s: float = 20.0):
     n_masks = cfg["n_masks"]
     t_first = _oracle_one_image((9000, cfg, n_masks))
     imgs, total = 1, t_first
-    while total + t_first < budget_s and imgs < 4:
+    while total + t_first < budget_s and imgs < 10:
         total += _oracle_one_image((9000 + imgs, cfg, n_masks)); imgs += 1
     return {"value": imgs * cfg["n_expr"] / total, "unit": METRIC, "cores": 1, "kind": "port",
             "sample": f"{imgs} image(s) x {n_masks} masks x {cfg['n_expr']} expressions of the same workload, numpy oracle port "
@@ -182,8 +182,9 @@ def run_reference(args, cfg):
 
 
 def workload_name(cfg):
+    vit = "ViT-L/14@336" if cfg["S"] == 336 else "ViT-B/16"
     return (f"RefCOCO-shaped synthetic batch: {cfg['images_per_gpu_per_step']} images/GPU/step, {cfg['h']}x{cfg['w']}, "
-            f"{cfg['n_masks']} masks/image, {cfg['n_expr']} expressions/image, ViT-B/16 geometry (S={cfg['S']}, g={cfg['g']}, "
+            f"{cfg['n_masks']} masks/image, {cfg['n_expr']} expressions/image, {vit} geometry (S={cfg['S']}, g={cfg['g']}, "
             f"De={cfg['De']}), fusion_mode {cfg['fusion_mode']}; features: dense tokens pooled per mask (hgl_mask_pool) unless --features supplied")
 
 

@@ -295,8 +295,8 @@ __device__ __forceinline__ void prep_pixel_of(const PrepGeom& gm, int bxi, int b
 // of stages of kPrepSub masks with NO CTA-wide barrier in the steady state:
 //   producer  (kTMA) one extra warp: its lane 0 keeps the ring of bit-row stages full: it waits for a slot to be released
 //             (`empty` mbarrier, one arrival per consumer warp) and refills it -- one 1-D bulk async copy (cp.async.bulk, SASS
-//             UBLKCP) per mask onto the slot's `full` mbarrier.  !kTMA (rows not 16-byte aligned): cooperative loads between
-//             two __syncthreads per stage.
+//             UBLKCP) per mask onto the slot's `full` mbarrier.  !kTMA (masks not 16-byte aligned: H * ceil(W/32) % 4 != 0):
+//             cooperative loads between two __syncthreads per stage.
 //   consumers per mask: window from shared memory, then two warp votes.  A warp whose 32 groups lie entirely inside or
 //             entirely outside the mask (the common case) is six 16-byte streaming stores straight from the FG or BG answer
 //             registers -- no select, no per-pixel work, no global load; the answers sit in registers for the CTA's whole
@@ -337,9 +337,12 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const Taps tl = make_taps(row_last, H, S);
   const int nrows = tl.i0 + tl.d - ylo + 1;
   const size_t mask_words = (size_t)H * WW;
-  const int per_mask = nrows * WW;                                   // words of one mask inside a stage
-  const int stage_words = p.stage_words;                             // ring pitch (host: kPrepSub * max rows * WW)
-  const uint32_t* src0 = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW;
+  // kTMA: every mask starts 16-byte aligned (H * WW % 4 == 0), the band's first row need not: a bulk copy starts `lead` words
+  // early and is rounded up to whole 16-byte units (it stays inside the mask)
+  const int lead = kTMA ? ((ylo * WW) & 3) : 0;
+  const int per_mask = kTMA ? ((lead + nrows * WW + 3) & ~3) : nrows * WW;   // words of one mask's slot inside a stage
+  const int stage_words = p.stage_words;                             // ring pitch (host: kPrepSub * max slot words)
+  const uint32_t* src0 = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW - lead;
 
   if (kTMA) {
     if (tid == 0) {
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const size_t plane_bytes = (size_t)SS * kElem;
   uint8_t* lp0 = reinterpret_cast<uint8_t*>(p.local_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;    // planes of mask n_lo
   uint8_t* gp0 = reinterpret_cast<uint8_t*>(p.global_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
-  const int row_off0 = (ty.i0 - ylo) * WW, row_off1 = row_off0 + ty.d * WW;
+  const int row_off0 = lead + (ty.i0 - ylo) * WW, row_off1 = row_off0 + ty.d * WW;
   const size_t tap_base = (size_t)b * 6 * SS;
 
   // exact values of the listed outline pixels (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel), one lane
@@ -657,8 +660,9 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   int gw = 1;
   while (gw < 8 && G % (gw * 2) == 0) gw *= 2;
   const int gh = 32 / gw, ppr = G / gw;
-  // 1-D bulk copies need 16-byte aligned rows: WW % 4 == 0 and an aligned base; otherwise cooperative loads
-  const bool tma = (p.WW % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
+  // 1-D bulk copies need 16-byte aligned masks (H * WW % 4 == 0 and an aligned base; a band's first row may sit anywhere,
+  // the copy then starts up to 3 words early); otherwise cooperative loads
+  const bool tma = (((size_t)H * p.WW) % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
   int cw = 1;
   for (int d = 1; d <= (tma ? 7 : 8); ++d) if (ppr % d == 0) cw = d;        // kTMA: one more warp (the producer) joins the CTA
   p.gw = gw; p.gh = gh; p.cw = cw; p.nbx = ppr / cw; p.strip = 0;
@@ -680,7 +684,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   const int per_image = (B == 1) ? M : std::min(max_n, M);
   const double sy = (double)H / (double)S;
   const int stage_rows = std::min(H, (int)(gh_ * sy) + 3);                    // source rows behind a band
-  const size_t per_mask_bytes = (size_t)stage_rows * p.WW * 4;
+  const size_t per_mask_bytes = (size_t)((stage_rows * p.WW + 3 + 3) & ~3) * 4;   // slot of one mask: rows + lead words, whole 16-byte units
   // barriers | per-warp scratch | stages (+ the word after the last row)
   const size_t fixed_smem = 64 + (size_t)cw * kPrepWarpBytes + 16;
   const size_t stage_budget = fixed_smem + 24 * 1024 <= 112 * 1024 ? 112 * 1024 - fixed_smem      // two CTAs per SM
