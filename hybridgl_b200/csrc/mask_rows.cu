@@ -448,6 +448,9 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
             const uint4* r4 = reinterpret_cast<const uint4*>(rowp);
             for (int u = 0; u < (WW >> 2); ++u) {
               const uint4 v = __ldg(r4 + u);
+              // 128 pixels on one side of the outline (most of a frame for a blob): nothing to record
+              if ((v.x | v.y | v.z | v.w) == 0u && prev == 0u) continue;
+              if ((v.x & v.y & v.z & v.w) == 0xffffffffu && prev == 1u) { c_row += 128; continue; }
               look(v.x, 4 * u); look(v.y, 4 * u + 1); look(v.z, 4 * u + 2); look(v.w, 4 * u + 3);
             }
           } else {

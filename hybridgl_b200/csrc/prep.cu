@@ -34,13 +34,14 @@ struct Taps {
 };
 
 // ATen area_pixel_compute_source_index + compute_source_index_and_lambda (float, align_corners=False)
-__device__ __forceinline__ Taps make_taps(int dst, int in_size, int out_size) {
+__device__ __forceinline__ float tap_scale(int in_size, int out_size) { return __fdiv_rn((float)in_size, (float)out_size); }
+// `scale` = tap_scale(in_size, out_size): one correctly-rounded division shared by every pixel of an axis
+__device__ __forceinline__ Taps make_taps(int dst, int in_size, int out_size, float scale) {
   Taps t;
   if (in_size == out_size) {
     t.i0 = dst; t.d = 0; t.w0 = 1.f; t.w1 = 0.f;
     return t;
   }
-  const float scale = __fdiv_rn((float)in_size, (float)out_size);
   float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
   src = fmaxf(src, 0.f);
   int i0 = (int)src;
@@ -59,6 +60,8 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, floa
   const float bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
   return __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
 }
+
+__device__ __forceinline__ Taps make_taps(int dst, int in_size, int out_size) { return make_taps(dst, in_size, out_size, tap_scale(in_size, out_size)); }
 
 __constant__ float c_in_mean[3] = {0.485f, 0.456f, 0.406f};
 __constant__ float c_in_std[3] = {0.229f, 0.224f, 0.225f};
@@ -332,9 +335,10 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const int kPrepSub = p.sub;
   const int nst = (cnt + kPrepSub - 1) / kPrepSub;
 
+  const float sc_y = tap_scale(H, S), sc_x = tap_scale(W, S);
   const int row_first = byi * gm.gh, row_last = min(S, row_first + gm.gh) - 1;   // output rows of the band
-  const int ylo = make_taps(row_first, H, S).i0;
-  const Taps tl = make_taps(row_last, H, S);
+  const int ylo = make_taps(row_first, H, S, sc_y).i0;
+  const Taps tl = make_taps(row_last, H, S, sc_y);
   const int nrows = tl.i0 + tl.d - ylo + 1;
   const size_t mask_words = (size_t)H * WW;
   // kTMA: every mask starts 16-byte aligned (H * WW % 4 == 0), the band's first row need not: a bulk copy starts `lead` words
@@ -371,15 +375,15 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   prep_pixel_of(gm, bxi, byi, tid, PX, i, j0);
   const bool live = i <= row_last && j0 < S;                         // partial last band / idle lanes of the last warp (strip mode)
   if (!live) { i = row_last; j0 = 0; }
-  const Taps ty = make_taps(i, H, S);
-  const int bx = make_taps(j0, W, S).i0;
+  const Taps ty = make_taps(i, H, S, sc_y);
+  const int bx = make_taps(j0, W, S, sc_x).i0;
   uint32_t tapmask = 0;
   uint32_t tm[PX];                   // per pixel: the two tap columns as bits of the 32-bit window starting at bx
 #pragma unroll
   for (int q = 0; q < PX; ++q) {
     tm[q] = 0;
     if (kNarrow) {
-      const Taps tx = make_taps(j0 + q, W, S);
+      const Taps tx = make_taps(j0 + q, W, S, sc_x);
       tm[q] = (1u << (tx.i0 - bx)) | (1u << (tx.i0 + tx.d - bx));
       tapmask |= tm[q];
     }
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
       int pi, pj0;
       prep_pixel_of(gm, bxi, byi, (warp << 5) | ol_, PX, pi, pj0);
       const int pj = pj0 + oq, gpx = pi * S + pj;
-      const Taps tyy = make_taps(pi, H, S), txx = make_taps(pj, W, S);
+      const Taps tyy = make_taps(pi, H, S, sc_y), txx = make_taps(pj, W, S, sc_x);
       float o6[6];
       prep_boundary_pixel(p.taps, tap_base + gpx, SS, ent & 15u, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
       const size_t o = ((size_t)(n_lo + (int)(ent >> 16)) * 3) * SS + gpx;
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
       } else {
 #pragma unroll
         for (int q = 0; q < PX; ++q) {
-          const Taps tx = make_taps(j0 + q, W, S);
+          const Taps tx = make_taps(j0 + q, W, S, sc_x);
           const int xa = tx.i0, xb = tx.i0 + tx.d;
           const uint32_t code = ((s0[xa >> 5] >> (xa & 31)) & 1u) | (((s0[xb >> 5] >> (xb & 31)) & 1u) << 1) |
                                 (((s1[xa >> 5] >> (xa & 31)) & 1u) << 2) | (((s1[xb >> 5] >> (xb & 31)) & 1u) << 3);
