@@ -67,7 +67,10 @@ def test_prep_matches_reference_golden(ops, golden, tag):
 
 
 @pytest.mark.parametrize("h,w,S,n,seed", [(480, 640, 224, 9, 5), (333, 500, 224, 5, 6), (480, 640, 336, 3, 7),
-                                          (224, 224, 224, 2, 8), (60, 90, 64, 7, 9), (427, 641, 224, 4, 10)])
+                                          (224, 224, 224, 2, 8), (60, 90, 64, 7, 9), (427, 641, 224, 4, 10),
+                                          # 11 source columns per output pixel: the taps of a 4-pixel group do not fit one 32-bit
+                                          # window (the general, per-pixel path of prep_main); 600x800: bit rows of 25 words
+                                          (40, 352, 32, 4, 11), (48, 2400, 224, 2, 12), (600, 800, 224, 3, 13)])
 def test_prep_vs_oracle_f32_and_bf16(ops, h, w, S, n, seed):
     it = synth.make_item(seed, h, w, n, 0, with_features=False)
     blur = O.gaussian_blur_u8(it.image)
