@@ -6,32 +6,32 @@
 
 namespace hgl {
 
-// (a3) full boolean attention mask, written once, 16 bytes per store
-__global__ void attn_mask_kernel(const float* __restrict__ grid, int M, int L, int heads, uint8_t* __restrict__ out) {
+// (a3) full boolean attention mask, written once, 16 bytes per store.  Only row 0 of every (mask, head) slab can be non-zero:
+// a 16-byte chunk that lies past row 0 and inside one slab (99.5 % of them) is a plain zero store after ONE 64-bit division.
+__global__ void __launch_bounds__(256) attn_mask_kernel(const float* __restrict__ grid, int M, int L, int heads, uint8_t* __restrict__ out) {
   const int L1 = L + 1;
   const size_t per = (size_t)L1 * L1;
   const size_t total = (size_t)M * heads * per;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 16;
-  for (size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; o < total; o += stride) {
+  size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  size_t mh = o / per, within = o - mh * per;                 // slab and offset inside it: divided once, then advanced by adds
+  const size_t dq = stride / per, dr = stride - dq * per;
+  for (; o < total; o += stride, mh += dq, within += dr) {
+    if (within >= per) { within -= per; ++mh; }
     uint32_t w[4] = {0, 0, 0, 0};
-    const size_t mh = o / per;
-    const size_t within = o - mh * per;
-    if (within < (size_t)L1 || (within + 15) / per != 0 || true) {
-      // only bytes that fall in row 0 of some (m,h) slab can be non-zero
+    if (within < (size_t)L1 || within + 16 > per) {          // touches row 0 of this slab or of the next one
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const size_t oo = o + q;
-        if (oo >= total) break;
-        const size_t mh2 = oo / per;
-        const size_t r = oo - mh2 * per;
-        if (r >= 1 && r < (size_t)L1) {
+        size_t mh2 = mh, r = within + q;
+        while (r >= per) { r -= per; ++mh2; }                 // (tiny grids: a chunk may span several slabs)
+        if (o + q < total && r >= 1 && r < (size_t)L1) {
           const int m = (int)(mh2 / heads);
           if (grid[(size_t)m * L + (r - 1)] == 0.f) w[q >> 2] |= 1u << ((q & 3) * 8);
         }
       }
     }
     if (o + 16 <= total) {
-      *reinterpret_cast<uint4*>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      stg_stream(reinterpret_cast<uint4*>(out + o), make_uint4(w[0], w[1], w[2], w[3]));
     } else {
       for (int q = 0; o + q < total; ++q) out[o + q] = (w[q >> 2] >> ((q & 3) * 8)) & 0xff;
     }
