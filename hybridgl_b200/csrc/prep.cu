@@ -5,18 +5,19 @@
 //   local[n]  = bilinear_S( where(m_n, Normalize_IN(img/255), clip_pixel_mean) )
 // with the non-antialiased bilinear of T.Resize(..., antialias=None) (ATen upsample_bilinear2d, align_corners=False).
 //
-// B200 design -- three streaming kernels, all HBM-bound, no shared-memory staging (no data reuse inside a kernel):
+// B200 design -- three kernels, all HBM-bound:
 //   pack   : the byte masks (M*H*W B, the largest input of the whole path) are read exactly ONCE, 16 B per lane fully
 //            coalesced, and squeezed to 1 bit/pixel ([M,H,ceil(W/32)] u32).  Every later kernel (prep, mask grid,
-//            heat-map pooling) works on this 8x smaller tensor, which stays L2-resident for typical batches.
+//            heat-map pooling, IoU) works on this 8x smaller tensor, which stays L2-resident for typical batches.
 //   setup  : per IMAGE (not per mask) the two possible answers of every output pixel -- "all four taps inside the mask"
 //            (FG) and "all four outside" (BG) -- for the 6 output planes, already in the output dtype, plus the 24 tap
 //            bytes of the pixel for the rare boundary case.  12 planes of S*S per image: L2-resident.
-//   main   : a thread owns 4 adjacent output pixels and streams over a chunk of masks: 2-4 word loads of mask bits give
-//            all 8 taps; two AND/compare decide FG / BG for the whole group (the overwhelmingly common case) and the
-//            6 planes leave as 8-byte (bf16) / 16-byte (f32) streaming stores.  Only pixels whose taps straddle the mask
-//            boundary re-evaluate the exact per-tap formula.  No barriers, no smem; chunks are small, so the grid has
-//            many waves and no tail.
+//   main   : streams over the masks of an image band by band.  A lane owns 8 adjacent output pixels (4 for f32) and keeps
+//            their FG / BG answers in registers; a producer warp stages the band's bit rows with 1-D bulk async copies;
+//            one funnel shift + two warp votes decide a whole warp's 256 pixels in the common case and the 6 planes leave
+//            as 16-byte streaming stores, 512 contiguous bytes per warp.  Only pixels whose taps straddle the mask outline
+//            re-evaluate the exact per-tap formula (see prep_main_kernel).  The kernel is write-dominated: 2*M*3*S*S
+//            output elements against M*H*W/8 bytes of mask bits.
 // Arithmetic follows ATen's CPU kernel op for op (explicit __fmaf_rn/__fmul_rn/__fdiv_rn, no re-contraction),
 // so f32 output is bit-identical to the reference on the S=224/336 paths (see oracle/hybridgl_oracle.py header).
 #include <stdlib.h>
