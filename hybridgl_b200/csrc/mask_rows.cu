@@ -20,6 +20,8 @@
 // row for a blob).  After every 32-row block the warp folds the rows' horizontal sums into the <= 4 vertical bins they
 // feed (ascending row order).  Bands are independent tasks; the LAST band of a mask to finish (atomic ticket after a
 // __threadfence) adds the four partial results in a fixed order, so results are bit-reproducible from run to run.
+#include <stdlib.h>
+
 #include "hgl_common.cuh"
 
 namespace hgl {
@@ -660,7 +662,8 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
   p.off_pgrid = take(want_grid ? (size_t)warps * p.g * p.g * 4 : 0, 16);
   const size_t smem = off;
   HGL_REQUIRE(smem <= 220 * 1024, "mask rows pass: frame %dx%d (g=%d) needs %zu B of shared memory", p.H, p.W, p.g, smem);
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+  if (const char* pv = getenv("HGL_ROWS_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(pv)));     // tuning hook
   const int ctas = std::min(ceil_div(p.M * kBands, warps), sm_count() * per_sm);
   auto go = [&](auto kern) -> int {
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
