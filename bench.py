@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (ScoringPath.capture) instead of launching every kernel from the host; "
                     "measured equal within noise on the device (0.499 vs 0.495 ms) -- it removes ~0.3 ms of host work per step, which only matters on a slow host")
+    ap.add_argument("--pipeline", action="store_true", help="software-pipeline consecutive steps (ScoringPath.pipelined); measured SLOWER than joined steps "
+                    "(0.647 vs 0.497 ms: pack reads of step k+1 mixed into the prep writes of step k cost more HBM efficiency than the overlap gains)")
     ap.add_argument("--no-overlap", action="store_true", help="launch every stage in order on one stream (no side-stream chain)")
     ap.add_argument("--serial-steps", type=int, default=50, help="extra untimed-for-value pass with overlap off: each kernel timed alone")
     ap.add_argument("--rle-steps", type=int, default=50, help="extra pass with the proposals given as SAM uncompressed RLE (0 = skip)")
@@ -291,6 +293,7 @@ def run_ours(args, cfg):
     # cost ~3 % of the step when every stage is bracketed (profiles/host_overhead.py)
     top_events = []
     top_samples = []
+    pipelined = False
     path.events_only = {"prep"}
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -305,10 +308,16 @@ def run_ours(args, cfg):
                 top_samples.append(e0.elapsed_time(e1))
             prev = g
     else:
+        # --pipeline: consecutive steps software-pipelined (ScoringPath.pipelined): each stage chain has its own stream, two buffer
+        # sets alternate, a step only waits for the step before last; the region ends with a full join (sync + barrier)
+        path.pipelined = path.overlap and args.pipeline
         for s in range(args.steps):
             path.events = []
             path.run(batches[s % 2], max_n)
             top_events.append(path.events)
+        path.sync()
+        pipelined = path.pipelined
+        path.pipelined = False
     path.events = None
     path.events_only = None
     cum = path.cum.clone()
@@ -504,6 +513,7 @@ def run_ours(args, cfg):
                            **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
                 "clocks": clocks, "host_affinity": numa, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
                 "launch": ("one CUDA-graph replay per step (ScoringPath.capture)" if graphs is not None else "eager: one host launch per kernel"),
+                "steps_pipelined": (graphs is None and pipelined),
                 "streams": ("2 (heat-map tables, blur and prep on the caller's stream; pack and the post-pack chain on a high-priority side stream)"
                             if path.overlap else "1"),
                 "ms_per_step_serial": ms_serial,

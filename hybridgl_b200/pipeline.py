@@ -52,9 +52,18 @@ class ScoringPath:
         self._pre: Optional[torch.cuda.Stream] = None
         self._tab: Optional[torch.cuda.Stream] = None
         self._capturing = False
+        # software pipeline across steps (see run()): two buffer sets, no join at the end of a step
+        self.pipelined = False
+        self._pk: Optional[torch.cuda.Stream] = None
+        self._pm: Optional[torch.cuda.Stream] = None
+        self._step = 0
+        self._slot = 0
+        self._done = [None, None]
 
     # ------------------------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype) -> torch.Tensor:
+        if self.pipelined:
+            name = f"{name}#{self._slot}"          # two buffer sets: step k+1 never writes what step k still reads
         t = self._buf.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
@@ -106,18 +115,36 @@ class ScoringPath:
         moff, eoff = batch["mask_off"], batch["expr_off"]
         lib = ops._lib.load()
         main = torch.cuda.current_stream()
-        side = pre = tab = main
+        side = pre = tab = pk = pm = main
+        pipelined = self.overlap and self.pipelined and not self._capturing
         if self.overlap:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device, priority=-1)
                 self._pre = torch.cuda.Stream(device=self.device, priority=-1)
                 self._tab = torch.cuda.Stream(device=self.device, priority=-1)
+                self._pk = torch.cuda.Stream(device=self.device, priority=-1)
+                self._pm = torch.cuda.Stream(device=self.device)
             side, pre, tab = self._side, self._pre, self._tab
-            for s_ in (side, pre, tab):
-                s_.wait_stream(main)
+            pk, pm = side, main
+            if pipelined:
+                # Steps overlap: every stage chain has its own stream (FIFO across steps), the caller's stream only marks
+                # "inputs ready", nothing joins at the end of a step (sync() / res["done"] do), and a step reuses the buffer
+                # set of the step before last only after that step has completed.
+                pk, pm = self._pk, self._pm
+                self._slot = self._step % 2
+                self._step += 1
+                ev_in = torch.cuda.Event()
+                ev_in.record(main)
+                for s_ in (pk, side, pre, tab, pm):
+                    s_.wait_event(ev_in)
+                    for ev in (self._done[self._slot] or ()):
+                        s_.wait_event(ev)
+            else:
+                for s_ in (side, pre, tab):
+                    s_.wait_stream(main)
 
         # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(pk):
             bits = self._get("bits", (M, H, (W + 31) // 32), torch.int32)
             if rle:
                 with self._span("rle"):
@@ -162,15 +189,22 @@ class ScoringPath:
                     ev_tables.record()
 
         # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
-        if ev_pack is not None:
-            main.wait_event(ev_pack)
-            main.wait_event(ev_setup)
-        with self._span("prep"):
-            ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
+        with torch.cuda.stream(pm):
+            if ev_pack is not None:
+                pm.wait_event(ev_pack)
+                pm.wait_event(ev_setup)
+            with self._span("prep"):
+                ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
+            ev_pm = None
+            if pipelined:
+                ev_pm = torch.cuda.Event()
+                ev_pm.record()
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
             feats = features if features is not None else batch.get("features")
+            if pipelined:
+                side.wait_event(ev_pack)
             if ev_tables is not None:
                 side.wait_event(ev_tables)
             with self._span("grid_heat_pool"):
@@ -195,11 +229,27 @@ class ScoringPath:
                                        workspace=sws)
             with self._span("iou"):
                 iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
-        if self.overlap:
+            ev_side = None
+            if pipelined:
+                ev_side = torch.cuda.Event()
+                ev_side.record()
+        if pipelined:
+            if ev_tables is None:          # (split off: the table stream did nothing)
+                pass
+            self._done[self._slot] = (ev_pm, ev_side)
+            res["done"] = (ev_pm, ev_side)
+        elif self.overlap:
             main.wait_stream(side)
             main.wait_stream(tab)          # (already ordered before the mask pass; keeps the join explicit when split is off)
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
+
+    def sync(self) -> None:
+        """Pipelined mode: make the caller's stream wait for every step enqueued so far (results, IoU counters)."""
+        main = torch.cuda.current_stream()
+        for d in self._done:
+            for ev in (d or ()):
+                main.wait_event(ev)
 
     def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None) -> "GraphStep":
         """One step as a CUDA graph: the whole stage graph of run() (four streams, ~12 kernels, memsets, fork / join events) is

@@ -645,3 +645,40 @@ def test_captured_step_equals_eager_step(ops):
     assert path.cum.tolist() == [3 * v for v in eager.cum.tolist()]
     (name, e0, e1), = step.events
     assert name == "prep" and e0.elapsed_time(e1) > 0.0
+
+
+def test_pipelined_steps_equal_joined_steps(ops):
+    """ScoringPath.pipelined: consecutive steps overlap (own stream per stage chain, two buffer sets, no join per step);
+    every step's results and the IoU counters are the same bits as with one joined step at a time."""
+    from hybridgl_b200.pipeline import ScoringPath
+    B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
+    batches = [synth.make_batch_device(90 + i, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True) for i in range(3)]
+    keys = ("local_imgs", "global_imgs", "grid", "area", "score_clip", "score_gem", "idx_hybrid", "idx_final", "iu", "features")
+    ref_path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    refs = []
+    for s in range(7):
+        r = ref_path.run(batches[s % 3], n)
+        refs.append({k: r[k].clone() for k in keys})
+    torch.cuda.synchronize()
+    path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    path.pipelined = True
+    outs = []
+    for s in range(7):
+        r = path.run(batches[s % 3], n)
+        for ev in r["done"]:
+            torch.cuda.current_stream().wait_event(ev)
+        outs.append({k: r[k].clone() for k in keys})          # cloned on the caller's stream after the step's done events
+    path.sync()
+    torch.cuda.synchronize()
+    for s in range(7):
+        for k in keys:
+            assert torch.equal(outs[s][k], refs[s][k]), (s, k)
+    assert path.cum.tolist() == ref_path.cum.tolist()
+    # and without touching the results in between (the bench's sweep form): only the counters matter
+    path2 = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    path2.pipelined = True
+    for s in range(7):
+        path2.run(batches[s % 3], n)
+    path2.sync()
+    torch.cuda.synchronize()
+    assert path2.cum.tolist() == ref_path.cum.tolist()
