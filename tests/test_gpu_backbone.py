@@ -102,3 +102,15 @@ def test_utils_mirror(golden):
             i0, u0, ref_iou = O.compute_iou(masks[pick], target)
             assert abs(float(iou) - ref_iou) < 1e-6
         assert len(lst) == 2
+
+
+@pytest.mark.parametrize("mode", ["G2L", "L2G", "G2L&L2G"])
+def test_example_eval_loop_runs_all_fusion_modes(mode):
+    """examples/eval_synthetic.py: the reference's evaluation loop with libhgl behind it, end to end with the ViT blocks."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("eval_synthetic", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "eval_synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rep = mod.main(["--images", "2", "--masks", "12", "--expr", "2", "--fusion_mode", mode, "--height", "240", "--width", "320"])
+    assert rep["n_expressions"] == 4 and 0.0 <= rep["oIoU"] <= 100.0
