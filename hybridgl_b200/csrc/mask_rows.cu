@@ -151,14 +151,16 @@ static HeatWs heat_carve(void* ws, int E, int H, int W) {
 // so the CTA first runs the HORIZONTAL pass for those raw rows into shared memory (exactly ATen's intermediate tensor,
 // same tap order), and a pixel is then three shared-memory reads and the vertical taps.  The raw map (a few KB per
 // expression) is read through L1; the frame-sized heat-map never exists in HBM.
-template <bool kLR>
+// kOut (with kLR): write the resized map itself ([E,H,W] in `cr`, pitch Wp = W) instead of the tables -- the up-sampling fast
+// path of hgl_heat_resize_aa (same per-CTA horizontal pass, same tap order as the table form and as ATen).
+template <bool kLR, bool kOut = false>
 __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const float* __restrict__ heat, const int32_t* __restrict__ dirflag,
                                                                       int H, int W, int Wp, int hh, int hw, int nr_max, float* __restrict__ cr,
                                                                       float* __restrict__ rp, float* __restrict__ rowstat) {
   extern __shared__ __align__(16) float ramp[];      // [W rounded up to 128]  (+ kLR: hrow [nr_max][W128])
   const int e = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W128 = (W + 127) & ~127;
-  const int dir = dirflag[e];
+  const int dir = kOut ? 0 : dirflag[e];
   const int y_first = blockIdx.x * kPrefRows, y_last = min(H, y_first + kPrefRows) - 1;
   float* hrow = ramp + W128;                              // kLR: horizontal pass of raw rows [ry0, ry0 + nr)
   int ry0 = 0, nr = 0;
@@ -193,6 +195,27 @@ __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const floa
     float wy[3] = {0.f, 0.f, 0.f};
     if (kLR) aa_fill(y, hh, H, 3, &ymin, &ysize, wy);
     const float* hr = hrow + (ymin - ry0) * W128;
+    if (kLR && kOut) {                                     // the resized row itself: [E,H,W], scalar stores (any W / alignment)
+      float* orow = cr + ((size_t)e * H + y) * W;
+      for (int x0 = 0; x0 < W; x0 += 128) {
+        const int x = x0 + 4 * lane;
+        float h4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          if (ky < ysize) {
+            const float4 t4 = *reinterpret_cast<const float4*>(hr + ky * W128 + x);
+            h4[0] = __fadd_rn(h4[0], __fmul_rn(t4.x, wy[ky])); h4[1] = __fadd_rn(h4[1], __fmul_rn(t4.y, wy[ky]));
+            h4[2] = __fadd_rn(h4[2], __fmul_rn(t4.z, wy[ky])); h4[3] = __fadd_rn(h4[3], __fmul_rn(t4.w, wy[ky]));
+          }
+        }
+        if (x + 3 < W && ((reinterpret_cast<uintptr_t>(orow + x) & 15) == 0)) *reinterpret_cast<float4*>(orow + x) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (x + q < W) orow[x + q] = h4[q];
+        }
+      }
+      continue;
+    }
     for (int pass = (y == 0 ? 0 : 1); pass < 2; ++pass) {   // pass 0 (row 0 only): the ramp itself; pass 1: A * ramp
       float* dst = (pass == 0) ? rp + (size_t)e * Wp : cr + ((size_t)e * H + y) * Wp;
       float mn = INFINITY, mx = -INFINITY, carry = 0.f;
@@ -834,8 +857,23 @@ extern "C" int hgl_heat_resize_aa(const float* heat_raw, int E, int hh, int hw, 
   if (E == 0) return HGL_OK;
   HGL_REQUIRE(heat_raw && out, "hgl_heat_resize_aa: null pointer");
   HGL_REQUIRE(E > 0 && hh >= 1 && hw >= 1 && H >= 1 && W >= 1, "hgl_heat_resize_aa: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (aa_maxk(hh, H) <= 3 && aa_maxk(hw, W) <= 3 && E <= 65535) {
+    // both axes up-sampled (the GEM case, 28x37 -> frame): a CTA runs the horizontal pass for the few raw rows behind its 32
+    // output rows once (shared memory), every pixel is then three shared-memory reads and the vertical taps
+    const size_t w128 = (size_t)((W + 127) & ~127);
+    const int nr_max = (int)((double)kPrefRows * hh / H) + 4;
+    const size_t smem = w128 * 4 * (1 + (size_t)nr_max);
+    if (smem <= 200 * 1024) {
+      auto kern = heat_prefix_kernel<true, true>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("hgl_heat_resize_aa: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+      kern<<<dim3(ceil_div(H, kPrefRows), E), kPrefWarps * 32, smem, st>>>(heat_raw, nullptr, H, W, W, hh, hw, nr_max, out, nullptr, nullptr);
+      return launch_status("hgl_heat_resize_aa");
+    }
+  }
   const int blocks = (int)std::min<size_t>(((size_t)E * H * W + 255) / 256, (size_t)sm_count() * 16);
-  heat_resize_aa_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(heat_raw, E, hh, hw, H, W, out);
+  heat_resize_aa_kernel<<<blocks, 256, 0, st>>>(heat_raw, E, hh, hw, H, W, out);
   return launch_status("hgl_heat_resize_aa");
 }
 
