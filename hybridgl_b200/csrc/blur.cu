@@ -28,8 +28,9 @@ __host__ __device__ constexpr uint32_t gq(int k) {   // Q8 taps of getGaussianKe
   return (k >= 0 && k < 15) ? q[k] : 0u;
 }
 // row pass: coefficient quad of word wi (bytes 4wi..4wi+3 of the 20-byte window) for output j of the group (tap = byte - j)
+// (plane column k holds pixel x0 - 8 + k, so byte b of the window is tap b - 1 - j of output j)
 __host__ __device__ constexpr uint32_t row_coef(int j, int wi) {
-  return gq(4 * wi - j) | (gq(4 * wi + 1 - j) << 8) | (gq(4 * wi + 2 - j) << 16) | (gq(4 * wi + 3 - j) << 24);
+  return gq(4 * wi - 1 - j) | (gq(4 * wi - j) << 8) | (gq(4 * wi + 1 - j) << 16) | (gq(4 * wi + 2 - j) << 24);
 }
 // col pass: coefficient pair p for an output row of parity `odd` (taps 2p, 2p+1 for even rows; 2p-1, 2p for odd rows)
 __host__ __device__ constexpr uint32_t col_coef(int odd, int p) {
@@ -50,12 +51,31 @@ __global__ void __launch_bounds__(256) blur15_kernel(const uint8_t* __restrict__
   const uint8_t* src = img + (size_t)b * H * W * 3;
   const int tid = threadIdx.x;
 
-  // ---- load + de-interleave (reflect-101 border)
-  for (int t = tid; t < kInH * kInW; t += 256) {
-    const int ty = t / kInW, tx = t - ty * kInW;
-    const int y = reflect101(y0 + ty - kBR, H), x = reflect101(x0 + tx - kBR, W);
-    const uint8_t* px = src + ((size_t)y * W + x) * 3;
-    plane[0][ty][tx] = px[0]; plane[1][ty][tx] = px[1]; plane[2][ty][tx] = px[2];
+  // ---- load + de-interleave (reflect-101 border).  Plane column k holds pixel x0 - 8 + k (column 0 is only there so that
+  //      groups of 4 pixels = 12 interleaved bytes = 3 aligned words line up with the plane's words).
+  const bool interior = x0 >= 8 && x0 + kTX + 8 <= W && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;   // block-uniform
+  if (interior) {
+    // 4 pixels per item: three 32-bit loads, six byte permutes, three 32-bit shared-memory stores
+    constexpr int kGroups = (kTX + 16) / 4;                              // 20 groups cover pixels x0-8 .. x0+71
+    for (int t = tid; t < kInH * kGroups; t += 256) {
+      const int ty = t / kGroups, gq4 = t - ty * kGroups;
+      const int y = reflect101(y0 + ty - kBR, H);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + ((size_t)y * W + (x0 - 8)) * 3) + 3 * gq4;
+      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);     // R0G0B0R1 G1B1R2G2 B2R3G3B3
+      const uint32_t r = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+      const uint32_t g = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+      const uint32_t bl = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+      reinterpret_cast<uint32_t*>(&plane[0][ty][0])[gq4] = r;
+      reinterpret_cast<uint32_t*>(&plane[1][ty][0])[gq4] = g;
+      reinterpret_cast<uint32_t*>(&plane[2][ty][0])[gq4] = bl;
+    }
+  } else {
+    for (int t = tid; t < kInH * kInW; t += 256) {
+      const int ty = t / kInW, tx = t - ty * kInW;
+      const int y = reflect101(y0 + ty - kBR, H), x = reflect101(x0 + tx - kBR, W);
+      const uint8_t* px = src + ((size_t)y * W + x) * 3;
+      plane[0][ty][tx + 1] = px[0]; plane[1][ty][tx + 1] = px[1]; plane[2][ty][tx + 1] = px[2];
+    }
   }
   __syncthreads();
 
