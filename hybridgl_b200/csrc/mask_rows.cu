@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const floa
   const int dir = kOut ? 0 : dirflag[e];
   const int y_first = blockIdx.x * kPrefRows, y_last = min(H, y_first + kPrefRows) - 1;
   float* hrow = ramp + W128;                              // kLR: horizontal pass of raw rows [ry0, ry0 + nr)
+  __shared__ int s_ymin[kPrefRows], s_ysize[kPrefRows];   // kLR: vertical taps of the CTA's rows, built once (not once per lane)
+  __shared__ float s_wy[kPrefRows][3];
+  if (kLR && (int)threadIdx.x <= y_last - y_first)
+    aa_fill(y_first + threadIdx.x, hh, H, 3, &s_ymin[threadIdx.x], &s_ysize[threadIdx.x], s_wy[threadIdx.x]);
   int ry0 = 0, nr = 0;
   if (kLR) {
     int ym, ys;
@@ -193,7 +197,10 @@ __global__ void __launch_bounds__(kPrefWarps * 32) heat_prefix_kernel(const floa
     const bool vec = !kLR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
     int ymin = 0, ysize = 0;
     float wy[3] = {0.f, 0.f, 0.f};
-    if (kLR) aa_fill(y, hh, H, 3, &ymin, &ysize, wy);
+    if (kLR) {
+      const int r = y - y_first;
+      ymin = s_ymin[r]; ysize = s_ysize[r]; wy[0] = s_wy[r][0]; wy[1] = s_wy[r][1]; wy[2] = s_wy[r][2];
+    }
     const float* hr = hrow + (ymin - ry0) * W128;
     if (kLR && kOut) {                                     // the resized row itself: [E,H,W], scalar stores (any W / alignment)
       float* orow = cr + ((size_t)e * H + y) * W;
