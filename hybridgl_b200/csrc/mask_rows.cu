@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) heat_resize_aa_kernel(const float* __rest
 }
 
 // ---- the pass over the packed masks ----------------------------------------------------------------------------------
-constexpr int kBands = 4;                              // row bands (= independent warp tasks) per mask
+constexpr int kBands = 8;                              // row bands (= independent warp tasks) per mask
 
 struct RowsScratch {         // global scratch of one launch (byte offsets 256-aligned)
   int32_t* tickets;          // [M + 1]        zero at launch; entry M is the task counter of the dynamic scheduler
