@@ -54,6 +54,8 @@ class ScoringPath:
         self._capturing = False
         # software pipeline across steps (see run()): two buffer sets, no join at the end of a step
         self.pipelined = False
+        import os as _os
+        self.rows_first = bool(int(_os.environ.get("HGL_ROWS_FIRST", "0")))
         self._pk: Optional[torch.cuda.Stream] = None
         self._pm: Optional[torch.cuda.Stream] = None
         self._step = 0
@@ -119,13 +121,16 @@ class ScoringPath:
         pipelined = self.overlap and self.pipelined and not self._capturing
         if self.overlap:
             if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device, priority=-1)
-                self._pre = torch.cuda.Stream(device=self.device, priority=-1)
-                self._tab = torch.cuda.Stream(device=self.device, priority=-1)
-                self._pk = torch.cuda.Stream(device=self.device, priority=-1)
+                import os as _os
+                pr = lambda name, d: int(_os.environ.get(name, str(d)))      # noqa: E731  (tuning hooks; defaults = the bench)
+                self._side = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_SIDE", -1))
+                self._pre = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_PRE", -1))
+                self._tab = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_TAB", -1))
+                self._pk = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_PACK", -1))
                 self._pm = torch.cuda.Stream(device=self.device)
+                self._own_pack_stream = bool(pr("HGL_PACK_STREAM", 0))
             side, pre, tab = self._side, self._pre, self._tab
-            pk, pm = side, main
+            pk, pm = (self._pk if self._own_pack_stream else side), main
             if pipelined:
                 # Steps overlap: every stage chain has its own stream (FIFO across steps), the caller's stream only marks
                 # "inputs ready", nothing joins at the end of a step (sync() / res["done"] do), and a step reuses the buffer
@@ -140,7 +145,7 @@ class ScoringPath:
                     for ev in (self._done[self._slot] or ()):
                         s_.wait_event(ev)
             else:
-                for s_ in (side, pre, tab):
+                for s_ in {side, pre, tab, pk}:
                     s_.wait_stream(main)
 
         # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
@@ -188,22 +193,10 @@ class ScoringPath:
                     ev_tables = torch.cuda.Event()
                     ev_tables.record()
 
-        # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
-        with torch.cuda.stream(pm):
-            if ev_pack is not None:
-                pm.wait_event(ev_pack)
-                pm.wait_event(ev_setup)
-            with self._span("prep"):
-                ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
-            ev_pm = None
-            if pipelined:
-                ev_pm = torch.cuda.Event()
-                ev_pm.record()
-
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
             feats = features if features is not None else batch.get("features")
-            if pipelined:
+            if pk is not side:
                 side.wait_event(ev_pack)
             if ev_tables is not None:
                 side.wait_event(ev_tables)
@@ -218,6 +211,27 @@ class ScoringPath:
                         heat = ops.heat_resize_aa(heat, H, W, out=self._get("heat_full", (E, H, W), torch.float32))
                     grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
                     score_gem = ops.heat_pool(heat, batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
+            ev_rows = None
+            if self.overlap and self.rows_first:
+                ev_rows = torch.cuda.Event()
+                ev_rows.record()
+
+        # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
+        with torch.cuda.stream(pm):
+            if ev_pack is not None:
+                pm.wait_event(ev_pack)
+                pm.wait_event(ev_setup)
+                if ev_rows is not None:
+                    pm.wait_event(ev_rows)
+            with self._span("prep"):
+                ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
+            ev_pm = None
+            if pipelined:
+                ev_pm = torch.cuda.Event()
+                ev_pm.record()
+
+        # ---- chain S, last part: mask pooling -> score/select -> IoU (small kernels, in the shadow of the prep writes)
+        with torch.cuda.stream(side):
             if self.feature_source == "tokens" and features is None:
                 mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
                 with self._span("mask_pool"):
