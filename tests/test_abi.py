@@ -55,6 +55,11 @@ def test_sass_is_sm100(lib):
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout or "SM100a" in out.stdout or "sm_100" in out.stdout
     assert "STG.E.NA" in out.stdout        # streaming (no-allocate) stores of the prep kernel
+    # the Blackwell-only machinery the design relies on is really in the binary (B200_PROFILING.md, SASS mnemonics):
+    assert "UTCHMMA" in out.stdout         # tcgen05.mma (mask pooling on the 5th-generation tensor cores)
+    assert "LDTM" in out.stdout            # tcgen05.ld (TMEM accumulator read-back in the epilogue)
+    assert "UBLKCP" in out.stdout          # cp.async.bulk (TMA bulk copies: bit-row stages of prep_main)
+    assert "SYNCS.ARRIVE.TRANS64" in out.stdout   # mbarrier expect_tx / arrive (full / empty barriers of the stage ring)
 
 
 def test_ops_fail_loudly_without_cuda(lib):
