@@ -6,7 +6,7 @@ PyTorch is used for device memory and streams only -- no arithmetic of the path 
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch
 

@@ -11,6 +11,7 @@ buffers, streams and the order of launches.  Host language stays Python like the
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -54,8 +55,7 @@ class ScoringPath:
         self._capturing = False
         # software pipeline across steps (see run()): two buffer sets, no join at the end of a step
         self.pipelined = False
-        import os as _os
-        self.rows_first = bool(int(_os.environ.get("HGL_ROWS_FIRST", "0")))
+        self.rows_first = bool(int(os.environ.get("HGL_ROWS_FIRST", "0")))      # tuning hook: prep waits for the mask pass
         self._pk: Optional[torch.cuda.Stream] = None
         self._pm: Optional[torch.cuda.Stream] = None
         self._step = 0
@@ -121,8 +121,7 @@ class ScoringPath:
         pipelined = self.overlap and self.pipelined and not self._capturing
         if self.overlap:
             if self._side is None:
-                import os as _os
-                pr = lambda name, d: int(_os.environ.get(name, str(d)))      # noqa: E731  (tuning hooks; defaults = the bench)
+                pr = lambda name, d: int(os.environ.get(name, str(d)))      # noqa: E731  (tuning hooks; defaults = the bench)
                 self._side = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_SIDE", -1))
                 self._pre = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_PRE", -1))
                 self._tab = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_TAB", -1))

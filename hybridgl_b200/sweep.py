@@ -14,7 +14,7 @@ NCCL is the backend on GPUs; the same code runs under gloo on CPU tensors (tests
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
