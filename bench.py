@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (ScoringPath.capture) instead of launching every kernel from the host; "
                     "measured equal within noise on the device (0.499 vs 0.495 ms) -- it removes ~0.3 ms of host work per step, which only matters on a slow host")
     ap.add_argument("--pipeline", action="store_true", help="software-pipeline consecutive steps (ScoringPath.pipelined); measured SLOWER than joined steps "
-                    "(0.647 vs 0.497 ms: pack reads of step k+1 mixed into the prep writes of step k cost more HBM efficiency than the overlap gains)")
+                    "(0.65 ms or worse vs 0.48 ms: pack reads of step k+1 mixed into the prep writes of step k cost more HBM efficiency than the overlap gains)")
     ap.add_argument("--no-overlap", action="store_true", help="launch every stage in order on one stream (no side-stream chain)")
     ap.add_argument("--serial-steps", type=int, default=50, help="extra untimed-for-value pass with overlap off: each kernel timed alone")
     ap.add_argument("--rle-steps", type=int, default=50, help="extra pass with the proposals given as SAM uncompressed RLE (0 = skip)")
