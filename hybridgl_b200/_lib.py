@@ -54,6 +54,10 @@ SIGNATURES = {
     "hgl_mask_pool_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "hgl_mask_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_void_p]),
+    "hgl_pool_score_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_double, c_double, c_double, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgl_score_select_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "hgl_iou": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p]),

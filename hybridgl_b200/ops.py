@@ -424,12 +424,63 @@ def mask_pool(weights: torch.Tensor, tokens: torch.Tensor, mask_off: Optional[to
         max_n = max(M, 1)
     lib = _lib.load()
     out = torch.empty((M, D), dtype=dtype, device=w.device)
-    need = lib.hgl_mask_pool_workspace_bytes(M, D, _dt(dtype))
-    if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=w.device)
     check(lib.hgl_mask_pool(w.data_ptr(), tok.data_ptr(), _ptr(moff), B, M, max_n, L, D, int(bool(normalize)), _dt(dtype),
-                            out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_mask_pool")
+                            out.data_ptr(), _ptr(workspace), _stream()), "hgl_mask_pool")
     return out
+
+
+def pool_score_select(weights: torch.Tensor, tokens: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, others: torch.Tensor,
+                      other_off: torch.Tensor, boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],
+                      mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
+                      logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
+                      want_features: bool = False, dtype: torch.dtype = torch.bfloat16):
+    """mask_pool + score_select in ONE kernel (hgl_pool_score_select): the pooled, normalised rows are scored straight from
+    the f32 TMEM accumulators and only leave the SM when want_features is set.  Returns the score_select dict
+    (+ "features" [M,D] of `dtype` when want_features)."""
+    _req(weights, torch.float32, "weights")
+    w = weights.reshape(weights.shape[0], -1)
+    tok = tokens[None] if tokens.dim() == 2 else tokens
+    _req(tok, torch.bfloat16, "tokens", 3)
+    M, L = w.shape
+    B, Lt, D = tok.shape
+    if Lt != L:
+        raise ValueError(f"weights have {L} cells per mask, tokens {Lt} per image")
+    _req(sent, torch.float32, "sent", 2)
+    _req(noun, torch.float32, "noun", 2)
+    E = sent.shape[0]
+    _req(others, torch.float32, "others", 2)
+    _req(other_off, torch.int32, "other_off", 1)
+    _req(boxes, torch.int64, "boxes", 2)
+    _req(relaflag, torch.int32, "relaflag", 1)
+    if sent.shape != (E, D) or noun.shape != (E, D) or other_off.numel() != E + 1 or boxes.shape != (M, 4):
+        raise ValueError("pool_score_select: inconsistent shapes")
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    if score_gem is not None:
+        _req(score_gem, torch.float32, "score_gem", 2)
+        if score_gem.shape != (E, max_n):
+            raise ValueError("score_gem must be [E, max_n]")
+    dev = w.device
+    feats = torch.empty((M, D), dtype=dtype, device=dev) if want_features else None
+    score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
+    idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
+    idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
+    top = torch.empty((E, 3), dtype=torch.int32, device=dev)
+    blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    check(_lib.load().hgl_pool_score_select(w.data_ptr(), tok.data_ptr(), _ptr(moff), _ptr(eoff), B, M, E, max_n, L, D,
+                                            sent.data_ptr(), noun.data_ptr(), others.data_ptr(), other_off.data_ptr(),
+                                            boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
+                                            float(logit_scale_exp), float(r), float(alpha), _ptr(feats), _dt(dtype),
+                                            score_clip.data_ptr(), idx_h.data_ptr(), idx_f.data_ptr(), top.data_ptr(),
+                                            blended.data_ptr(), _stream()), "hgl_pool_score_select")
+    res = dict(score_clip=score_clip, idx_hybrid=idx_h, idx_final=idx_f, top_idx=top, blended=blended)
+    if want_features:
+        res["features"] = feats
+    return res
 
 
 # ---- (a6)-(a9),(a12) ----------------------------------------------------------------------------------
@@ -468,14 +519,11 @@ def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, oth
     idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
     top = torch.empty((E, 3), dtype=torch.int32, device=dev)
     blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
-    need = _lib.load().hgl_score_select_workspace_bytes(B, E, max_n)
-    if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
     check(_lib.load().hgl_score_select(feat.data_ptr(), _dt(feat.dtype), sent.data_ptr(), noun.data_ptr(), others.data_ptr(),
                                        other_off.data_ptr(), boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
                                        _ptr(moff), _ptr(eoff), B, M, E, De, max_n, float(logit_scale_exp), float(r), float(alpha),
                                        score_clip.data_ptr(), idx_h.data_ptr(), idx_f.data_ptr(), top.data_ptr(),
-                                       blended.data_ptr(), workspace.data_ptr(), _stream()), "hgl_score_select")
+                                       blended.data_ptr(), _ptr(workspace), _stream()), "hgl_score_select")
     return dict(score_clip=score_clip, idx_hybrid=idx_h, idx_final=idx_f, top_idx=top, blended=blended)
 
 

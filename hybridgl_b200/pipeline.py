@@ -30,13 +30,16 @@ class ScoringPath:
 
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
-                 feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True):
+                 feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True,
+                 keep_features: bool = False):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
-        under every proposal's soft grid mask on the tensor cores (hgl_mask_pool) and the pooled, normalised rows are scored."""
+        under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
+        keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"]."""
         if feature_source not in ("supplied", "tokens"):
             raise ValueError(feature_source)
         self.feature_source = feature_source
+        self.keep_features = keep_features
         ops.device_ok()
         self.size, self.grid = size, grid
         self.prep_dtype, self.antialias, self.background = prep_dtype, antialias, background
@@ -232,14 +235,16 @@ class ScoringPath:
         # ---- chain S, last part: mask pooling -> score/select -> IoU (small kernels, in the shadow of the prep writes)
         with torch.cuda.stream(side):
             if self.feature_source == "tokens" and features is None:
-                mws = self._get("pool_ws", (max(lib.hgl_mask_pool_workspace_bytes(M, batch["tokens"].shape[2], ops.HGL_BF16), 1),), torch.uint8)
-                with self._span("mask_pool"):
-                    feats = ops.mask_pool(grid, batch["tokens"], moff, max_n, normalize=True, dtype=torch.bfloat16, workspace=mws)
-            sws = self._get("score_ws", (max(lib.hgl_score_select_workspace_bytes(B, E, max_n), 1),), torch.uint8)
-            with self._span("score_select"):
-                res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
-                                       batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha,
-                                       workspace=sws)
+                # pooling (tcgen05) + cosine scoring + selection tail in ONE launch; the pooled rows stay on the SM unless asked for
+                with self._span("pool_score"):
+                    res = ops.pool_score_select(grid, batch["tokens"], batch["sent"], batch["noun"], batch["others"], batch["other_off"],
+                                                batch["boxes"], batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp,
+                                                self.r, self.alpha, want_features=self.keep_features, dtype=torch.bfloat16)
+                feats = res.pop("features", None)
+            else:
+                with self._span("score_select"):
+                    res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
+                                           batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)
             with self._span("iou"):
                 iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
             ev_side = None
@@ -290,11 +295,12 @@ class ScoringPath:
             self.events, self.events_only = saved
         return GraphStep(graph, res, events, batch)
 
-    # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), score_select 2 (text, score+select), iou 2
-    LAUNCHES_PER_RUN = 11      # + 1 (mask_pool) with feature_source="tokens"
+    # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), scoring 1 (hgl_score_select, or
+    # hgl_pool_score_select with feature_source="tokens"), iou 2
+    LAUNCHES_PER_RUN = 10
 
     def launches_per_run(self) -> int:
-        return self.LAUNCHES_PER_RUN + (1 if self.feature_source == "tokens" else 0)
+        return self.LAUNCHES_PER_RUN
 
     def input_keys(self, host_batch=None):
         skip = {"features" if self.feature_source == "tokens" else "tokens"}

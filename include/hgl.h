@@ -166,12 +166,28 @@ HGL_API int hgl_grid_heat_pool_rows(const uint32_t* bits, const int32_t* mask_of
  * The masks x tokens x D contraction of the north star; token-space form of the pooling loop Hybridgl_main.py:218-223
  * (S_in = (M~ . F^) . t) with the normalisation of model/backbone.py:79 fused:
  *   pooled[n,:] = sum_l weights[n,l] * tokens[b(n)][l,:];   out[n,:] = normalize ? pooled / ||pooled||_2 : pooled
- * weights f32 [M,L] (e.g. the soft grid masks of hgl_mask_grid, L = g*g); tokens bf16 [B,L,D] (D % 16 == 0);
- * mask_off int32 [B+1] (NULL => B==1); out [M,D] of out_dtype.  bf16 x bf16 -> f32 on tcgen05 (weights are rounded to
- * bf16 once).  workspace: hgl_mask_pool_workspace_bytes(M, D, out_dtype) bytes, 16-byte aligned (may be NULL for f32 output). */
+ * weights f32 [M,L] (e.g. the soft grid masks of hgl_mask_grid, L = g*g); tokens bf16 [B,L,D] (D % 8 == 0, 16-byte aligned;
+ * staged by TMA); mask_off int32 [B+1] (NULL => B==1); out [M,D] of out_dtype.  bf16 x bf16 -> f32 on tcgen05; the f32
+ * weights enter as a hi + lo pair of bf16 operands (two MMAs), i.e. with 16 mantissa bits, not 8.
+ * At most min(512, 128 * (512 / Nw)) proposals per image (Nw = 64 for D <= 512, 128 for D <= 1024, else 256).
+ * workspace: unused (hgl_mask_pool_workspace_bytes() == 0; may be NULL). */
 HGL_API int64_t hgl_mask_pool_workspace_bytes(int M, int D, int out_dtype);
 HGL_API int hgl_mask_pool(const float* weights, const void* tokens, const int32_t* mask_off, int B, int M, int max_n, int L, int D,
                   int normalize, int out_dtype, void* out, void* workspace, void* stream);
+
+/* ---- (b3') + (a6)-(a9),(a12) in ONE kernel ------------------------------------------------------------
+ * hgl_mask_pool followed by hgl_score_select without the pooled features ever leaving the SM: the cosine scores
+ * (model/backbone.py:74-87 on the text ensemble / negatives of Hybridgl_main.py:153-166) are taken from the f32 TMEM
+ * accumulators, the selection tail (Hybridgl_main.py:168-196, 225-227; utils.py:240-268) runs in the same launch.
+ * Arguments as in hgl_mask_pool (weights, tokens, L, D) and hgl_score_select (everything else).
+ * features_out: [M,D] of out_dtype, the normalised pooled rows, or NULL (nothing but scores and picks is written). */
+HGL_API int hgl_pool_score_select(const float* weights, const void* tokens, const int32_t* mask_off, const int32_t* expr_off,
+                          int B, int M, int E, int max_n, int L, int D,
+                          const float* sent, const float* noun, const float* others, const int32_t* other_off,
+                          const int64_t* boxes, const int32_t* relaflag, const float* score_gem,
+                          double logit_scale_exp, double r, double alpha, void* features_out, int out_dtype,
+                          float* score_clip, int64_t* idx_hybrid, int64_t* idx_final, int32_t* top_idx, float* blended,
+                          void* stream);
 
 /* ---- (a6)-(a9),(a12) scoring, spatial-relationship re-ranking, per-expression argmax ----------------
  * Replaces Hybridgl_main.py:153-196 and :225-227 plus CLIPViTFM.calculate_score model/backbone.py:74-87 and
@@ -183,8 +199,8 @@ HGL_API int hgl_mask_pool(const float* weights, const void* tokens, const int32_
  * feat [M,De] feat_dtype; sent/noun f32 [E,De]; others f32 [K,De] with other_off int32 [E+1];
  * boxes int64 [M,4] XYWH; relaflag int32 [E]; score_gem f32 [E,max_n] or NULL (=> alpha term skipped);
  * outputs: score_clip f32 [E,max_n] (pre-softmax), idx_hybrid/idx_final int64 [E] (index local to the image),
- * top_idx int32 [E,3] (-1 padded), blended f32 [E,3].
- * workspace: hgl_score_select_workspace_bytes(B, E, max_n) bytes, 256-byte aligned (negative scores + per-image tickets). */
+ * top_idx int32 [E,3] (-1 padded), blended f32 [E,3].  Masks of an image beyond max_n are ignored.
+ * workspace: unused (hgl_score_select_workspace_bytes() == 0; may be NULL): one launch, scores meet in distributed shared memory. */
 HGL_API int64_t hgl_score_select_workspace_bytes(int B, int E, int max_n);
 HGL_API int hgl_score_select(const void* feat, int feat_dtype, const float* sent, const float* noun, const float* others,
                      const int32_t* other_off, const int64_t* boxes, const int32_t* relaflag, const float* score_gem,

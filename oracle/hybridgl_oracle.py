@@ -375,11 +375,10 @@ def score_and_select(features, sentence_feat, noun_feat, other_feats, boxes, rel
 def mask_pool_tokens(weights: np.ndarray, tokens: np.ndarray, normalize: bool = True) -> np.ndarray:
     """Token-space form of the pooling loop Hybridgl_main.py:218-223:
     pooled[n,:] = sum_l weights[n,l] * tokens[l,:]  (the masks x tokens x D contraction), optionally followed by the
-    L2 normalisation of model/backbone.py:79.  weights f32 [N,L] (rounded to bf16 like the kernel's A operand),
-    tokens [L,D] (bf16-representable).  No reference code computes this directly; tests/test_oracle_golden.py pins it to
-    gem_pool through the identity  sum_p m[p] * (U h)[p] == (U^T m) . h  for the linear up-sampling U of the heat-map."""
-    from hybridgl_b200.synth import bf16_round
-    w = bf16_round(np.asarray(weights, f32).reshape(weights.shape[0], -1)).astype(f64)
+    L2 normalisation of model/backbone.py:79.  weights f32 [N,L] (used exactly as given), tokens [L,D]; accumulated in
+    float64.  No reference code computes this directly; tests/test_oracle_golden.py pins it to gem_pool through the
+    identity  sum_p m[p] * (U h)[p] == (U^T m) . h  for the linear up-sampling U of the heat-map."""
+    w = np.asarray(weights, f32).reshape(weights.shape[0], -1).astype(f64)
     pooled = (w @ np.asarray(tokens, f64)).astype(f32)
     if normalize:
         with np.errstate(divide="ignore", invalid="ignore"):

@@ -129,9 +129,9 @@ def test_token_space_pooling_equals_pixel_space_pooling():
     weights = (masks.reshape(n, -1).astype(np.float64) @ U).astype(np.float32)          # U^T m, one row per mask
     # exact identity with unrounded weights ...
     np.testing.assert_allclose((weights.astype(np.float64) @ F.astype(np.float64)) @ t, s_in_pixel, rtol=1e-5)
-    # ... and the oracle (weights rounded to bf16 like the kernel's A operand) within bf16 accuracy
+    # ... and the oracle (f32 weights as given, f32 pooled rows) within the north star's 1e-3
     pooled = O.mask_pool_tokens(weights, F, normalize=False)
-    np.testing.assert_allclose(pooled.astype(np.float64) @ t, s_in_pixel, rtol=2e-2, atol=2e-2 * np.abs(s_in_pixel).max())
+    np.testing.assert_allclose(pooled.astype(np.float64) @ t, s_in_pixel, rtol=1e-3, atol=1e-3 * np.abs(s_in_pixel).max())
     # closed form of Hybridgl_main.py:220 from the pooled sums == gem_pool on the pixel map
     black = 1.8
     area = masks.reshape(n, -1).sum(1)
