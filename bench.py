@@ -34,21 +34,27 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", type=int, default=2, help="BASELINE.json config index (1-based), default 2")
-    ap.add_argument("--images", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--images", type=int, default=None, help="images per GPU per pass (default 16; 8 with --sweep)")
+    ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (ScoringPath.capture) instead of launching every kernel from the host; "
-                    "measured equal within noise on the device (0.499 vs 0.495 ms) -- it removes ~0.3 ms of host work per step, which only matters on a slow host")
-    ap.add_argument("--pipeline", action="store_true", help="software-pipeline consecutive steps (ScoringPath.pipelined); measured SLOWER than joined steps "
-                    "(0.65 ms or worse vs 0.48 ms: pack reads of step k+1 mixed into the prep writes of step k cost more HBM efficiency than the overlap gains)")
-    ap.add_argument("--no-overlap", action="store_true", help="launch every stage in order on one stream (no side-stream chain)")
+    ap.add_argument("--no-backbone-view", action="store_true", help="skip the e2e_with_backbone view (path + random-init PyTorch CLIP ViT, N=1 only)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the step from a CUDA graph "
+                    "(ScoringPath.capture); device time per pass is equal within noise, the graph removes ~0.3 ms of host work per pass")
+    ap.add_argument("--inner", type=int, default=0, help="passes per timed step; 0 = sized so that the timed region lasts >= 0.6 s")
+    ap.add_argument("--no-overlap", action="store_true", help="launch every stage in order on one stream (no helper streams)")
     ap.add_argument("--serial-steps", type=int, default=50, help="extra untimed-for-value pass with overlap off: each kernel timed alone")
-    ap.add_argument("--rle-steps", type=int, default=50, help="extra pass with the proposals given as SAM uncompressed RLE (0 = skip)")
+    ap.add_argument("--rle-steps", type=int, default=200, help="extra pass with the proposals given as SAM uncompressed RLE (0 = skip)")
+    ap.add_argument("--sweep", action="store_true", help="strong-scaling evaluation sweep (BASELINE.json configs[4]; use with --workload 5)")
+    ap.add_argument("--sweep-images", type=int, default=4096)
+    ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
                     help="tokens: pool dense patch tokens under the grid masks on the tensor cores (hgl_mask_pool) and score those; "
                          "supplied: score hybrid features given as an input")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.images is None:
+        a.images = 8 if a.sweep else 16
+    return a
 
 
 def workload_config(idx: int, images: int):
@@ -187,7 +193,8 @@ def workload_name(cfg):
     vit = "ViT-L/14@336" if cfg["S"] == 336 else "ViT-B/16"
     return (f"RefCOCO-shaped synthetic batch: {cfg['images_per_gpu_per_step']} images/GPU/step, {cfg['h']}x{cfg['w']}, "
             f"{cfg['n_masks']} masks/image, {cfg['n_expr']} expressions/image, {vit} geometry (S={cfg['S']}, g={cfg['g']}, "
-            f"De={cfg['De']}), fusion_mode {cfg['fusion_mode']}; features: dense tokens pooled per mask (hgl_mask_pool) unless --features supplied")
+            f"De={cfg['De']}); features: dense patch tokens pooled per mask and scored on the tensor cores (hgl_pool_score_select) "
+            f"unless --features supplied")
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -225,20 +232,17 @@ def algorithmic_bytes(cfg, B, prep_bytes):
         "heat_tables": ET * 28 * 37 * 4 + ET * H * W * 4,
         # one pass over the packed masks (mask grid + heat-map pooling): packed masks in, grid + pooled scores out
         "grid_heat_pool": M * H * ((W + 31) // 32) * 4 + M * cfg["g"] ** 2 * 4 + ET * N * 4,
-        # tensor-core pooling of the dense tokens: soft masks f32 + tokens bf16 in, pooled rows bf16 out (flops: MASK_POOL_FLOPS)
-        "mask_pool": M * cfg["g"] ** 2 * 4 + B * cfg["g"] ** 2 * De * 2 + M * De * 2,
+        # tensor-core pooling + scoring + selection in one kernel: soft masks f32 + tokens bf16 + text + boxes in, scores / picks out
+        # (the pooled rows never reach HBM); flops: 2*M*L*De
+        "pool_score": M * cfg["g"] ** 2 * 4 + B * cfg["g"] ** 2 * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
         "score_select": M * De * 2 + 3 * ET * De * 4 + 32 * M + 12 * ET * N,
         "iou": 2 * 2 * ET * H * W,
     }
 
 
-def run_ours(args, cfg):
+def setup_dist():
     import torch
     import torch.distributed as dist
-
-    from hybridgl_b200 import synth
-    from hybridgl_b200.pipeline import ScoringPath
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,6 +264,109 @@ def run_ours(args, cfg):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+    return world, rank, local, dev, numa
+
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    tf_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if "bf16_tflops_sustained" in peaks
+              else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)")
+    return hbm, src, tf, tf_src
+
+
+PCIE_GEN5_X16_GBS = 63.0      # nominal per direction (32 GT/s x 16 lanes, 128b/130b); ~52-55 GB/s is what pinned cudaMemcpyAsync delivers
+
+
+def time_e2e(path, hosts, max_n, steps, world, dev, barrier, expr_per_step, pipelined=True):
+    """e2e through the public host-buffer API.  pipelined: ScoringPath.run_host_iter (H2D of batch k+1 under the kernels of batch k,
+    one CUDA graph per buffer set); else one blocking run_host call per step."""
+    import torch
+    import torch.distributed as dist
+    seq = [hosts[s % len(hosts)] for s in range(steps)]
+    if pipelined:
+        for _ in path.run_host_iter(seq[:4], max_n, graph=True):
+            pass
+    else:
+        for w in range(2):
+            path.run_host(hosts[w % len(hosts)], max_n)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    if pipelined:
+        for out in path.run_host_iter(seq, max_n, graph=True):
+            pass
+    else:
+        for hb in seq:
+            out = path.run_host(hb, max_n)
+    t1.record()
+    barrier()
+    ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    sec = float(ems.item()) / 1e3
+    h2d = path.h2d_bytes(hosts[0])
+    link = h2d * steps / sec / 1e9
+    del out
+    return {"value": expr_per_step * steps / sec, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": path.d2h_bytes(),
+            "steps": steps, "ms_per_step": sec / steps * 1e3, "link_gbs_per_gpu": round(link, 2),
+            "link_frac_of_pcie_gen5_x16": round(link / PCIE_GEN5_X16_GBS, 3),
+            "api": ("hybridgl_b200.pipeline.ScoringPath.run_host_iter (pinned host tensors in / out; copies of step k+1 overlap the kernels of step k)"
+                    if pipelined else "hybridgl_b200.pipeline.ScoringPath.run_host (pinned host tensors in / out, one blocking call per step)")}
+
+
+def backbone_view(cfg, dev, images=2):
+    """BASELINE.md section 3 'two views': the same path WITH the hybrid CLIP ViT (plain PyTorch, random-init weights of the named
+    architecture, bf16) producing the features that are scored -- one image per call like the reference loop.  Rank 0, N=1 only."""
+    import torch
+    from hybridgl_b200 import ops, synth
+    from hybridgl_b200.backbone import CLIPViTFM
+    name = "ViT-L/14@336px" if cfg["S"] == 336 else "ViT-B/16"
+    model = CLIPViTFM(name, device=dev, dtype=torch.bfloat16)
+    mb = model.last_layer - 1
+    t_path = t_vit = 0.0
+    ev = lambda: torch.cuda.Event(enable_timing=True)      # noqa: E731
+    for i in range(-1, images):                            # image -1: untimed warm-up
+        b = synth.make_batch_device(300 + i, 1, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev, grid=cfg["g"], raw_heat=True)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        bits = ops.pack_masks(b["masks"])
+        blur = ops.gaussian_blur15(b["image"])
+        local, glob = ops.prep_visual_prompts(b["image"], blur, bits, cfg["S"], dtype=torch.bfloat16)
+        e1.record()
+        feats = model(local, glob, b["masks"], masking_block=mb, fusion_mode=cfg["fusion_mode"])
+        e2.record()
+        _, _, score_gem = ops.grid_heat_pool(bits, cfg["w"], cfg["g"], b["heat"], b["dirflag"], b["black"])
+        res = ops.score_select(feats.contiguous(), b["sent"], b["noun"], b["others"], b["other_off"], b["boxes"], b["relaflag"], score_gem)
+        cum = torch.zeros(4, dtype=torch.int64, device=dev)
+        ops.iou_accumulate(bits, b["target"], res["idx_hybrid"], res["idx_final"], cum)
+        e3.record()
+        torch.cuda.synchronize()
+        if i >= 0:
+            t_path += e0.elapsed_time(e1) + e2.elapsed_time(e3); t_vit += e1.elapsed_time(e2)
+    del model
+    torch.cuda.empty_cache()
+    return {"value": images * cfg["n_expr"] / ((t_path + t_vit) / 1e3), "unit": METRIC, "images": images,
+            "path_ms_per_image": round(t_path / images, 3), "vit_ms_per_image": round(t_vit / images, 3),
+            "backbone": f"{name} hybrid forward ({cfg['fusion_mode']}, masking_block={mb}), plain PyTorch bf16, random-init weights",
+            "note": "device-resident inputs, one image per call like the reference loop; end to end the reference's loop is backbone-bound "
+                    "(SURVEY.md section 8(d)); `value` / `e2e` above are the path with features / tokens as inputs, as the north star's I/O contract states"}
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from hybridgl_b200 import synth
+    from hybridgl_b200.pipeline import ScoringPath
+
+    world, rank, local, dev, numa = setup_dist()
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
     path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap)
@@ -275,63 +382,77 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
+    for w in range(max(3, args.warmup)):
         path.run(batches[w % 2], max_n)
     # The step as a CUDA graph (one per device batch): the four-stream stage graph of ScoringPath.run is captured once and
-    # replayed with ONE launch per step; `prep` is bracketed by two event-record nodes inside the graph.
+    # replayed with ONE launch per pass; `prep` is bracketed by two event-record nodes inside the graph.
     graphs = None
-    if args.graph:
+    if not args.no_graph:
         graphs = [path.capture(b, max_n, time_stages=("prep",)) for b in batches]
         for w in range(max(3, args.warmup)):
             graphs[w % 2].replay()
+    # inner repeats: a timed "step" is `inner` passes over alternating batches, sized so that the timed region lasts >= ~0.6 s
+    # whatever --steps is (a 10 ms region measures launch jitter and rank skew, not the path)
+    inner = args.inner
+    if inner <= 0:
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for w in range(8):
+            (graphs[w % 2].replay() if graphs else path.run(batches[w % 2], max_n))
+        c1.record()
+        torch.cuda.synchronize()
+        t_pass = c0.elapsed_time(c1) / 8.0
+        inner_t = torch.tensor([max(1, min(1024, int(600.0 / (max(args.steps, 1) * t_pass)) + 1))], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(inner_t, op=dist.ReduceOp.MAX)
+        inner = int(inner_t.item())
+    passes = args.steps * inner
     path.cum.zero_()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # timed region: only the dominant stage (prep) is bracketed with events -- two records per step instead of twenty, which
+    # timed region: only the dominant stage (prep) is bracketed with events -- two records per pass instead of twenty, which
     # cost ~3 % of the step when every stage is bracketed (profiles/host_overhead.py)
     top_events = []
     top_samples = []
-    pipelined = False
     path.events_only = {"prep"}
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
     if graphs is not None:
         prev = None
-        for s in range(args.steps):
+        for s in range(passes):
             g = graphs[s % 2]
             g.replay()
-            if prev is not None:          # the previous step's pair, read while this step runs (re-stamped only by ITS next replay)
+            if prev is not None and s % 8 == 1:   # a previous pass's pair, read while this pass runs (re-stamped only by ITS next replay)
                 _, e0, e1 = prev.events[0]
                 e1.synchronize()
                 top_samples.append(e0.elapsed_time(e1))
             prev = g
     else:
-        # --pipeline: consecutive steps software-pipelined (ScoringPath.pipelined): each stage chain has its own stream, two buffer
-        # sets alternate, a step only waits for the step before last; the region ends with a full join (sync + barrier)
-        path.pipelined = path.overlap and args.pipeline
-        for s in range(args.steps):
+        for s in range(passes):
             path.events = []
             path.run(batches[s % 2], max_n)
             top_events.append(path.events)
-        path.sync()
-        pipelined = path.pipelined
-        path.pipelined = False
     path.events = None
     path.events_only = None
-    cum = path.cum.clone()
-    if world > 1:
-        dist.all_reduce(cum)              # the path's only collective: IoU accumulators (64 bytes)
     t_end.record()
+    # the path's only collective, timed on its own: all-reduce of the IoU accumulators (32 bytes)
+    cum = path.cum.clone()
+    k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+    k0.record()
+    if world > 1:
+        dist.all_reduce(cum)
+    k1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    ms = torch.tensor([t_start.elapsed_time(t_end), k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    expr_per_step = world * B * cfg["n_expr"]
-    value = expr_per_step * args.steps / (ms_total / 1e3)
+    ms_total, collective_ms = float(ms[0].item()), float(ms[1].item())
+    expr_per_pass = world * B * cfg["n_expr"]
+    value = expr_per_pass * passes / ((ms_total + collective_ms) / 1e3)        # the sweep's one collective is charged to the job
 
     # per-stage durations from event pairs, each pair on the stream its stage runs on
     def stage_avg(all_events):
@@ -344,7 +465,7 @@ def run_ours(args, cfg):
     # every stage bracketed, same overlapped stage graph, right after the timed region (durations UNDER the overlap: the
     # helper-stream chains run concurrently with prep)
     stage_events = []
-    for s in range(min(args.steps, 50)):
+    for s in range(50):
         path.events = []
         path.run(batches[s % 2], max_n)
         stage_events.append(path.events)
@@ -372,15 +493,8 @@ def run_ours(args, cfg):
         barrier()
         ms_serial = s0.elapsed_time(s1) / args.serial_steps
     alone_ms = stage_avg(serial_events)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak_hbm, peak_src, peak_tf, peak_tf_src = load_peaks()
     alg = algorithmic_bytes(cfg, B, 2 if prep_dtype == torch.bfloat16 else 4)
-    world_local_masks = B * cfg["n_masks"]
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -395,42 +509,40 @@ def run_ours(args, cfg):
             if alone_ms.get(k, 0) > 0:
                 a1 = b / (alone_ms[k] * 1e-3) / 1e9
                 kernels[k].update({"ms_alone": round(alone_ms[k], 4), "achieved_gbs_alone": round(a1, 1), "frac_alone": round(a1 / peak_hbm, 4)})
-    if "mask_pool" in kernels:           # the tensor-core stage also gets its flop rate against the measured bf16 peak
-        flop = 2.0 * world_local_masks * cfg["g"] ** 2 * cfg["De"]
-        tf = flop / (kernels["mask_pool"]["ms"] * 1e-3) / 1e12
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        kernels["mask_pool"].update({"algorithmic_flop": flop, "achieved_tflops": round(tf, 2), "frac_tensor": round(tf / peak_tf, 5),
-                                     "tensor_peak_tflops": peak_tf})
+    if "pool_score" in kernels:
+        # the tensor-core stage: algorithmic flops 2*M*L*De against the measured bf16 peak AND against its own ceiling
+        # min(tensor peak, arithmetic intensity x HBM peak) -- at AI ~ 60 flop/B the HBM-limited ceiling is ~1/4 of the tensor peak
+        flop = 2.0 * B * cfg["n_masks"] * cfg["g"] ** 2 * cfg["De"]
+        ai = flop / alg["pool_score"]
+        ceil_tf = min(peak_tf, ai * peak_hbm / 1e3)
+        kk = kernels["pool_score"]
+        kk.update({"algorithmic_flop": flop, "arithmetic_intensity_flop_per_byte": round(ai, 1), "tensor_peak_tflops": peak_tf,
+                   "tensor_peak_source": peak_tf_src, "ceiling_tflops_min_tensor_ai_hbm": round(ceil_tf, 1)})
+        for tag in ("", "_alone"):
+            if "ms" + tag in kk:
+                tf = flop / (kk["ms" + tag] * 1e-3) / 1e12
+                kk.update({"achieved_tflops" + tag: round(tf, 2), "frac_tensor" + tag: round(tf / peak_tf, 5),
+                           "frac_of_ceiling" + tag: round(tf / ceil_tf, 4)})
     top = "prep" if "prep" in kernels else max(kernels, key=lambda k: kernels[k]["ms"])      # the bandwidth-bound bulk of the step
     roofline = {"kernel": f"hgl_{top}", "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak_hbm, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": traffic.get(top), "peak_source": peak_src,
-                "timing": ("CUDA events around the stage on its own stream inside the timed region (the other stages are bracketed in "
-                           "a second pass right after it: kernels{})" +
-                           ("; the side-stream chain (pack, mask grid + heat-map pooling, mask pooling, score/select, IoU) runs "
-                            "concurrently with prep, so `frac` is prep's share of HBM while sharing it; `frac_alone` is the same "
+                "timing": ("CUDA events around the stage on its own stream inside the timed region (event-record nodes of the replayed graph; "
+                           "the other stages are bracketed in a second pass right after it: kernels{})" +
+                           ("; the helper-stream chains (pack, mask grid + heat-map pooling, pooling + scoring, IoU; blur, prep setup; heat-map "
+                            "tables) run concurrently with prep, so `frac` is prep's share of HBM while sharing it; `frac_alone` is the same "
                             "kernel timed alone in the serial pass" if path.overlap else "")),
                 "frac_alone": kernels[top].get("frac_alone"), "achieved_alone": kernels[top].get("achieved_gbs_alone")}
 
-    # ---- e2e: the public API with pinned HOST buffers
-    e2e = None
+    # ---- e2e: the public API with pinned HOST buffers (byte masks: what the reference's call surface receives)
+    e2e = e2e_serial = None
+    hosts = None
     if args.e2e_steps > 0:
-        host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
-        for w in range(2):
-            path.run_host(host[w % 2], max_n)
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for s in range(args.e2e_steps):
-            out = path.run_host(host[s % 2], max_n)
-        t1.record()
-        barrier()
-        ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": expr_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": METRIC,
-               "h2d_bytes_per_step": path.h2d_bytes(host[0]), "d2h_bytes_per_step": path.d2h_bytes(),
-               "steps": args.e2e_steps, "api": "hybridgl_b200.pipeline.ScoringPath.run_host (pinned host tensors in / out)"}
-        del out
+        hosts = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
+        e2e = time_e2e(path, hosts, max_n, args.e2e_steps, world, dev, barrier, expr_per_pass, pipelined=True)
+        e2e_serial = time_e2e(path, hosts, max_n, max(4, args.e2e_steps // 3), world, dev, barrier, expr_per_pass, pipelined=False)
+        e2e["bound"] = (f"host link: {e2e['h2d_bytes_per_step'] / 1e6:.0f} MB of H2D per step ({B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB of it "
+                        "byte masks) against ~0.5 ms of kernels")
+        e2e["serial_run_host"] = {k: e2e_serial[k] for k in ("value", "ms_per_step", "link_gbs_per_gpu")}
 
     # ---- the same workload with the proposals handed over as SAM's uncompressed RLE (amg.py:107-135) instead of byte masks:
     # hgl_rle_to_bits replaces hgl_pack_masks, the H*W-byte masks exist neither on the host nor in HBM.  Reported NEXT TO the
@@ -473,53 +585,116 @@ def run_ours(args, cfg):
         rle_ms = float(rms.item()) / args.rle_steps
         rle_stage = stage_avg(rle_events).get("rle", 0.0)
         rle_bytes = rb[0]["rle_counts"].numel() * 4 + B * cfg["n_masks"] * cfg["h"] * ((cfg["w"] + 31) // 32) * 4
-        rle_info = {"value": expr_per_step / (rle_ms / 1e3), "unit": METRIC, "ms_per_step": rle_ms, "steps": args.rle_steps,
+        rle_info = {"value": expr_per_pass / (rle_ms / 1e3), "unit": METRIC, "ms_per_step": rle_ms, "steps": args.rle_steps,
                     "runs_per_mask": rb[0]["rle_counts"].numel() / max(1, B * cfg["n_masks"]),
                     "rle_to_bits": {"ms": round(rle_stage, 4), "algorithmic_bytes": rle_bytes,
                                     "achieved_gbs": round(rle_bytes / max(rle_stage, 1e-9) / 1e6, 1),
                                     "frac": round(rle_bytes / max(rle_stage, 1e-9) / 1e6 / peak_hbm, 4)},
                     "note": "proposals as SAM uncompressed RLE (SamAutomaticMaskGenerator(output_mode='uncompressed_rle')); "
-                            "results bit-identical to the byte-mask run (tests/test_gpu_parity.py::test_pipeline_rle_input_equals_byte_mask_input)"}
+                            "results bit-identical to the byte-mask run (tests/test_gpu_parity.py::test_bench_workload_parity)"}
+        del rgraphs
         if args.e2e_steps > 0:
             rhost = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in rb]
-            for w in range(2):
-                path.run_host(rhost[w % 2], max_n)
-            barrier()
-            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for s in range(args.e2e_steps):
-                out = path.run_host(rhost[s % 2], max_n)
-            t1.record()
-            barrier()
-            ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-            rle_info["e2e"] = {"value": expr_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": METRIC,
-                               "h2d_bytes_per_step": path.h2d_bytes(rhost[0]), "d2h_bytes_per_step": path.d2h_bytes(),
-                               "steps": args.e2e_steps}
-            del out, rhost
+            rle_info["e2e"] = time_e2e(path, rhost, max_n, args.e2e_steps * 10, world, dev, barrier, expr_per_pass, pipelined=True)
+            rs = time_e2e(path, rhost, max_n, args.e2e_steps * 3, world, dev, barrier, expr_per_pass, pipelined=False)
+            rle_info["e2e"]["serial_run_host"] = {k: rs[k] for k in ("value", "ms_per_step", "link_gbs_per_gpu")}
+            del rhost
         path.cum.copy_(cum_bytes)
+
+    with_backbone = None
+    if rank == 0 and world == 1 and not args.no_backbone_view:
+        try:
+            with_backbone = backbone_view(cfg, dev)
+        except Exception as e:      # a reported view, never the headline: do not lose the line over it
+            with_backbone = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_sample(cfg)
         c = [int(v) for v in cum.tolist()]
+        ms_per_step = (ms_total + collective_ms) / args.steps
         line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if prep_dtype == torch.bfloat16 else "f32", "data": "synthetic",
-                "config": {"workload": workload_name(cfg), "l2": "two alternating batches, masks alone are "
-                           f"{B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
-                           **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-                "clocks": clocks, "host_affinity": numa, "e2e": e2e, "gpu_launches": path.launches_per_run() * args.steps,
-                "launch": ("one CUDA-graph replay per step (ScoringPath.capture)" if graphs is not None else "eager: one host launch per kernel"),
-                "steps_pipelined": (graphs is None and pipelined),
-                "streams": ("2 (heat-map tables, blur and prep on the caller's stream; pack and the post-pack chain on a high-priority side stream)"
-                            if path.overlap else "1"),
-                "ms_per_step_serial": ms_serial,
+                "config": {"workload": workload_name(cfg), **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
+                "inner_repeats": inner, "passes_timed": passes, "ms_per_pass": ms_total / passes, "timed_region_s": ms_total / 1e3,
+                "collective_ms": collective_ms,
+                "collective": "one all-reduce(SUM) of the int64[4] IoU accumulators after the last pass (NCCL), timed on its own and charged to the job",
+                "l2": f"two alternating batches; the byte masks alone are {B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
+                "clocks": clocks, "host_affinity": numa, "e2e": e2e, "e2e_with_backbone": with_backbone,
+                "gpu_launches": path.launches_per_run() * passes,
+                "launch": ("one CUDA-graph replay per pass (ScoringPath.capture)" if graphs is not None else "eager: one host launch per kernel"),
+                "streams": ("4 (prep on the caller's stream; pack -> mask pass -> pooling+scoring -> IoU, blur -> prep setup, heat-map tables on "
+                            "high-priority helper streams)" if path.overlap else "1"),
+                "ms_per_pass_serial": ms_serial,
                 "roofline": roofline, "kernels": kernels, "rle_input": rle_info, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
                         "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sweep_mode(args, cfg):
+    """`--sweep`: BASELINE.json configs[4] -- a PhraseCut-shaped evaluation sweep of `--sweep-images` images sharded by image over the
+    ranks (STRONG scaling: the total is fixed), hybridgl_b200/sweep.py::run_sweep_batches + reduce_counters (one all-reduce of the
+    int64[4] accumulators and one all-gather of the per-expression IU rows at the end; Hybridgl_main.py:52-55, 240-247).
+    The dataset is `pool` distinct synthetic batches of `--images` images visited round-robin (180 GB of HBM cannot hold 4096 frames
+    of byte masks; the generator is not part of the path): batch j of the sweep = pool[j % pool], owned by rank j % world."""
+    import torch
+    import torch.distributed as dist
+
+    from hybridgl_b200 import sweep, synth
+    from hybridgl_b200.pipeline import ScoringPath
+    world, rank, local, dev, numa = setup_dist()
+    B = args.images
+    n_batches = max(1, args.sweep_images // B)
+    pool = [synth.make_batch_device(7000 + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev, grid=cfg["g"], raw_heat=True)
+            for i in range(args.sweep_pool)]
+    max_n = cfg["n_masks"]
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=torch.bfloat16, feature_source=args.features)
+    steps = [path.capture(b, max_n) for b in pool]          # one CUDA graph per pool batch
+    E_b = B * cfg["n_expr"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_sweep():
+        return sweep.run_sweep_batches(n_batches, lambda j: steps[j % len(steps)].replay(), path, E_b)
+
+    for w in range(max(1, min(args.warmup, 2))):
+        one_sweep()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        out = one_sweep()
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sec = float(ms.item()) / 1e3
+    n_expr = n_batches * E_b
+    if rank == 0:
+        line = {"metric": METRIC, "value": n_expr * args.steps / sec, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"PhraseCut-shaped eval sweep: {n_batches * B} images {cfg['h']}x{cfg['w']}, {cfg['n_masks']} masks and "
+                                       f"{cfg['n_expr']} expressions per image, sharded by image over the ranks ({B} images per launch); a step = one whole sweep",
+                           **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
+                "sweep": {"images": n_batches * B, "expressions": n_expr, "pool_batches": len(pool), "cum": out["cum"].tolist(),
+                          "oIoU": out["oIoU"], "mIoU": out["mIoU"], "oIoU_final": out["oIoU_final"], "mIoU_final": out["mIoU_final"],
+                          "collective": "all_reduce(int64[4]) + all_gather of the per-expression IU rows, once per sweep (inside the timed region)"},
+                "clocks": clocks, "host_affinity": numa, "gpu_launches": path.launches_per_run() * ((n_batches + world - 1) // world) * args.steps,
+                "e2e": None, "roofline": None, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -530,6 +705,8 @@ def main():
     cfg = workload_config(args.workload, args.images)
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.sweep:
+        run_sweep_mode(args, cfg)
     else:
         run_ours(args, cfg)
 

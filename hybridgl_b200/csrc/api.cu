@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "hgl_common.cuh"
 
 namespace hgl {
@@ -34,6 +37,27 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+int ensure_dyn_smem(const void* kernel, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return HGL_OK;                      // the default limit needs no opt-in
+  struct Entry { const void* k; int dev; size_t granted; };
+  static std::mutex mu;
+  static std::vector<Entry> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* hit = nullptr;
+  for (auto& e : table)
+    if (e.k == kernel && e.dev == dev) { hit = &e; break; }
+  if (hit && hit->granted >= bytes) return HGL_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu B of shared memory): %s", what, bytes, cudaGetErrorString(e));
+    return HGL_ECUDA;
+  }
+  if (hit) hit->granted = bytes; else table.push_back({kernel, dev, bytes});
+  return HGL_OK;
 }
 
 }  // namespace hgl

@@ -21,9 +21,23 @@ int launch_status(const char* what);   // cudaGetLastError -> HGL_ECUDA / HGL_OK
     }                                          \
   } while (0)
 
+// Tuning hooks (environment variables) exist only in builds with -DHGL_TUNING; the shipped library ignores the environment.
+#ifdef HGL_TUNING
+#include <stdlib.h>
+static inline int tuning_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+static inline bool tuning_flag(const char* name) { return getenv(name) != nullptr; }
+#else
+static inline int tuning_int(const char*, int dflt) { return dflt; }
+static inline bool tuning_flag(const char*) { return false; }
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
+// Opt a kernel in to `bytes` of dynamic shared memory (cudaFuncAttributeMaxDynamicSharedMemorySize) ONCE per (kernel, device)
+// and size: later launches that need no more than what was already granted cost a table lookup, not a driver call.
+// Returns HGL_OK / HGL_ECUDA (error text set).
+int ensure_dyn_smem(const void* kernel, size_t bytes, const char* what);
 
 // ---- device helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
 #pragma unroll
         for (int j = 0; j < kEB; ++j) {
           const float sc = warp_sum(acc[j]), sr = warp_sum(accr[j]);
-          if (lane == 0 && j < ne) {
+          if (lane == 0 && j < ne && (m - n_lo) < p.max_n) {        // a mask beyond the row stride is dropped, never written past its row
             float* o = p.sc.pheat + (((size_t)(eg + j) * p.max_n + (m - n_lo)) * kBands + band) * 2;
             o[0] = sc; o[1] = sr;
           }
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
         p.grid[(size_t)m * gg + t] = a;
       }
     }
-    if (kHeat) {
+    if (kHeat && (m - n_lo) < p.max_n) {
       for (int e = e_lo + lane; e < e_hi; e += 32) {
         const float* o = p.sc.pheat + ((size_t)e * p.max_n + (m - n_lo)) * kBands * 2;
         float sc = 0.f, sr = 0.f;
@@ -693,11 +693,11 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
   const size_t smem = off;
   HGL_REQUIRE(smem <= 220 * 1024, "mask rows pass: frame %dx%d (g=%d) needs %zu B of shared memory", p.H, p.W, p.g, smem);
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
-  if (const char* pv = getenv("HGL_ROWS_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(pv)));     // tuning hook
+  per_sm = std::max(1, std::min(per_sm, tuning_int("HGL_ROWS_CTAS_PER_SM", per_sm)));
   const int ctas = std::min(ceil_div(p.M * kBands, warps), sm_count() * per_sm);
   auto go = [&](auto kern) -> int {
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e2 != cudaSuccess) { set_error("mask rows pass: cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return HGL_ECUDA; }
+    const int rc2 = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, "mask rows pass");
+    if (rc2 != HGL_OK) return rc2;
     kern<<<ctas, kRowsThreads, smem, st>>>(p);
     return launch_status("mask rows pass");
   };
@@ -723,8 +723,8 @@ static int launch_heat_tables(const float* heat, int hh, int hw, float* full, co
   const size_t smem = w128 * 4 * (1 + (size_t)nr_max);
   HGL_REQUIRE(smem <= 200 * 1024, "hgl_heat_pool: W=%d too wide", W);
   auto kern = lr ? heat_prefix_kernel<true> : heat_prefix_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("hgl_heat_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+  int rc0 = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, "hgl_heat_pool(prefix)");
+  if (rc0 != HGL_OK) return rc0;
   kern<<<dim3(ceil_div(H, kPrefRows), E), kPrefWarps * 32, smem, st>>>(heat, dirflag, H, W, ws.Wp, hh, hw, nr_max, ws.cr, ws.rp, ws.rowstat);
   int rc = launch_status("hgl_heat_pool(prefix)");
   if (rc != HGL_OK) return rc;
@@ -873,8 +873,8 @@ extern "C" int hgl_heat_resize_aa(const float* heat_raw, int E, int hh, int hw, 
     const size_t smem = w128 * 4 * (1 + (size_t)nr_max);
     if (smem <= 200 * 1024) {
       auto kern = heat_prefix_kernel<true, true>;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { set_error("hgl_heat_resize_aa: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
+      const int rc0 = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, "hgl_heat_resize_aa");
+      if (rc0 != HGL_OK) return rc0;
       kern<<<dim3(ceil_div(H, kPrefRows), E), kPrefWarps * 32, smem, st>>>(heat_raw, nullptr, H, W, W, hh, hw, nr_max, out, nullptr, nullptr);
       return launch_status("hgl_heat_resize_aa");
     }

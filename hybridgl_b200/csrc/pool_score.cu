@@ -459,13 +459,9 @@ static int pool_score_launch(PoolScoreParams& p, const void* tokens, cudaStream_
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d; D=%d L=%d B=%d)", what, (int)cr, D, L, p.B); return HGL_ECUDA; }
 
-  static int smem_set[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !smem_set[dev]) {                  // once per device: opt in to the full shared-memory carve-out
-    cudaError_t e = cudaFuncSetAttribute(pool_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return HGL_ECUDA; }
-    if (dev >= 0 && dev < 64) smem_set[dev] = 1;
+  {
+    const int rc_s = ensure_dyn_smem(reinterpret_cast<const void*>(pool_score_kernel), smem, what);
+    if (rc_s != HGL_OK) return rc_s;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.NT, p.B, 1);

@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __res
   constexpr int kU = 8;   // independent 16-byte loads in flight per thread
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + (kU - 1) * stride < n16; i += kU * stride) {
+  // The unrolled loop runs only while the WHOLE warp is in range (the test uses the warp's last lane, so it is warp-uniform and
+  // the full-mask shuffle below is well defined); whatever is left goes through the tail loop.
+  const size_t lane = threadIdx.x & 31;
+  for (; (i - lane + 31) + (kU - 1) * stride < n16; i += kU * stride) {
     uint4 v[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) v[u] = ldg_stream(src + i + u * stride);
@@ -100,11 +103,16 @@ __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __res
       if (!(threadIdx.x & 1)) bits[(i + u * stride) >> 1] = h | (o << 16);
     }
   }
-  // tail: n16 is even (W % 32 == 0) and the stride is even, so lane pairs stay together
-  for (; i < n16; i += stride) {
-    const uint32_t h = half_of(ldg_stream(src + i));
-    const uint32_t o = __shfl_xor_sync(__activemask(), h, 1);
-    if (!(threadIdx.x & 1)) bits[i >> 1] = h | (o << 16);
+  // tail: n16 is even (W % 32 == 0) and the stride is even, so lane pairs (2k, 2k+1) enter and leave together; the pair
+  // exchanges through a ballot-derived mask of the lanes that are really here
+  for (; (i - lane) < n16; i += stride) {
+    const bool in = i < n16;
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const uint32_t h = half_of(ldg_stream(src + i));
+      const uint32_t o = __shfl_xor_sync(act, h, 1);
+      if (!(threadIdx.x & 1)) bits[i >> 1] = h | (o << 16);
+    }
   }
 }
 
@@ -588,7 +596,9 @@ extern "C" int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_
     // the kernel only takes a quarter of every SM's thread slots (measured fastest alone, too): kernels of a concurrent stream (blur, prep setup, heat-map
     // tables in the batched pipeline) then run beside it instead of queueing behind a grid that fills the machine.
     int per_sm = 2;
-    if (const char* pv = getenv("HGL_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(pv)));     // tuning hook
+#ifdef HGL_TUNING
+    if (const char* pv = getenv("HGL_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(pv)));
+#endif
     const int blocks = (int)std::min<size_t>((n16 + 256 * 8 - 1) / (256 * 8), (size_t)sm_count() * per_sm);
     pack_masks_flat_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const uint4*>(masks), n16, bits);
   } else {
@@ -667,7 +677,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   const int gh = 32 / gw, ppr = G / gw;
   // 1-D bulk copies need 16-byte aligned masks (H * WW % 4 == 0 and an aligned base; a band's first row may sit anywhere,
   // the copy then starts up to 3 words early); otherwise cooperative loads
-  const bool tma = (((size_t)H * p.WW) % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !getenv("HGL_PREP_NO_TMA");
+  const bool tma = (((size_t)H * p.WW) % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && !tuning_flag("HGL_PREP_NO_TMA");
   int cw = 1;
   for (int d = 1; d <= (tma ? 7 : 8); ++d) if (ppr % d == 0) cw = d;        // kTMA: one more warp (the producer) joins the CTA
   p.gw = gw; p.gh = gh; p.cw = cw; p.nbx = ppr / cw; p.strip = 0;
@@ -676,7 +686,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   // lines; measured 6.2 TB/s of pure stores against 5.1 TB/s for 2-D patches of 64-byte row pieces).  The last warp may
   // have idle lanes when R * G is not a multiple of 32.
   const int max_cons = tma ? kPrepThreads - 32 : kPrepThreads;
-  if (G <= max_cons && !getenv("HGL_PREP_PATCH")) {
+  if (G <= max_cons && !tuning_flag("HGL_PREP_PATCH")) {
     const int R = max_cons / G;
     p.strip = G; p.gh = R; p.cw = ceil_div(R * G, 32); p.nbx = 1; p.gw = 1;
   }
@@ -694,8 +704,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   const size_t fixed_smem = 64 + (size_t)cw * kPrepWarpBytes + 16;
   const size_t stage_budget = fixed_smem + 24 * 1024 <= 112 * 1024 ? 112 * 1024 - fixed_smem      // two CTAs per SM
                                                                      : (fixed_smem < 200 * 1024 ? 224 * 1024 - fixed_smem : 0);
-  int kPrepSub = kPrepSubDefault;
-  if (const char* sv = getenv("HGL_PREP_SUB")) kPrepSub = std::max(1, std::min(kPrepMaxSub, atoi(sv)));
+  int kPrepSub = std::max(1, std::min(kPrepMaxSub, tuning_int("HGL_PREP_SUB", kPrepSubDefault)));
   while (kPrepSub > 1 && (size_t)kPrepStages * kPrepSub * per_mask_bytes > std::min<size_t>(stage_budget, 96 * 1024)) kPrepSub /= 2;
   p.sub = kPrepSub;
   HGL_REQUIRE((size_t)kPrepStages * kPrepSub * per_mask_bytes <= stage_budget, "hgl_prep: frame %dx%d (S=%d) too large for the shared-memory stages",
@@ -714,16 +723,18 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
       if (eff > best) { best = eff; gz = z; }
     }
   }
-  if (const char* ov = getenv("HGL_PREP_GZ")) gz = std::max(1, atoi(ov));         // tuning hook
+  gz = std::max(1, tuning_int("HGL_PREP_GZ", gz));
   p.debug = 0;
-  p.flush_every = kPrepSub;
-  if (const char* fv = getenv("HGL_PREP_FLUSH")) p.flush_every = std::max(1, atoi(fv));                 // tuning hook
-  if (const char* dv = getenv("HGL_PREP_DEBUG")) p.debug = atoi(dv);              // profiling only: results are wrong when set
+  p.flush_every = std::max(1, tuning_int("HGL_PREP_FLUSH", kPrepSub));
+#ifdef HGL_TUNING
+  p.debug = tuning_int("HGL_PREP_DEBUG", 0);       // profiling builds only (results are wrong when set): never in the shipped library
+#endif
   dim3 grid(gx, B, gz);
   HGL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "hgl_prep: batch too large for one launch (B=%d, max_n=%d)", B, max_n);
+  int smem_rc = HGL_OK;
   auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>(p);
+    smem_rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, "hgl_prep(main)");
+    if (smem_rc == HGL_OK) kern<<<grid, threads, smem, st>>>(p);
   };
   HGL_REQUIRE(per_image <= 65535 * gz, "hgl_prep: more than 65535 masks of one image per CTA span");
   const bool nw = p.narrow != 0;
@@ -735,5 +746,6 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
     if (nw) { if (tma) launch(prep_main_kernel<false, kPrepPx, true, true>); else launch(prep_main_kernel<false, kPrepPx, false, true>); }
     else { if (tma) launch(prep_main_kernel<false, kPrepPx, true, false>); else launch(prep_main_kernel<false, kPrepPx, false, false>); }
   }
+  if (smem_rc != HGL_OK) return smem_rc;
   return launch_status("hgl_prep(main)");
 }

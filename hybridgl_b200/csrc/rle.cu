@@ -206,9 +206,10 @@ extern "C" int hgl_rle_to_bits(const int32_t* counts, const int32_t* rle_off, in
   int HPW, XS, RS;
   size_t smem;
   HGL_REQUIRE(rle_geometry(H, W, &HPW, &XS, &RS, &smem) == HGL_OK, "hgl_rle_to_bits: frame height %d too large", H);
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(rle_to_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
-    return launch_status("hgl_rle_to_bits(attr)");
+  {
+    const int rc0 = ensure_dyn_smem(reinterpret_cast<const void*>(rle_to_bits_kernel), smem, "hgl_rle_to_bits");
+    if (rc0 != HGL_OK) return rc0;
+  }
   const int WW = (W + 31) / 32;
   const int strips = ceil_div(W, XS);
   rle_to_bits_kernel<<<dim3(M, strips), kRleThreads, smem, (cudaStream_t)stream>>>(counts, rle_off, H, W, WW, HPW, XS, RS, bits);

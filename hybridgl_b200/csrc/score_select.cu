@@ -165,13 +165,9 @@ extern "C" int hgl_score_select(const void* feat, int feat_dtype, const float* s
   p.CS = std::max(1, std::min(8, ceil_div(std::max(per_image, 1), 16)));       // >= 2 rows per warp before another CTA pays off
   const size_t smem = ((size_t)2 * kEG * De + 2 * kEG + (size_t)2 * kEG * max_n) * 4 + (size_t)kScoreWarps * 9 * 4 + 16;
   HGL_REQUIRE(smem <= 227 * 1024, "hgl_score_select: De=%d max_n=%d needs %zu B of shared memory", De, max_n, smem);
-  static int smem_set[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !smem_set[dev]) {                  // once per device
-    cudaError_t e = cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("hgl_score_select: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
-    if (dev >= 0 && dev < 64) smem_set[dev] = 1;
+  {
+    const int rc_s = ensure_dyn_smem(reinterpret_cast<const void*>(score_select_kernel), smem, "hgl_score_select");
+    if (rc_s != HGL_OK) return rc_s;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.CS, B, 1);

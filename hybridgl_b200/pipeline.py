@@ -11,7 +11,6 @@ buffers, streams and the order of launches.  Host language stays Python like the
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, Optional
 
 import torch
@@ -47,8 +46,6 @@ class ScoringPath:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.cum = torch.zeros(4, dtype=torch.int64, device=self.device)     # cum_I, cum_U, cum_I_final, cum_U_final
         self._buf: Dict[str, torch.Tensor] = {}
-        self._dev_in: Dict[str, torch.Tensor] = {}
-        self._host_out: Dict[str, torch.Tensor] = {}
         self.events = None            # optional per-stage CUDA event pairs (bench.py): [(stage, start, end)]
         self.events_only = None       # optional set of stage names to bracket (None = every stage)
         self.overlap = overlap        # fork the post-pack chain onto a high-priority side stream (see run())
@@ -56,24 +53,32 @@ class ScoringPath:
         self._pre: Optional[torch.cuda.Stream] = None
         self._tab: Optional[torch.cuda.Stream] = None
         self._capturing = False
-        # software pipeline across steps (see run()): two buffer sets, no join at the end of a step
-        self.pipelined = False
-        self.rows_first = bool(int(os.environ.get("HGL_ROWS_FIRST", "0")))      # tuning hook: prep waits for the mask pass
-        self._pk: Optional[torch.cuda.Stream] = None
-        self._pm: Optional[torch.cuda.Stream] = None
-        self._step = 0
-        self._slot = 0
-        self._done = [None, None]
+        self._checked = set()         # (mask_off ptr, version, max_n) triples whose per-image mask counts were validated
+        self._copy: Optional[torch.cuda.Stream] = None       # H2D stream of run_host_iter
+        self._slots: Dict[int, Dict[str, torch.Tensor]] = {}  # run_host / run_host_iter: device input + pinned output buffer sets
 
     # ------------------------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype) -> torch.Tensor:
-        if self.pipelined:
-            name = f"{name}#{self._slot}"          # two buffer sets: step k+1 never writes what step k still reads
         t = self._buf.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
             self._buf[name] = t
         return t
+
+    def _check_max_n(self, mask_off: torch.Tensor, max_n: int, host_off: Optional[torch.Tensor] = None) -> None:
+        """max_n is the row stride of every [E, max_n] result and the per-image bound of every kernel: an image with more masks
+        would silently lose its tail (the kernels clamp), so reject it here.  Checked once per offsets tensor (one small
+        device->host read the first time a device-resident offsets tensor is seen; free when the host copy is at hand)."""
+        key = (mask_off.data_ptr(), mask_off._version, int(max_n))
+        if key in self._checked or self._capturing:
+            return
+        src = host_off if host_off is not None else mask_off
+        worst = int((src[1:] - src[:-1]).max()) if src.numel() > 1 else 0
+        if worst > max_n:
+            raise ValueError(f"max_n={max_n} but an image of this batch has {worst} masks")
+        if len(self._checked) > 64:
+            self._checked.clear()
+        self._checked.add(key)
 
     class _Span:
         """Brackets one stage with CUDA events on the stream it is launched on (bench.py reads them)."""
@@ -119,39 +124,20 @@ class ScoringPath:
         M = batch["rle_off"].numel() - 1 if rle else masks.shape[0]
         moff, eoff = batch["mask_off"], batch["expr_off"]
         lib = ops._lib.load()
+        self._check_max_n(moff, max_n)
         main = torch.cuda.current_stream()
-        side = pre = tab = pk = pm = main
-        pipelined = self.overlap and self.pipelined and not self._capturing
+        side = pre = tab = main
         if self.overlap:
-            if self._side is None:
-                pr = lambda name, d: int(os.environ.get(name, str(d)))      # noqa: E731  (tuning hooks; defaults = the bench)
-                self._side = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_SIDE", -1))
-                self._pre = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_PRE", -1))
-                self._tab = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_TAB", -1))
-                self._pk = torch.cuda.Stream(device=self.device, priority=pr("HGL_P_PACK", -1))
-                self._pm = torch.cuda.Stream(device=self.device)
-                self._own_pack_stream = bool(pr("HGL_PACK_STREAM", 0))
+            if self._side is None:      # helper streams at high priority: their small kernels take SM slots as prep CTAs retire
+                self._side = torch.cuda.Stream(device=self.device, priority=-1)
+                self._pre = torch.cuda.Stream(device=self.device, priority=-1)
+                self._tab = torch.cuda.Stream(device=self.device, priority=-1)
             side, pre, tab = self._side, self._pre, self._tab
-            pk, pm = (self._pk if self._own_pack_stream else side), main
-            if pipelined:
-                # Steps overlap: every stage chain has its own stream (FIFO across steps), the caller's stream only marks
-                # "inputs ready", nothing joins at the end of a step (sync() / res["done"] do), and a step reuses the buffer
-                # set of the step before last only after that step has completed.
-                pk, pm = self._pk, self._pm
-                self._slot = self._step % 2
-                self._step += 1
-                ev_in = torch.cuda.Event()
-                ev_in.record(main)
-                for s_ in (pk, side, pre, tab, pm):
-                    s_.wait_event(ev_in)
-                    for ev in (self._done[self._slot] or ()):
-                        s_.wait_event(ev)
-            else:
-                for s_ in {side, pre, tab, pk}:
-                    s_.wait_stream(main)
+            for s_ in (side, pre, tab):
+                s_.wait_stream(main)
 
         # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
-        with torch.cuda.stream(pk):
+        with torch.cuda.stream(side):
             bits = self._get("bits", (M, H, (W + 31) // 32), torch.int32)
             if rle:
                 with self._span("rle"):
@@ -198,8 +184,6 @@ class ScoringPath:
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
             feats = features if features is not None else batch.get("features")
-            if pk is not side:
-                side.wait_event(ev_pack)
             if ev_tables is not None:
                 side.wait_event(ev_tables)
             with self._span("grid_heat_pool"):
@@ -213,24 +197,13 @@ class ScoringPath:
                         heat = ops.heat_resize_aa(heat, H, W, out=self._get("heat_full", (E, H, W), torch.float32))
                     grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
                     score_gem = ops.heat_pool(heat, batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
-            ev_rows = None
-            if self.overlap and self.rows_first:
-                ev_rows = torch.cuda.Event()
-                ev_rows.record()
 
         # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
-        with torch.cuda.stream(pm):
-            if ev_pack is not None:
-                pm.wait_event(ev_pack)
-                pm.wait_event(ev_setup)
-                if ev_rows is not None:
-                    pm.wait_event(ev_rows)
-            with self._span("prep"):
-                ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
-            ev_pm = None
-            if pipelined:
-                ev_pm = torch.cuda.Event()
-                ev_pm.record()
+        if ev_pack is not None:
+            main.wait_event(ev_pack)
+            main.wait_event(ev_setup)
+        with self._span("prep"):
+            ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
 
         # ---- chain S, last part: mask pooling -> score/select -> IoU (small kernels, in the shadow of the prep writes)
         with torch.cuda.stream(side):
@@ -247,27 +220,11 @@ class ScoringPath:
                                            batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)
             with self._span("iou"):
                 iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
-            ev_side = None
-            if pipelined:
-                ev_side = torch.cuda.Event()
-                ev_side.record()
-        if pipelined:
-            if ev_tables is None:          # (split off: the table stream did nothing)
-                pass
-            self._done[self._slot] = (ev_pm, ev_side)
-            res["done"] = (ev_pm, ev_side)
-        elif self.overlap:
+        if self.overlap:
             main.wait_stream(side)
             main.wait_stream(tab)          # (already ordered before the mask pass; keeps the join explicit when split is off)
         res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
         return res
-
-    def sync(self) -> None:
-        """Pipelined mode: make the caller's stream wait for every step enqueued so far (results, IoU counters)."""
-        main = torch.cuda.current_stream()
-        for d in self._done:
-            for ev in (d or ()):
-                main.wait_event(ev)
 
     def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None) -> "GraphStep":
         """One step as a CUDA graph: the whole stage graph of run() (four streams, ~12 kernels, memsets, fork / join events) is
@@ -310,35 +267,114 @@ class ScoringPath:
             keys = keys + ("rle_counts", "rle_off")
         return tuple(k for k in keys if k not in skip)
 
-    def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:
-        """End-to-end call with HOST buffers (pinned): H2D of every input, the kernels, D2H of the results,
-        then a stream synchronise.  This is what bench.py times as `e2e`."""
+    # ---- host-buffer API ---------------------------------------------------------------------------------------------
+    def _slot_buffers(self, slot: int, host_batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Device input buffers of one slot, (re)allocated when a shape changes (which also drops the slot's captured graph)."""
+        st = self._slots.setdefault(slot, {"in": {}, "out": {}, "graph": None})
         for k in self.input_keys(host_batch):
             src = host_batch[k]
-            dst = self._dev_in.get(k)
+            dst = st["in"].get(k)
             if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
-                dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
-                self._dev_in[k] = dst
-            dst.copy_(src, non_blocking=True)
-        dev_in = {k: self._dev_in[k] for k in self.input_keys(host_batch)}
-        res = self.run(dev_in, max_n)
+                st["in"][k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                st["graph"] = None
+        for k in [k for k in st["in"] if k not in self.input_keys(host_batch)]:
+            del st["in"][k]
+            st["graph"] = None
+        return st
+
+    def _h2d(self, st, host_batch) -> None:
+        for k, dst in st["in"].items():
+            dst.copy_(host_batch[k], non_blocking=True)
+
+    def _d2h(self, st, res) -> Dict[str, torch.Tensor]:
         out = {}
         for k in OUTPUT_KEYS:
             src = res[k]
-            dst = self._host_out.get(k)
+            dst = st["out"].get(k)
             if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
                 dst = torch.empty(src.shape, dtype=src.dtype).pin_memory()
-                self._host_out[k] = dst
+                st["out"][k] = dst
             dst.copy_(src, non_blocking=True)
             out[k] = dst
+        return out
+
+    def run_host(self, host_batch: Dict[str, torch.Tensor], max_n: int) -> Dict[str, torch.Tensor]:
+        """End-to-end call with HOST buffers (pinned): H2D of every input, the kernels, D2H of the results, then a stream
+        synchronise.  One batch at a time, nothing overlaps; run_host_iter() is the pipelined form of the same call."""
+        st = self._slot_buffers(0, host_batch)
+        self._check_max_n(st["in"]["mask_off"], max_n, host_batch["mask_off"])
+        self._h2d(st, host_batch)
+        out = self._d2h(st, self.run(st["in"], max_n))
         torch.cuda.current_stream().synchronize()
         return out
+
+    def run_host_iter(self, host_batches, max_n: int, depth: int = 2, graph: bool = False):
+        """Generator over an iterable of pinned host batches; yields the pinned host result dict of every batch, in order.
+
+        Software pipeline of `depth` buffer sets: the H2D copies of batch k+1 run on a copy stream under the kernels of batch k,
+        whose (small) D2H copies are enqueued right behind its kernels and awaited only while batch k+1 is already running.
+        A yielded dict is overwritten `depth` batches later.  graph=True replays the step from one CUDA graph per buffer set
+        (ScoringPath.capture) -- the per-step host work drops from ~25 launches to one; tensor shapes must then repeat."""
+        main = torch.cuda.current_stream()
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+        copy = self._copy
+        done: Dict[int, torch.cuda.Event] = {}
+
+        def stage_in(k, hb):
+            st = self._slot_buffers(k % depth, hb)
+            self._check_max_n(st["in"]["mask_off"], max_n, hb["mask_off"])
+            if (k % depth) in done:
+                copy.wait_event(done[k % depth])      # the step that last read this buffer set has finished
+            else:
+                copy.wait_stream(main)
+            with torch.cuda.stream(copy):
+                self._h2d(st, hb)
+                ev = torch.cuda.Event()
+                ev.record()
+            return st, ev
+
+        it = iter(host_batches)
+        hb = next(it, None)
+        if hb is None:
+            return
+        nxt = stage_in(0, hb)
+        pending = []
+        k = 0
+        while nxt is not None:
+            st, ev_in = nxt
+            hb = next(it, None)
+            nxt = stage_in(k + 1, hb) if hb is not None else None      # queue the next batch's copies before this batch's kernels
+            main.wait_event(ev_in)
+            if graph:
+                if st["graph"] is None:
+                    main.synchronize()                                  # capture() runs the step once eagerly on these inputs
+                    cum0 = self.cum.clone()
+                    st["graph"] = self.capture(st["in"], max_n)
+                    self.cum.copy_(cum0)
+                res = st["graph"].replay()
+            else:
+                res = self.run(st["in"], max_n)
+            out = self._d2h(st, res)
+            ev_out = torch.cuda.Event()
+            ev_out.record()
+            done[k % depth] = ev_out
+            pending.append((ev_out, out))
+            if len(pending) >= depth:
+                ev, o = pending.pop(0)
+                ev.synchronize()
+                yield o
+            k += 1
+        for ev, o in pending:
+            ev.synchronize()
+            yield o
 
     def h2d_bytes(self, host_batch: Dict[str, torch.Tensor]) -> int:
         return sum(host_batch[k].numel() * host_batch[k].element_size() for k in self.input_keys(host_batch))
 
     def d2h_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self._host_out.values())
+        st = self._slots.get(0)
+        return sum(t.numel() * t.element_size() for t in st["out"].values()) if st else 0
 
 
 class GraphStep:

@@ -98,3 +98,23 @@ def run_sweep(n_images: int, make_batch: Callable[[Sequence[int]], Tuple[Dict[st
     iu = torch.cat(rows) if rows else torch.zeros((0, 4), dtype=torch.int64, device=dev)
     eid = torch.cat(ids) if ids else torch.zeros((0,), dtype=torch.int64, device=dev)
     return reduce_counters(path.cum, iu, eid, group)
+
+
+def run_sweep_batches(n_batches: int, run_batch: Callable[[int], Dict[str, torch.Tensor]], path, exprs_per_batch: int,
+                      group=None) -> Dict[str, object]:
+    """The sweep over a dataset that is already cut into batches of images (bench.py --sweep): batch j belongs to rank
+    j % world; run_batch(j) runs the path on it (ScoringPath.run or a captured GraphStep.replay) and returns its result dict,
+    whose `iu` rows are the batch's `exprs_per_batch` expressions in dataset order.  Same reduction as run_sweep."""
+    rank, world = _world(group)
+    mine = shard_indices(n_batches, rank, world)
+    path.cum.zero_()
+    dev = path.cum.device
+    rows, ids = [], []
+    local_ids = torch.arange(exprs_per_batch, dtype=torch.int64, device=dev)
+    for j in mine:
+        res = run_batch(j)
+        rows.append(res["iu"].clone())          # a replayed graph overwrites its result tensors
+        ids.append(local_ids + j * exprs_per_batch)
+    iu = torch.cat(rows) if rows else torch.zeros((0, 4), dtype=torch.int64, device=dev)
+    eid = torch.cat(ids) if ids else torch.zeros((0,), dtype=torch.int64, device=dev)
+    return reduce_counters(path.cum, iu, eid, group)

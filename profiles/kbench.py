@@ -52,7 +52,7 @@ B = int(os.environ.get("KB_IMAGES", "16"))
 H, W, N, E, S, g, De = cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["S"], cfg["g"], cfg["De"]
 batch = synth.make_batch_device(1234, B, H, W, N, E, De, device="cuda", grid=g)
 counts, roff = synth.masks_to_rle_device(batch["masks"])
-path = ScoringPath(size=S, grid=g, feature_source="tokens", overlap=False)
+path = ScoringPath(size=S, grid=g, feature_source="tokens", overlap=False, keep_features=True)
 res = path.run(batch, N)
 torch.cuda.synchronize()
 bits, grid, feats, sg = res["bits"].clone(), res["grid"], res["features"], res["score_gem"]
@@ -77,6 +77,9 @@ stages = {
                        M * H * WW * 4 + M * g * g * 4 + 2 * B * E * H * W * 4 + B * E * N * 4),
     "mask_pool": (lambda: ops.mask_pool(grid, batch["tokens"], moff, N, normalize=True, dtype=torch.bfloat16),
                   M * g * g * 4 + B * g * g * De * 2 + M * De * 2),
+    "pool_score": (lambda: ops.pool_score_select(grid, batch["tokens"], batch["sent"], batch["noun"], batch["others"], batch["other_off"],
+                                                 batch["boxes"], batch["relaflag"], sg, moff, eoff, N),
+                   M * g * g * 4 + B * g * g * De * 2 + 3 * B * E * De * 4 + 32 * M + 12 * B * E * N),
     "score_select": (lambda: ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
                                               batch["relaflag"], sg, moff, eoff, N),
                      M * De * 2 + 3 * B * E * De * 4 + 32 * M + 12 * B * E * N),

@@ -720,10 +720,10 @@ def test_captured_step_equals_eager_step(ops):
     from hybridgl_b200.pipeline import ScoringPath
     B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
     batch = synth.make_batch_device(78, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True)
-    eager = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    eager = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens", keep_features=True)
     ref = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in eager.run(batch, n).items()}
     torch.cuda.synchronize()
-    path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens", keep_features=True)
     step = path.capture(batch, n, time_stages=("prep",))
     assert path.cum.tolist() == [0, 0, 0, 0]                         # neither the warm-up nor the capture counts
     for r in range(3):
@@ -736,41 +736,50 @@ def test_captured_step_equals_eager_step(ops):
     assert name == "prep" and e0.elapsed_time(e1) > 0.0
 
 
-def test_pipelined_steps_equal_joined_steps(ops):
-    """ScoringPath.pipelined: consecutive steps overlap (own stream per stage chain, two buffer sets, no join per step);
-    every step's results and the IoU counters are the same bits as with one joined step at a time."""
-    from hybridgl_b200.pipeline import ScoringPath
+@pytest.mark.parametrize("graph", [False, True])
+def test_run_host_iter_equals_run_host(ops, graph):
+    """ScoringPath.run_host_iter (H2D of batch k+1 under the kernels of batch k, D2H awaited one batch late, optionally one CUDA
+    graph per buffer set): every batch's results and the IoU counters are the bits of the serial run_host calls."""
+    from hybridgl_b200.pipeline import OUTPUT_KEYS, ScoringPath
     B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
-    batches = [synth.make_batch_device(90 + i, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True) for i in range(3)]
-    keys = ("local_imgs", "global_imgs", "grid", "area", "score_clip", "score_gem", "idx_hybrid", "idx_final", "iu", "features")
+    hosts = [{k: v.cpu().pin_memory() for k, v in synth.make_batch_device(90 + i, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True).items()}
+             for i in range(3)]
+    seq = [hosts[s % 3] for s in range(7)]
     ref_path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
-    refs = []
-    for s in range(7):
-        r = ref_path.run(batches[s % 3], n)
-        refs.append({k: r[k].clone() for k in keys})
-    torch.cuda.synchronize()
+    refs = [{k: v.clone() for k, v in ref_path.run_host(hb, n).items()} for hb in seq]
     path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
-    path.pipelined = True
-    outs = []
-    for s in range(7):
-        r = path.run(batches[s % 3], n)
-        for ev in r["done"]:
-            torch.cuda.current_stream().wait_event(ev)
-        outs.append({k: r[k].clone() for k in keys})          # cloned on the caller's stream after the step's done events
-    path.sync()
+    outs = [{k: v.clone() for k, v in o.items()} for o in path.run_host_iter(seq, n, depth=2, graph=graph)]
     torch.cuda.synchronize()
+    assert len(outs) == len(refs) == 7
     for s in range(7):
-        for k in keys:
+        for k in OUTPUT_KEYS:
             assert torch.equal(outs[s][k], refs[s][k]), (s, k)
     assert path.cum.tolist() == ref_path.cum.tolist()
-    # and without touching the results in between (the bench's sweep form): only the counters matter
-    path2 = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
-    path2.pipelined = True
-    for s in range(7):
-        path2.run(batches[s % 3], n)
-    path2.sync()
+    assert list(path.run_host_iter([], n)) == []
+
+
+def test_max_n_smaller_than_an_image_is_rejected(ops):
+    """max_n is the row stride of the [E, max_n] results: a batch holding an image with more masks is refused by the pipeline, and
+    the kernels themselves clamp (no write past a row) when called directly."""
+    from hybridgl_b200.pipeline import ScoringPath
+    B, h, w, n, e, de, g = 2, 96, 128, 9, 2, 64, 6
+    batch = synth.make_batch_device(5, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True)
+    batch["mask_off"] = cu(np.array([0, 12, 18], np.int32))
+    path = ScoringPath(size=32, grid=g, feature_source="tokens")
+    with pytest.raises(ValueError, match="max_n"):
+        path.run(batch, 9)
+    res = path.run(batch, 12)
     torch.cuda.synchronize()
-    assert path2.cum.tolist() == ref_path.cum.tolist()
+    # direct kernel calls with a too-small max_n: rows stay inside [E, max_n] (guard cells after the buffer are untouched)
+    bits = ops.pack_masks(batch["masks"])
+    lib = ops._lib.load()
+    E = batch["sent"].shape[0]
+    ws = torch.empty((lib.hgl_grid_heat_pool_raw_workspace_bytes(B, 18, E, h, w, g, 9, 28, 37),), dtype=torch.uint8, device=DEV)
+    ops.heat_tables(batch["heat"], batch["dirflag"], h, w, ws)
+    grid, area, sg = ops.grid_heat_pool_rows(bits, w, g, batch["heat"].shape, batch["black"], batch["mask_off"], batch["expr_off"], 9, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(sg[:e, :9], res["score_gem"][:e, :9])          # image 0: its first 9 masks, nothing spilled into the next rows
+    assert torch.equal(sg[e:, :6], res["score_gem"][e:, :6])
 
 
 # ------------------------------------------------------------------------------------------------ the bench workload itself

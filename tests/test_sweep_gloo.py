@@ -92,3 +92,54 @@ def test_shard_indices_cover_and_partition():
 def test_report_handles_empty_union():
     rep = sweep.report(torch.tensor([5, 10, 0, 0]), torch.tensor([[5, 10, 0, 0]]))
     assert rep["oIoU"] == 50.0 and rep["mIoU"] == 50.0 and np.isnan(rep["oIoU_final"]) and rep["mIoU_final"] == 0.0
+
+
+class _StubPath:
+    """Stands in for pipeline.ScoringPath on the CPU: the sweep driver only touches `.cum`."""
+    def __init__(self):
+        self.cum = torch.zeros(4, dtype=torch.int64)
+
+
+def _batch_rows(j):
+    """Deterministic integer IU rows of 'batch' j (3 expressions), as ScoringPath.run would return them."""
+    rng = np.random.default_rng(40 + j)
+    u = rng.integers(1, 1000, (3, 2))
+    i = (u * rng.random((3, 2))).astype(np.int64)
+    return np.stack([i[:, 0], u[:, 0], i[:, 1], u[:, 1]], 1).astype(np.int64)
+
+
+def _worker_batches(rank, world, port, q, n_batches):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        path = _StubPath()
+
+        def run_batch(j):
+            rows = torch.from_numpy(_batch_rows(j))
+            path.cum += rows.sum(0)                      # what hgl_iou does on the device
+            return {"iu": rows}
+        out = sweep.run_sweep_batches(n_batches, run_batch, path, 3)
+        q.put((rank, out["cum"].tolist(), out["iu"].tolist(), out["expr_ids"].tolist(), out["mIoU"], out["mIoU_final"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_batch_sharded_sweep_matches_single_process(world):
+    """bench.py --sweep (strong scaling): batches owned round-robin by the ranks, one all-reduce + all-gather at the end."""
+    n_batches = 5
+    rows_ref = np.concatenate([_batch_rows(j) for j in range(n_batches)])
+    ref = sweep.report(torch.from_numpy(rows_ref.sum(0)), torch.from_numpy(rows_ref))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batches, args=(r, world, port, q, n_batches)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, cum, iu, ids, m, mf in results:
+        assert cum == rows_ref.sum(0).tolist() and iu == rows_ref.tolist() and ids == list(range(3 * n_batches))
+        assert (m, mf) == (ref["mIoU"], ref["mIoU_final"])
