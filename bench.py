@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="strong-scaling evaluation sweep (BASELINE.json configs[4]; use with --workload 5)")
     ap.add_argument("--sweep-images", type=int, default=4096)
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
+    ap.add_argument("--chunks", type=int, default=2, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
                     help="tokens: pool dense patch tokens under the grid masks on the tensor cores (hgl_mask_pool) and score those; "
@@ -369,7 +370,8 @@ def run_ours(args, cfg):
     world, rank, local, dev, numa = setup_dist()
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
-    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap)
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap,
+                       chunks=args.chunks)
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
     batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
                                          grid=cfg["g"], raw_heat=True)
@@ -425,10 +427,9 @@ def run_ours(args, cfg):
         for s in range(passes):
             g = graphs[s % 2]
             g.replay()
-            if prev is not None and s % 8 == 1:   # a previous pass's pair, read while this pass runs (re-stamped only by ITS next replay)
-                _, e0, e1 = prev.events[0]
-                e1.synchronize()
-                top_samples.append(e0.elapsed_time(e1))
+            if prev is not None and s % 8 == 1:   # a previous pass's pairs (one per image group), read while this pass runs
+                prev.events[-1][2].synchronize()  # (re-stamped only by ITS next replay)
+                top_samples.append(sum(e0.elapsed_time(e1) for _, e0, e1 in prev.events))
             prev = g
     else:
         for s in range(passes):
@@ -458,41 +459,78 @@ def run_ours(args, cfg):
     def stage_avg(all_events):
         dur = {}
         for evs in all_events:
+            d1 = {}
             for name, e0, e1 in evs:
-                dur.setdefault(name, []).append(e0.elapsed_time(e1))
+                if name != "t0":
+                    d1[name] = d1.get(name, 0.0) + e0.elapsed_time(e1)      # one launch per image group: summed per pass
+            for name, v in d1.items():
+                dur.setdefault(name, []).append(v)
         return {k: sum(v) / len(v) for k, v in dur.items()}
     top_ms = stage_avg(top_events) if graphs is None else {"prep": sum(top_samples) / max(1, len(top_samples))}
     # every stage bracketed, same overlapped stage graph, right after the timed region (durations UNDER the overlap: the
-    # helper-stream chains run concurrently with prep)
-    stage_events = []
-    for s in range(50):
-        path.events = []
-        path.run(batches[s % 2], max_n)
-        stage_events.append(path.events)
-    path.events = None
-    barrier()
-    avg_ms = stage_avg(stage_events)
+    # helper-stream chains run concurrently with prep).  The brackets are event-record NODES of a captured graph, so a small
+    # kernel's duration is its device time, not the host's launch latency (an eager pass cannot resolve a 10 us kernel).
+    ALL = ("t0", "pack", "rle", "blur", "prep_setup", "heat_tables", "grid_heat_pool", "prep", "pool_score", "score_select", "iou")
+    timelines = {}
+
+    def staged_pass(reps, tag):
+        """-> {stage: mean ms}; also records timelines[tag] = {stage: [start, end]} in ms from the start of the pass."""
+        dur, span = {}, {}
+
+        def take(evs):
+            # a stage is launched once per image group: its duration is the sum over the groups, its span first start .. last end
+            t0 = [e for e in evs if e[0] == "t0"][0][1]
+            d1, s1 = {}, {}
+            for name, e0, e1 in evs:
+                if name == "t0":
+                    continue
+                d1[name] = d1.get(name, 0.0) + e0.elapsed_time(e1)
+                a, b_ = t0.elapsed_time(e0), t0.elapsed_time(e1)
+                s1[name] = (min(a, s1[name][0]), max(b_, s1[name][1])) if name in s1 else (a, b_)
+            for name in d1:
+                dur.setdefault(name, []).append(d1[name])
+                span.setdefault(name, []).append(s1[name])
+        if args.no_graph:
+            for s in range(reps):
+                path.events = []
+                path.run(batches[s % 2], max_n)
+                torch.cuda.synchronize()
+                take(path.events)
+            path.events = None
+        else:
+            gs = [path.capture(b, max_n, time_stages=ALL) for b in batches]
+            for s in range(reps):
+                g = gs[s % 2]
+                g.replay()
+                torch.cuda.synchronize()
+                take(g.events)
+        timelines[tag] = {k: [round(sum(a for a, _ in v) / len(v), 4), round(sum(b_ for _, b_ in v) / len(v), 4)] for k, v in span.items()}
+        return {k: sum(v) / len(v) for k, v in dur.items()}
+
+    cum_keep = path.cum.clone()
+    avg_ms = staged_pass(50, "overlapped")
     avg_ms.update(top_ms)                # the dominant stage: the timed region's own measurement
+    barrier()
     # the same stages launched back to back on one stream (no overlap): each kernel timed ALONE, after the timed region
-    serial_events = []
     ms_serial = None
+    alone_ms = {}
     if args.serial_steps > 0:
         path.overlap = False
         for w in range(3):
             path.run(batches[w % 2], max_n)
+        alone_ms = staged_pass(args.serial_steps, "serial")
+        sg_ = [path.capture(b, max_n) for b in batches] if not args.no_graph else None
         barrier()
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
         s0.record()
         for s in range(args.serial_steps):
-            path.events = []
-            path.run(batches[s % 2], max_n)
-            serial_events.append(path.events)
+            (sg_[s % 2].replay() if sg_ else path.run(batches[s % 2], max_n))
         s1.record()
-        path.events = None
         path.overlap = not args.no_overlap
         barrier()
         ms_serial = s0.elapsed_time(s1) / args.serial_steps
-    alone_ms = stage_avg(serial_events)
+        del sg_
+    path.cum.copy_(cum_keep)
     peak_hbm, peak_src, peak_tf, peak_tf_src = load_peaks()
     alg = algorithmic_bytes(cfg, B, 2 if prep_dtype == torch.bfloat16 else 4)
     traffic = {}
@@ -618,7 +656,7 @@ def run_ours(args, cfg):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if prep_dtype == torch.bfloat16 else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(cfg), **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-                "inner_repeats": inner, "passes_timed": passes, "ms_per_pass": ms_total / passes, "timed_region_s": ms_total / 1e3,
+                "image_groups_per_pass": args.chunks, "inner_repeats": inner, "passes_timed": passes, "ms_per_pass": ms_total / passes, "timed_region_s": ms_total / 1e3,
                 "collective_ms": collective_ms,
                 "collective": "one all-reduce(SUM) of the int64[4] IoU accumulators after the last pass (NCCL), timed on its own and charged to the job",
                 "l2": f"two alternating batches; the byte masks alone are {B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",
@@ -628,7 +666,7 @@ def run_ours(args, cfg):
                 "streams": ("4 (prep on the caller's stream; pack -> mask pass -> pooling+scoring -> IoU, blur -> prep setup, heat-map tables on "
                             "high-priority helper streams)" if path.overlap else "1"),
                 "ms_per_pass_serial": ms_serial,
-                "roofline": roofline, "kernels": kernels, "rle_input": rle_info, "cpu_baseline": cpu,
+                "roofline": roofline, "kernels": kernels, "timeline_ms": timelines, "rle_input": rle_info, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
                         "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}
         print(json.dumps(line), flush=True)
@@ -653,7 +691,7 @@ def run_sweep_mode(args, cfg):
     pool = [synth.make_batch_device(7000 + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev, grid=cfg["g"], raw_heat=True)
             for i in range(args.sweep_pool)]
     max_n = cfg["n_masks"]
-    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=torch.bfloat16, feature_source=args.features)
+    path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=torch.bfloat16, feature_source=args.features, chunks=args.chunks)
     steps = [path.capture(b, max_n) for b in pool]          # one CUDA graph per pool batch
     E_b = B * cfg["n_expr"]
 

@@ -6,7 +6,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhgl.so")
+LIB_PATH = os.environ.get("HGL_LIB") or os.path.join(_PKG, "libhgl.so")     # HGL_LIB: profiling builds (build.py, HGL_BUILD_TUNING=1)
 
 HGL_F32, HGL_BF16 = 0, 1
 HGL_BG_BLUR, HGL_BG_BLACK = 0, 1

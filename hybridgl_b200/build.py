@@ -17,8 +17,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-BUILD = os.path.join(PKG, "_build")
-LIB = os.path.join(PKG, "libhgl.so")
+# HGL_BUILD_TUNING=1: a separate profiling build (-DHGL_TUNING: environment tuning hooks, phase traces) next to the product library
+TUNING = bool(int(os.environ.get("HGL_BUILD_TUNING", "0")))
+BUILD = os.path.join(PKG, "_build_tuning" if TUNING else "_build")
+LIB = os.path.join(PKG, "libhgl_tuning.so" if TUNING else "libhgl.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -26,7 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + (["-DHGL_TUNING"] if TUNING else [])
 
 
 def _nvcc() -> str:

@@ -34,7 +34,8 @@
 
 namespace hgl {
 
-constexpr int kPsThreads = 256;   // 8 warps: all stage A; thread 0 issues TMA + MMA; warps w and w+4 share TMEM lanes 32*(w%4)..
+constexpr int kPsThreads = 512;   // 16 warps (4 per scheduler: a lone warp issues one instruction every ~13 cycles, the kernel is issue-latency
+                                  // bound): all stage A; thread 0 issues TMA + MMA; warps w, w+4, w+8, w+12 share TMEM lanes 32*(w%4)..
 constexpr int kPsM = 128;         // proposals per row tile (UMMA M)
 constexpr int kPsKC = 64;         // tokens per ring stage (4 MMA k-steps)
 constexpr int kPsER = 4;          // expressions per scoring round
@@ -43,16 +44,21 @@ constexpr int kPsMaxStages = 8;
 constexpr uint32_t kPsAHalf = kPsM * kPsKC * 2;   // one bf16 [128 x 64] operand block (hi or lo)
 constexpr uint32_t kPsBBox = kPsKC * 64 * 2;      // one TMA box: 64 tokens x 64 columns bf16
 constexpr int kPsPiece = 64;      // output columns staged through shared memory per round of the feature pass
-// shared-memory map (offsets from the 1024-byte aligned base)
-constexpr uint32_t kOffFull = 0, kOffFree = 64, kOffAcc = 128, kOffTmem = 192, kOffTnp = 256, kOffTn = 320, kOffText = 512;
-constexpr uint32_t kOffRing = kOffText + 2 * kPsER * 256 * 4;          // text slice: [2*kPsER][Nw <= 256] f32 -> ring at 8704 ...
-constexpr uint32_t kRingBase = (kOffRing + 1023) & ~1023u;             // ... rounded to the swizzle atom: 9216
-// epilogue scratch, aliased onto the ring once every MMA has completed
-constexpr uint32_t kEpPart = 0;                                                    // [tiles][1 + 2*kPsER][128] f32
-constexpr uint32_t kEpSc = kEpPart + kPsMaxTiles * (1 + 2 * kPsER) * kPsM * 4;     // [2][kPsER][tiles*128] f32
-constexpr uint32_t kEpPicks = kEpSc + 2 * kPsER * kPsMaxTiles * kPsM * 4;          // [8 warps][9] int
-constexpr uint32_t kEpInv = kEpPicks + 512;                                        // [tiles*128] f32
-constexpr uint32_t kEpStage = kEpInv + kPsMaxTiles * kPsM * 4;                     // [128][kPsPiece + 1] f32; also the half-1 partials
+// shared-memory map (offsets from the 1024-byte aligned base).  Fixed part; the rest (PoolScoreParams::off_*) depends on Nw / NT / tiles:
+//   text   [2*kPsER][Nw] f32           this CTA's column slice of the text ensemble / negatives
+//   boxes  [tiles*128][4] int64        rank 0: the image's boxes            } prefetched at kernel start: the selection tail
+//   sg     [kPsER][tiles*128] f32      rank 0: score_gem rows of the round  } then never waits for global memory
+//   gather [NT][kNP][128] f32          rank 0: partial sums pushed by every CTA of the cluster (NOT in the ring: peers push
+//   tn     [NT][2*kPsER] f32                    while rank 0's MMAs may still be reading its ring)
+//   ring   S stages of (A hi | A lo | B boxes), 1024-byte aligned
+constexpr uint32_t kOffFull = 0, kOffFree = 64, kOffAcc = 128, kOffTmem = 136, kOffAFull = 192, kOffTnp = 256, kOffMeta = 320, kOffText = 512;
+constexpr int kNP = 1 + 2 * kPsER;                                     // partial sums per row: |row|^2, 4 text dots, 4 negative dots
+// epilogue scratch, aliased onto the CTA's OWN ring once every one of its MMAs has completed
+constexpr uint32_t kEpPart1 = 0;                                       // [3][kNP][128] f32: partial sums of the column quarters 1..3
+constexpr uint32_t kEpSc = kEpPart1 + 3 * kNP * kPsM * 4;              // rank 0: [2*kPsER][tiles*128] f32 raw scores
+constexpr uint32_t kEpPicks = kEpSc + 2 * kPsER * kPsMaxTiles * kPsM * 4;   // rank 0: [kPsER][kTailPicks] int
+constexpr uint32_t kEpInv = kEpPicks + 256;                            // rank 0: [tiles*128] f32 |row|
+constexpr uint32_t kEpStage = kEpInv + kPsMaxTiles * kPsM * 4;         // [128][kPsPiece + 1] f32 (feature output only)
 constexpr uint32_t kEpEnd = kEpStage + kPsM * (kPsPiece + 1) * 4;
 
 // ---- tcgen05 / TMEM / TMA wrappers (PTX ISA 8.6+, sm_100a) ------------------------------------------------------------
@@ -74,10 +80,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the accumulate flag known at compile time and the descriptors' invariant high words kept apart (the issuing
+// thread is alone in its warp: every instruction it does not execute is ~13 cycles off the critical path)
+template <bool kAcc>
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(kAcc ? 1 : 0)
+      : "memory");
+}
 // arrive on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 32 consecutive accumulator columns of this thread's TMEM lane (row); NO wait: pair with tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                 "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                 "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 16 consecutive accumulator columns of this thread's TMEM lane (row)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -101,6 +128,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
                : "memory");
 }
 
+// Phase trace for tuning builds (-DHGL_TUNING, never the shipped library): thread 0 of every CTA stamps clock64() at the
+// phase boundaries; read back with hgl_debug_pool_score_trace (profiles/trace_pool_score.py).
+#ifdef HGL_TUNING
+__device__ long long g_ps_trace[16 * 4096];
+#define PS_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.y * gridDim.x + blockIdx.x < 4096) \
+    g_ps_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
+#else
+#define PS_TRACE(k) do { } while (0)
+#endif
+
 struct PoolScoreParams {
   const float* w;              // [M, L] f32 soft grid masks
   const int32_t* mask_off;     // [B+1] or null (B == 1)
@@ -108,6 +145,7 @@ struct PoolScoreParams {
   int B, M, E, L, D, max_n;
   int Nw, NT, NKC, stages, boxes;   // columns per CTA, CTAs per cluster, token chunks, ring depth, TMA boxes per stage (Nw / 64)
   uint32_t stage_bytes, tmem_cols;
+  uint32_t off_boxes, off_sg, off_gather, off_tn, off_ring;   // shared-memory map (bytes from the aligned base)
   // optional pooled rows
   void* out; int out_bf16, normalize;
   // scoring (E == 0: pooling only)
@@ -127,18 +165,23 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
   if (p.expr_off) { e_lo = p.expr_off[b]; e_hi = p.expr_off[b + 1]; }
   const int n = min(max(n_hi - n_lo, 0), p.max_n);                 // uniform for the whole cluster
   const int EB = max(e_hi - e_lo, 0);
-  const int L = p.L, D = p.D, Nw = p.Nw, S = p.stages, NKC = p.NKC;
+  const int L = p.L, D = p.D, Nw = p.Nw, S = p.stages, NKC = p.NKC, NT = p.NT;
   const int col0 = (int)rank * Nw;
 
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffFull);
   uint64_t* bar_free = reinterpret_cast<uint64_t*>(smem + kOffFree);
   uint64_t* bar_acc = reinterpret_cast<uint64_t*>(smem + kOffAcc);
+  uint64_t* bar_afull = reinterpret_cast<uint64_t*>(smem + kOffAFull);   // [kPsMaxStages] A stage converted: one arrival per warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   float* tnp = reinterpret_cast<float*>(smem + kOffTnp);          // [2*kPsER] this CTA's partial |text|^2 (its column slice)
-  float* tn_s = reinterpret_cast<float*>(smem + kOffTn);          // [2*kPsER] rank 0: text norms
   float* text = reinterpret_cast<float*>(smem + kOffText);        // [2*kPsER][Nw]: rows 0..3 text ensemble, 4..7 negatives
-  uint8_t* ring = smem + kRingBase;
-  float* part = reinterpret_cast<float*>(ring + kEpPart);
+  int64_t* box_s = reinterpret_cast<int64_t*>(smem + p.off_boxes);  // rank 0: boxes of the image
+  float* sg_s = reinterpret_cast<float*>(smem + p.off_sg);          // rank 0: score_gem rows of the round's expressions
+  int* meta_s = reinterpret_cast<int*>(smem + kOffMeta);            // rank 0: (n_other, relaflag) of the round's expressions
+  float* gather = reinterpret_cast<float*>(smem + p.off_gather);
+  float* gather_tn = reinterpret_cast<float*>(smem + p.off_tn);
+  uint8_t* ring = smem + p.off_ring;
+  float* part1 = reinterpret_cast<float*>(ring + kEpPart1);
   float* sc = reinterpret_cast<float*>(ring + kEpSc);
   int* picks = reinterpret_cast<int*>(ring + kEpPicks);
   float* inv_s = reinterpret_cast<float*>(ring + kEpInv);
@@ -146,17 +189,19 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
 
   if (n == 0) {
     // an image without proposals: nothing to pool; the selection tail still defines its outputs (-1 picks), like hgl_score_select
-    if (rank == 0) {
-      float* s0 = reinterpret_cast<float*>(smem + kOffText);
-      for (int e = e_lo + warp; e < e_hi; e += kPsThreads / 32) select_tail_warp(p.tail, e, 0, n_lo, s0, s0, picks + warp * 9, lane);
-    }
+    if (rank == 0)
+      for (int e0 = e_lo; e0 < e_hi; e0 += kPsER) {
+        select_tail_block(p.tail, e0, min(kPsER, e_hi - e0), 0, n_lo, sc, kPsM, picks, nullptr, nullptr, nullptr, warp, lane);
+        __syncthreads();
+      }
     return;
   }
   const int tiles = (n + kPsM - 1) / kPsM;
   const int total = tiles * NKC;
+  PS_TRACE(0);
 
   if (tid == 0) {
-    for (int i = 0; i < kPsMaxStages; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_free + i, 1); }
+    for (int i = 0; i < kPsMaxStages; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_free + i, 1); mbar_init(bar_afull + i, kPsThreads / 32); }
     mbar_init(bar_acc, 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -166,6 +211,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PS_TRACE(1);
 
   // B stage of iteration `it` (row tile it / NKC, token chunk it % NKC): Nw/64 boxes of 64 tokens x 64 columns
   const CUtensorMap* tmap_ptr = &tmap;
@@ -178,80 +224,176 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
   if (tid == 0)
     for (int it = 0; it < min(S, total); ++it) issue_b(it);
 
+  // ---- A: soft masks f32 -> (hi, lo) bf16 in the canonical K-major layout, one 64-token chunk per iteration.  A warp
+  //      converts 8 rows x 32 columns per item: lane -> (row % 8, 8-float column group): 32-byte global sectors in, one
+  //      contiguous 512-byte run of 16-byte core rows out (bank-conflict-free).  Rows beyond the image and k >= L are zero.
+  //      The loads of chunk it+1 are issued before chunk it is converted, so only the first chunk's latency is exposed.
+  constexpr int kItems = kPsM * (kPsKC / 8) / kPsThreads;      // 2
+  const bool w_vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0;
+  // per-thread invariants of the two items: source pointer, row, first column, offset inside an operand block
+  const float* a_src[kItems];
+  int a_row[kItems], a_col[kItems];
+  uint32_t a_off[kItems];
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int wi = warp + (kPsThreads / 32) * q;
+    const int r = (wi >> 1) * 8 + (lane & 7), c8 = (wi & 1) * 4 + (lane >> 3);
+    a_row[q] = r; a_col[q] = c8 * 8;
+    a_src[q] = p.w + (size_t)(n_lo + r) * L + c8 * 8;
+    a_off[q] = (uint32_t)(r >> 3) * 1024u + (uint32_t)c8 * 128u + (uint32_t)(r & 7) * 16u;
+  }
+  auto load_a = [&](int it, float4 (&f)[kItems][2]) {
+    const int kc = it % NKC, tile = it / NKC;
+    const size_t shift = (size_t)tile * kPsM * L + (size_t)kc * kPsKC;
+#pragma unroll
+    for (int q = 0; q < kItems; ++q) {
+      const int row = tile * kPsM + a_row[q], k = kc * kPsKC + a_col[q];
+      f[q][0] = make_float4(0.f, 0.f, 0.f, 0.f); f[q][1] = f[q][0];
+      if (row < n && k < L) {
+        const float* src = a_src[q] + shift;
+        if (w_vec && k + 8 <= L) {
+          f[q][0] = __ldg(reinterpret_cast<const float4*>(src)); f[q][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        } else {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (k + u < L) ? __ldg(src + u) : 0.f;
+          f[q][0] = make_float4(v[0], v[1], v[2], v[3]); f[q][1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+  };
+  // hi = bf16(w), lo = bf16(w - hi), two values per cvt.rn.bf16x2.f32
+  auto store_a = [&](int slot, const float4 (&f)[kItems][2]) {
+    uint8_t* a_hi = ring + (size_t)slot * p.stage_bytes;
+#pragma unroll
+    for (int q = 0; q < kItems; ++q) {
+      const float v[8] = {f[q][0].x, f[q][0].y, f[q][0].z, f[q][0].w, f[q][1].x, f[q][1].y, f[q][1].z, f[q][1].w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        hi[u] = pack_bf16x2(v[2 * u], v[2 * u + 1]);
+        lo[u] = pack_bf16x2(v[2 * u] - __uint_as_float(hi[u] << 16), v[2 * u + 1] - __uint_as_float(hi[u] & 0xffff0000u));
+      }
+      *reinterpret_cast<uint4*>(a_hi + a_off[q]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a_hi + kPsAHalf + a_off[q]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  };
+  // Every global load this kernel depends on is issued up front and in parallel (the kernel is a latency chain: a dependent
+  // DRAM round trip costs 1-2 us while the prep kernel saturates HBM beside it): the first four A chunks into registers ...
+  float4 f0[kItems][2], f1[kItems][2], f2[kItems][2], f3[kItems][2];
+  auto load_set = [&](int it) {
+    switch (it & 3) { case 0: load_a(it, f0); break; case 1: load_a(it, f1); break; case 2: load_a(it, f2); break; default: load_a(it, f3); break; }
+  };
+  auto store_set = [&](int it, int slot) {
+    switch (it & 3) { case 0: store_a(slot, f0); break; case 1: store_a(slot, f1); break; case 2: store_a(slot, f2); break; default: store_a(slot, f3); break; }
+  };
+  const int rows_pad = ((n + kPsM - 1) / kPsM) * kPsM;
+  for (int it = 0; it < min(4, total); ++it) load_set(it);
+  // ... and, on rank 0, what the selection tail will need: the image's boxes, the round's score_gem rows, (n_other, relaflag).
+  // Loads go to registers here and are stored to shared memory only after the text side below has issued ITS loads: a store
+  // right behind its load would stall the thread for a full memory round trip per statement.
+  constexpr int kPF = kPsMaxTiles * kPsM * 4 / kPsThreads;       // 8 elements per thread cover 512 boxes / 4 x 512 score_gem values
+  int64_t pf_box[kPF];
+  float pf_sg[kPF];
+  int pf_meta[2] = {0, 0};
+  auto tail_loads = [&](int rd, bool with_boxes) {
+    const int ne_r = min(kPsER, EB - rd * kPsER);
+    if (tid < ne_r) {
+      const int e = e_lo + rd * kPsER + tid;
+      pf_meta[0] = p.tail.other_off[e + 1] - p.tail.other_off[e];
+      pf_meta[1] = p.tail.relaflag[e];
+    }
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+      const int i = tid + u * kPsThreads;
+      pf_box[u] = (with_boxes && i < n * 4) ? __ldg(p.tail.boxes + (size_t)n_lo * 4 + i) : 0;
+      pf_sg[u] = 0.f;
+      if (p.tail.score_gem != nullptr && i < ne_r * n) {
+        const int j = i / n, c = i - j * n;
+        pf_sg[u] = __ldg(p.tail.score_gem + (size_t)(e_lo + rd * kPsER + j) * p.max_n + c);
+      }
+    }
+  };
+  auto tail_stores = [&](int rd, bool with_boxes) {
+    const int ne_r = min(kPsER, EB - rd * kPsER);
+    if (tid < ne_r) { meta_s[2 * tid] = pf_meta[0]; meta_s[2 * tid + 1] = pf_meta[1]; }
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+      const int i = tid + u * kPsThreads;
+      if (with_boxes && i < n * 4) box_s[i] = pf_box[u];
+      if (p.tail.score_gem != nullptr && i < ne_r * n) { const int j = i / n, c = i - j * n; sg_s[j * rows_pad + c] = pf_sg[u]; }
+    }
+  };
+  const bool tail_here = rank == 0 && EB > 0;
+  if (tail_here) tail_loads(0, true);
+
   // (a6) text side of one scoring round, this CTA's column slice: warp w -> expression w % 4, ensemble (w < 4) or negatives
   // (Hybridgl_main.py:153-164): text = r*sent + (1-r)*noun; neg = mean_k others[k] (zeros if none)
   auto text_round = [&](int rd) {
-    const int j = warp & 3, kind = warp >> 2;
+    const int j = warp & 3, kind = (warp >> 2) & 1;
     const int e = e_lo + rd * kPsER + j;
-    if (e < e_hi) {
-      const int k0 = p.other_off[e], k1 = p.other_off[e + 1];
-      float acc = 0.f;
-      for (int c = lane; c < Nw; c += 32) {
-        const int col = col0 + c;
-        float v = 0.f;
-        if (col < D) {
-          if (kind == 0) {
-            v = __fadd_rn(__fmul_rn(p.r, __ldg(p.sent + (size_t)e * D + col)), __fmul_rn(p.one_minus_r, __ldg(p.noun + (size_t)e * D + col)));
-          } else {
-            for (int k = k0; k < k1; ++k) v = __fadd_rn(v, __ldg(p.others + (size_t)k * D + col));
-            if (k1 > k0) v = __fdiv_rn(v, (float)(k1 - k0));
-          }
+    if (e < e_hi && warp < 8) {
+      constexpr int kCU = 8;                                     // columns per lane: Nw / 32 <= 8
+      float v[kCU];
+      if (kind == 0) {                                           // all loads first, then the arithmetic
+        float a[kCU], g[kCU];
+#pragma unroll
+        for (int ci = 0; ci < kCU; ++ci) {
+          const int c = lane + 32 * ci, col = col0 + c;
+          const bool ok = c < Nw && col < D;
+          a[ci] = ok ? __ldg(p.sent + (size_t)e * D + col) : 0.f;
+          g[ci] = ok ? __ldg(p.noun + (size_t)e * D + col) : 0.f;
         }
-        text[(kind * kPsER + j) * Nw + c] = v;
-        acc += v * v;
+#pragma unroll
+        for (int ci = 0; ci < kCU; ++ci) v[ci] = __fadd_rn(__fmul_rn(p.r, a[ci]), __fmul_rn(p.one_minus_r, g[ci]));
+      } else {
+        const int k0 = p.other_off[e], k1 = p.other_off[e + 1];
+#pragma unroll
+        for (int ci = 0; ci < kCU; ++ci) v[ci] = 0.f;
+        for (int kb = k0; kb < k1; kb += 4) {                    // four negatives' loads in flight, added in order
+          float o[4][kCU];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int ci = 0; ci < kCU; ++ci) {
+              const int c = lane + 32 * ci, col = col0 + c;
+              o[u][ci] = (kb + u < k1 && c < Nw && col < D) ? __ldg(p.others + (size_t)(kb + u) * D + col) : 0.f;
+            }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (kb + u < k1) {
+#pragma unroll
+              for (int ci = 0; ci < kCU; ++ci) v[ci] = __fadd_rn(v[ci], o[u][ci]);
+            }
+        }
+        if (k1 > k0) {
+#pragma unroll
+          for (int ci = 0; ci < kCU; ++ci) v[ci] = __fdiv_rn(v[ci], (float)(k1 - k0));
+        }
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < kCU; ++ci) {
+        const int c = lane + 32 * ci;
+        if (c < Nw) { text[(kind * kPsER + j) * Nw + c] = v[ci]; acc += v[ci] * v[ci]; }
       }
       acc = warp_sum(acc);
       if (lane == 0) tnp[kind * kPsER + j] = acc;
     }
   };
   if (EB > 0) text_round(0);
-
-  // ---- A: soft masks f32 -> (hi, lo) bf16 in the canonical K-major layout, one 64-token chunk per iteration.  A warp
-  //      converts 8 rows x 32 columns per item: lane -> (row % 8, 8-float column group): 32-byte global sectors in, one
-  //      contiguous 512-byte run of 16-byte core rows out (bank-conflict-free).  Rows beyond the image and k >= L are zero.
-  const bool w_vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0;
-  auto convert_a = [&](int tile, int kc, int slot) {
-    uint8_t* a_hi = ring + (size_t)slot * p.stage_bytes;
-    constexpr int kItems = kPsM * (kPsKC / 8) / kPsThreads;      // 4
-    float4 f[kItems][2];
-#pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      const int wi = warp + 8 * it;
-      const int r = (wi >> 1) * 8 + (lane & 7), c8 = (wi & 1) * 4 + (lane >> 3);
-      const int row = tile * kPsM + r, k = kc * kPsKC + c8 * 8;
-      f[it][0] = make_float4(0.f, 0.f, 0.f, 0.f); f[it][1] = f[it][0];
-      if (row < n && k < L) {
-        const float* src = p.w + (size_t)(n_lo + row) * L + k;
-        if (w_vec && k + 8 <= L) {
-          f[it][0] = __ldg(reinterpret_cast<const float4*>(src)); f[it][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        } else {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = (k + q < L) ? __ldg(src + q) : 0.f;
-          f[it][0] = make_float4(v[0], v[1], v[2], v[3]); f[it][1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      const int wi = warp + 8 * it;
-      const int r = (wi >> 1) * 8 + (lane & 7), c8 = (wi & 1) * 4 + (lane >> 3);
-      const float v[8] = {f[it][0].x, f[it][0].y, f[it][0].z, f[it][0].w, f[it][1].x, f[it][1].y, f[it][1].z, f[it][1].w};
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
-        hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lo[q] = pack_bf16x2(v[2 * q] - __bfloat162float(h0), v[2 * q + 1] - __bfloat162float(h1));
-      }
-      const size_t off = (size_t)(r >> 3) * 1024 + (size_t)c8 * 128 + (r & 7) * 16;
-      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(a_hi + kPsAHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  };
+  if (tail_here) tail_stores(0, true);
+  PS_TRACE(2);
 
   // instruction descriptor: D = f32, A = B = bf16, A K-major, B MN-major, N = Nw, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(Nw >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
+  // descriptor high words (invariant): A: no swizzle, SBO = 1024 (8-row groups), LBO = 128 (the two K-cores of a k-step);
+  // B: 128-byte swizzle, MN-major: SBO = 1024 (8-token groups), LBO = one box (64-column groups); a k-step is 16 tokens = 2048 B
+  const uint64_t a_tmpl = smem_desc(0u, 128u, 1024u, 0u), b_tmpl = smem_desc(0u, kPsBBox, 1024u, 2u);
+  const uint32_t a_hi32 = (uint32_t)(a_tmpl >> 32), b_hi32 = (uint32_t)(b_tmpl >> 32);
+  const uint32_t a_lo_tmpl = (uint32_t)a_tmpl, b_lo_tmpl = (uint32_t)b_tmpl;
+  // No CTA-wide barrier in this loop: a warp that has converted its share of a stage arrives on the stage's `afull` mbarrier
+  // and moves on; thread 0 trails behind, waits for (afull, full) of a stage and issues its MMAs.
   for (int it = 0; it < total; ++it) {
     const int slot = it % S, kc = it % NKC, tile = it / NKC;
     if (tid == 0) {                                              // keep S-1 B stages in flight ahead of the MMAs
@@ -262,127 +404,173 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
       }
     }
     if (it >= S) mbar_wait(bar_free + slot, (uint32_t)((it / S - 1) & 1));     // the MMAs that read this slot have completed
-    convert_a(tile, kc, slot);
+    store_set(it, slot);
+    if (it + 4 < total) load_set(it + 4);                        // refill the register set just drained
     proxy_fence_async();                                         // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_afull + slot);
+    if (it < 4) PS_TRACE(3 + it);
     if (tid == 0) {
+      mbar_wait(bar_afull + slot, (uint32_t)((it / S) & 1));     // all eight warps have converted their share of this stage
       mbar_wait(bar_full + slot, (uint32_t)((it / S) & 1));      // TMA has landed this stage's tokens
       tc_fence_after();
       const uint32_t a_addr = smem_u32(ring + (size_t)slot * p.stage_bytes);
-      const uint32_t b_addr = a_addr + 2 * kPsAHalf;
+      // (14-bit start-address field: in a cluster the shared-window address carries the CTA rank in its upper bits)
+      const uint32_t ah = a_lo_tmpl | ((a_addr >> 4) & 0x3fffu), al = a_lo_tmpl | (((a_addr + kPsAHalf) >> 4) & 0x3fffu);
+      const uint32_t bd = b_lo_tmpl | (((a_addr + 2 * kPsAHalf) >> 4) & 0x3fffu);
+      const uint32_t dcol = tmem_base + (uint32_t)(tile * Nw);
       const int ksteps = min(kPsKC / 16, (L - kc * kPsKC + 15) / 16);
-      for (int s2 = 0; s2 < ksteps; ++s2) {
-        // A: two K-cores 128 B apart, 8-row groups 1024 B apart.  B: 128-byte swizzle, MN-major: 8-token groups (SBO) 1024 B
-        // apart, 64-column groups (LBO) one box apart; a k-step is 16 tokens = 2048 B.
-        const uint64_t bd = smem_desc(b_addr + (uint32_t)s2 * 2048u, kPsBBox, 1024u, 2u);
-        const uint64_t ah = smem_desc(a_addr + (uint32_t)s2 * 256u, 128u, 1024u, 0u);
-        const uint64_t al = smem_desc(a_addr + kPsAHalf + (uint32_t)s2 * 256u, 128u, 1024u, 0u);
-        umma_bf16(tmem_base + (uint32_t)(tile * Nw), ah, bd, idesc, (kc > 0 || s2 > 0) ? 1u : 0u);
-        umma_bf16(tmem_base + (uint32_t)(tile * Nw), al, bd, idesc, 1u);
+      if (kc == 0) umma_bf16_lohi<false>(dcol, ah, a_hi32, bd, b_hi32, idesc);
+      else umma_bf16_lohi<true>(dcol, ah, a_hi32, bd, b_hi32, idesc);
+      umma_bf16_lohi<true>(dcol, al, a_hi32, bd, b_hi32, idesc);
+#pragma unroll
+      for (int s2 = 1; s2 < kPsKC / 16; ++s2) {
+        if (s2 < ksteps) {
+          umma_bf16_lohi<true>(dcol, ah + 16u * s2, a_hi32, bd + 128u * s2, b_hi32, idesc);
+          umma_bf16_lohi<true>(dcol, al + 16u * s2, a_hi32, bd + 128u * s2, b_hi32, idesc);
+        }
       }
       umma_commit(bar_free + slot);
       if (it == total - 1) umma_commit(bar_acc);
     }
   }
 
-  // ---- epilogue.  Warp w reads TMEM lanes 32*(w%4)..+31 (= proposal rows); warps 0-3 take the even 16-column groups,
-  //      warps 4-7 the odd ones.
+  // ---- epilogue.  Warp w reads TMEM lanes 32*(w%4)..+31 (= proposal rows); warps w, w+4, w+8, w+12 share the row's
+  //      32-column groups.  Every CTA PUSHES its rows' partial sums into rank 0's shared memory (st.shared::cluster:
+  //      fire and forget, no remote-load latency); one cluster barrier later rank 0 adds the NT slices up.
+  PS_TRACE(7);
   mbar_wait(bar_acc, 0u);
   tc_fence_after();
-  const int half = warp >> 2;
+  PS_TRACE(8);
+  const int quarter = warp >> 2;                                 // which 32-column groups of a row this thread reads
   const int my_row = (warp & 3) * 32 + lane;
   const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr int kNP = 1 + 2 * kPsER;                             // partial sums per row: |row|^2, 4 text dots, 4 negative dots
-  float* part1 = stage;                                          // half-1 partials [tiles][kNP][128] (<= 18 KB of the stage buffer)
   const int rounds = max(1, (EB + kPsER - 1) / kPsER);
-  const int rows_pad = tiles * kPsM;
+  const bool want_out = p.out != nullptr;
   for (int rd = 0; rd < rounds; ++rd) {
     const int ne = min(kPsER, EB - rd * kPsER);                  // <= 0 when the launch only pools
-    if (rd > 0) { text_round(rd); __syncthreads(); }
+    if (rd > 0) {
+      if (tail_here) tail_loads(rd, false);
+      text_round(rd);
+      if (tail_here) tail_stores(rd, false);
+      __syncthreads();
+    }
     for (int tile = 0; tile < tiles; ++tile) {
       float ss = 0.f, dt[kPsER], dn[kPsER];
 #pragma unroll
       for (int j = 0; j < kPsER; ++j) { dt[j] = 0.f; dn[j] = 0.f; }
-      for (int c = half * 16; c < Nw; c += 32) {
-        float v[16];
-        tmem_ld16(lane_addr + (uint32_t)(tile * Nw + c), v);
+      // this thread's columns: the 32-column groups quarter, quarter + 4, ... of the row
+      for (int c = quarter * 32; c < Nw; c += 128) {
+        uint32_t r[32];
+        tmem_ld32_nowait(lane_addr + (uint32_t)(tile * Nw + c), r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) ss += v[q] * v[q];
+        for (int q = 0; q < 32; ++q) { const float x = __uint_as_float(r[q]); ss += x * x; }
 #pragma unroll
         for (int j = 0; j < kPsER; ++j) {
           if (j < ne) {
             const float4* t4 = reinterpret_cast<const float4*>(text + j * Nw + c);
             const float4* n4 = reinterpret_cast<const float4*>(text + (kPsER + j) * Nw + c);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               const float4 a = t4[q], g = n4[q];
-              dt[j] += v[4 * q] * a.x + v[4 * q + 1] * a.y + v[4 * q + 2] * a.z + v[4 * q + 3] * a.w;
-              dn[j] += v[4 * q] * g.x + v[4 * q + 1] * g.y + v[4 * q + 2] * g.z + v[4 * q + 3] * g.w;
+              const float x0 = __uint_as_float(r[4 * q]), x1 = __uint_as_float(r[4 * q + 1]);
+              const float x2 = __uint_as_float(r[4 * q + 2]), x3 = __uint_as_float(r[4 * q + 3]);
+              dt[j] += x0 * a.x + x1 * a.y + x2 * a.z + x3 * a.w;
+              dn[j] += x0 * g.x + x1 * g.y + x2 * g.z + x3 * g.w;
             }
           }
         }
       }
-      float* dst = (half ? part1 : part) + (size_t)tile * kNP * kPsM + my_row;
-      dst[0] = ss;
+      if (quarter) {
+        float* pq = part1 + (size_t)(quarter - 1) * kNP * kPsM + my_row;
+        pq[0] = ss;
 #pragma unroll
-      for (int j = 0; j < kPsER; ++j) { dst[(1 + j) * kPsM] = dt[j]; dst[(1 + kPsER + j) * kPsM] = dn[j]; }
-    }
-    __syncthreads();
-    for (int i = tid; i < tiles * kNP * kPsM; i += kPsThreads) part[i] += part1[i];
-    cluster_sync_all();                                          // #1: every CTA's partial sums are visible cluster-wide
-
-    if (rank == 0 && ne > 0) {                                   // text norms: sum of the column slices
-      if (tid < 2 * kPsER) {
-        float t = 0.f;
-        for (int c = 0; c < p.NT; ++c) t += ld_peer_f32(tnp + tid, (uint32_t)c);
-        tn_s[tid] = sqrtf(t);
+        for (int j = 0; j < kPsER; ++j) { pq[(1 + j) * kPsM] = dt[j]; pq[(1 + kPsER + j) * kPsM] = dn[j]; }
+        if (tile == 0 && ne > 0 && tid >= 128 && tid < 128 + 2 * kPsER)
+          st_peer_f32(gather_tn + rank * 2 * kPsER + (tid - 128), 0u, tnp[tid - 128]);
       }
       __syncthreads();
-    }
-    if (tid < kPsM && (rank == 0 || (rd == 0 && p.out != nullptr))) {
-      for (int tile = 0; tile < tiles; ++tile) {
-        const float* src = part + (size_t)tile * kNP * kPsM + tid;
-        float ss = 0.f;
-        for (int c = 0; c < p.NT; ++c) ss += ld_peer_f32(src, (uint32_t)c);
-        const float fnorm = sqrtf(ss);
-        if (rd == 0) inv_s[tile * kPsM + tid] = p.normalize ? __frcp_rn(fnorm) : 1.f;
-        if (rank == 0 && ne > 0) {
-          const int grow = tile * kPsM + tid;
+      if (!quarter) {
+        float* dst = gather + (size_t)rank * kNP * kPsM + my_row;       // slice `rank` of rank 0's gather buffer
+        const float* p1 = part1 + my_row;
+        constexpr int kQ = kNP * kPsM;
+        if (rd == 0) st_peer_f32(dst, 0u, ss + p1[0] + p1[kQ] + p1[2 * kQ]);
+#pragma unroll
+        for (int j = 0; j < kPsER; ++j) {
+          if (j < ne) {
+            const int kt = (1 + j) * kPsM, kn = (1 + kPsER + j) * kPsM;
+            st_peer_f32(dst + kt, 0u, dt[j] + p1[kt] + p1[kQ + kt] + p1[2 * kQ + kt]);
+            st_peer_f32(dst + kn, 0u, dn[j] + p1[kn] + p1[kQ + kn] + p1[2 * kQ + kn]);
+          }
+        }
+      }
+      PS_TRACE(9);
+      cluster_sync_all();                                        // every CTA's partial sums have landed in rank 0
+      PS_TRACE(10);
+      if (rank == 0 && tid < kPsM) {
+        const float* src = gather + tid;
+        const int grow = tile * kPsM + tid;
+        float acc[kNP], tn[2 * kPsER];                           // independent accumulators: the loads of a slice overlap
+#pragma unroll
+        for (int k = 0; k < kNP; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * kPsER; ++k) tn[k] = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < NT; ++c) {
+          if (rd == 0) acc[0] += src[(size_t)c * kNP * kPsM];
 #pragma unroll
           for (int j = 0; j < kPsER; ++j) {
             if (j < ne) {
-              float a = 0.f, g = 0.f;
-              for (int c = 0; c < p.NT; ++c) {
-                a += ld_peer_f32(src + (1 + j) * kPsM, (uint32_t)c);
-                g += ld_peer_f32(src + (1 + kPsER + j) * kPsM, (uint32_t)c);
-              }
-              // scale * (f/|f|) . (t/|t|); a zero 'neg' vector gives 0/0 = NaN exactly like the reference (App. B-5)
-              const float s_pos = p.scale * __fdiv_rn(__fdiv_rn(a, fnorm), tn_s[j]);
-              const float s_neg = p.scale * __fdiv_rn(__fdiv_rn(g, fnorm), tn_s[kPsER + j]);
-              sc[j * rows_pad + grow] = s_pos;
-              sc[(kPsER + j) * rows_pad + grow] = s_neg;
-              if (grow < n) p.tail.score_clip[(size_t)(e_lo + rd * kPsER + j) * p.max_n + grow] = s_pos;
+              acc[1 + j] += src[((size_t)c * kNP + 1 + j) * kPsM];
+              acc[1 + kPsER + j] += src[((size_t)c * kNP + 1 + kPsER + j) * kPsM];
+              tn[j] += gather_tn[c * 2 * kPsER + j];
+              tn[kPsER + j] += gather_tn[c * 2 * kPsER + kPsER + j];
             }
           }
         }
+        float fnorm;
+        if (rd == 0) { fnorm = sqrtf(acc[0]); inv_s[grow] = fnorm; }     // |row|; turned into 1/|row| (or 1) by the feature pass
+        else fnorm = inv_s[grow];
+#pragma unroll
+        for (int j = 0; j < kPsER; ++j) {
+          if (j < ne) {
+            // scale * (f/|f|) . (t/|t|); a zero 'neg' vector gives 0/0 = NaN exactly like the reference (App. B-5)
+            const float s_pos = p.scale * __fdiv_rn(__fdiv_rn(acc[1 + j], fnorm), sqrtf(tn[j]));
+            const float s_neg = p.scale * __fdiv_rn(__fdiv_rn(acc[1 + kPsER + j], fnorm), sqrtf(tn[kPsER + j]));
+            sc[j * rows_pad + grow] = s_pos;
+            sc[(kPsER + j) * rows_pad + grow] = s_neg;
+            if (grow < n) p.tail.score_clip[(size_t)(e_lo + rd * kPsER + j) * p.max_n + grow] = s_pos;
+          }
+        }
       }
+      // another exchange follows (next tile / round) or the peers still need the row norms: rank 0 must be done reading first
+      if (tile + 1 < tiles || rd + 1 < rounds || want_out) cluster_sync_all();
     }
-    cluster_sync_all();                                          // #2: nobody reads a peer's shared memory past this point
+    PS_TRACE(11);
     if (rank == 0 && ne > 0) {
-      if (warp < ne) select_tail_warp(p.tail, e_lo + rd * kPsER + warp, n, n_lo, sc + warp * rows_pad, sc + (kPsER + warp) * rows_pad, picks + warp * 9, lane);
+      __syncthreads();                                           // the scores written by warps 0-3 above are read by every tail warp
+      select_tail_block(p.tail, e_lo + rd * kPsER, ne, n, n_lo, sc, rows_pad, picks, box_s, p.tail.score_gem ? sg_s : nullptr, meta_s, warp, lane);
       __syncthreads();
     }
   }
 
   // ---- optional: the pooled (normalised) rows themselves, staged 64 columns at a time through shared memory
-  if (p.out != nullptr) {
+  if (want_out) {
     constexpr int kPitch = kPsPiece + 1;
+    // the row norms live in rank 0 (the last cluster barrier above ordered its writes): every CTA fetches its rows' norms
     __syncthreads();
+    float my_inv[kPsMaxTiles];
+#pragma unroll
+    for (int tile = 0; tile < kPsMaxTiles; ++tile)
+      my_inv[tile] = (tile < tiles && p.normalize) ? __frcp_rn(ld_peer_f32(inv_s + tile * kPsM + my_row, 0u)) : 1.f;
     for (int tile = 0; tile < tiles; ++tile) {
       const int rows = min(kPsM, n - tile * kPsM);
-      const float inv = inv_s[tile * kPsM + my_row];
+      float inv = 1.f;
+#pragma unroll
+      for (int q = 0; q < kPsMaxTiles; ++q) if (q == tile) inv = my_inv[q];
       for (int c0 = 0; c0 < Nw; c0 += kPsPiece) {
-        for (int c = half * 16; c < kPsPiece; c += 32) {
+        for (int c = quarter * 16; c < kPsPiece; c += 64) {
           float v[16];
           tmem_ld16(lane_addr + (uint32_t)(tile * Nw + c0 + c), v);
 #pragma unroll
@@ -405,10 +593,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
         __syncthreads();
       }
     }
+    cluster_sync_all();                                          // rank 0 stays until every peer has read the norms
   }
+  PS_TRACE(12);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
+  PS_TRACE(13);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -428,7 +619,8 @@ static TensorMapEncodeFn tensor_map_encoder() {
 static int pool_score_launch(PoolScoreParams& p, const void* tokens, cudaStream_t st, const char* what) {
   const int D = p.D, L = p.L;
   // columns per CTA: whole 64-column swizzle atoms, at most 8 CTAs per (portable) cluster
-  int nw = 64;
+  // (128 columns per CTA: for D = 512 a cluster of 4 -- sixteen images' clusters of 8 do not all fit the GPCs at once)
+  int nw = D <= 64 ? 64 : 128;
   while (nw < 256 && ceil_div(D, nw) > 8) nw *= 2;
   p.Nw = nw; p.NT = ceil_div(D, nw); p.boxes = nw / 64;
   HGL_REQUIRE(p.NT <= 8, "%s: D=%d needs %d column tiles (> 8 CTAs per cluster)", what, D, p.NT);
@@ -440,12 +632,17 @@ static int pool_score_launch(PoolScoreParams& p, const void* tokens, cudaStream_
   p.tmem_cols = cols;
   p.NKC = ceil_div(L, kPsKC);
   p.stage_bytes = 2 * kPsAHalf + (uint32_t)p.boxes * kPsBBox;
-  const size_t budget = 227 * 1024 - 1024 - kRingBase;
+  p.off_boxes = kOffText + (uint32_t)(2 * kPsER * nw * 4);
+  p.off_sg = p.off_boxes + (uint32_t)(tiles * kPsM * 32);
+  p.off_gather = p.off_sg + (uint32_t)(kPsER * tiles * kPsM * 4);
+  p.off_tn = p.off_gather + (uint32_t)(p.NT * kNP * kPsM * 4);
+  p.off_ring = (p.off_tn + (uint32_t)(p.NT * 2 * kPsER * 4) + 1023u) & ~1023u;
+  const size_t budget = 227 * 1024 - 1024 - p.off_ring;
   int stages = (int)std::min<size_t>(std::min(p.NKC * tiles, 4), budget / p.stage_bytes);
   while ((size_t)stages * p.stage_bytes < kEpEnd) ++stages;      // the epilogue scratch lives in the ring
   HGL_REQUIRE(stages >= 1 && (size_t)stages * p.stage_bytes <= budget && stages <= kPsMaxStages, "%s: shared-memory budget", what);
   p.stages = stages;
-  const size_t smem = 1024 + kRingBase + (size_t)stages * p.stage_bytes;
+  const size_t smem = 1024 + p.off_ring + (size_t)stages * p.stage_bytes;
 
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) { set_error("%s: cuTensorMapEncodeTiled is not available from this driver", what); return HGL_ECUDA; }
@@ -478,6 +675,12 @@ static int pool_score_launch(PoolScoreParams& p, const void* tokens, cudaStream_
 }
 
 }  // namespace hgl
+
+#ifdef HGL_TUNING
+extern "C" HGL_API int hgl_debug_pool_score_trace(long long* host_out, int n_ctas) {
+  return cudaMemcpyFromSymbol(host_out, hgl::g_ps_trace, sizeof(long long) * 16 * (size_t)std::min(n_ctas, 4096)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int64_t hgl_mask_pool_workspace_bytes(int M, int D, int out_dtype) {
   if (M < 0 || D < 1) return -1;

@@ -13,7 +13,7 @@
 // of (up to 4) expressions in shared memory (r*sent + (1-r)*noun, mean of the negatives, their norms), then each WARP owns
 // mask rows of the CTA's slice of the feature matrix: 8-byte (bf16) / 16-byte (f32) coalesced loads, 1 + 2*4 running dot
 // products (|f|^2, f.text_j, f.neg_j), shuffle-tree reductions.  The scores are stored straight into the rank-0 CTA's shared
-// memory (st.shared::cluster); after one cluster barrier rank 0 runs the selection tail, one warp per expression.  One
+// memory (st.shared::cluster); after one cluster barrier rank 0 runs the selection tail, two warps per expression.  One
 // kernel, no workspace, no memset, no atomics.  HBM traffic per image ~ n*De*b + small (SURVEY 8(d) row c).
 #include <algorithm>
 
@@ -50,27 +50,79 @@ __global__ void __launch_bounds__(kScoreThreads) score_select_kernel(const Score
   float* txt = sm;                                  // [2*kEG][De]: rows 0..3 text ensemble, 4..7 negatives
   float* tnorm = txt + 2 * kEG * De;                // [2*kEG]
   float* sc = tnorm + 2 * kEG;                      // [2*kEG][max_n]  rank 0: score_clip / score_clip_Neg rows of the round
-  int* picks = reinterpret_cast<int*>(sc + 2 * kEG * max_n);   // [kScoreWarps][9]
+  int* picks = reinterpret_cast<int*>(sc + 2 * kEG * max_n);   // [kEG][kTailPicks]
+  int64_t* box_s = reinterpret_cast<int64_t*>(picks + kEG * kTailPicks);   // rank 0: the image's boxes [n][4] (8-byte aligned: even float count before)
+  float* sg_s = reinterpret_cast<float*>(box_s + (size_t)max_n * 4);       // rank 0: score_gem rows of the round [kEG][max_n]
+  int* meta_s = reinterpret_cast<int*>(sg_s + kEG * max_n);                // rank 0: (n_other, relaflag) of the round [kEG][2]
+  // what the selection tail needs is fetched while the scores are still being computed (the tail is a dependent chain:
+  // every global round trip it skips is 1-2 us)
+  if (rank == 0 && e_hi > e_lo)
+    for (int i = tid; i < n * 4; i += kScoreThreads) box_s[i] = __ldg(p.tail.boxes + (size_t)n_lo * 4 + i);
+  auto prefetch_tail = [&](int eg, int ne) {
+    if (tid < ne) {
+      meta_s[2 * tid] = p.tail.other_off[eg + tid + 1] - p.tail.other_off[eg + tid];
+      meta_s[2 * tid + 1] = p.tail.relaflag[eg + tid];
+    }
+    if (p.tail.score_gem != nullptr)
+      for (int i = tid; i < ne * n; i += kScoreThreads) {
+        const int j = i / n, c = i - j * n;
+        sg_s[j * max_n + c] = __ldg(p.tail.score_gem + (size_t)(eg + j) * max_n + c);
+      }
+  };
 
   for (int eg = e_lo; eg < e_hi; eg += kEG) {
     const int ne = min(kEG, e_hi - eg);
-    // ---- (a6) text side, Hybridgl_main.py:153-164: warp w -> expression w % 4, ensemble (w < 4) or mean of the negatives
+    if (rank == 0) prefetch_tail(eg, ne);
+    // ---- (a6) text side, Hybridgl_main.py:153-164: warp w -> expression w % 4, ensemble (w < 4) or mean of the negatives;
+    //      the loads of 8 columns per lane are issued together
     {
       const int j = warp & 3, kind = warp >> 2;
       const int e = eg + j;
       if (j < ne) {
         const int k0 = p.other_off[e], k1 = p.other_off[e + 1];
         float acc = 0.f;
-        for (int d = lane; d < De; d += 32) {
-          float v = 0.f;
+        constexpr int kCU = 8;
+        for (int d0 = 0; d0 < De; d0 += 32 * kCU) {
+          float v[kCU];
           if (kind == 0) {
-            v = __fadd_rn(__fmul_rn(p.r, __ldg(p.sent + (size_t)e * De + d)), __fmul_rn(p.one_minus_r, __ldg(p.noun + (size_t)e * De + d)));
+            float a[kCU], g[kCU];
+#pragma unroll
+            for (int ci = 0; ci < kCU; ++ci) {
+              const int d = d0 + lane + 32 * ci;
+              a[ci] = d < De ? __ldg(p.sent + (size_t)e * De + d) : 0.f;
+              g[ci] = d < De ? __ldg(p.noun + (size_t)e * De + d) : 0.f;
+            }
+#pragma unroll
+            for (int ci = 0; ci < kCU; ++ci) v[ci] = __fadd_rn(__fmul_rn(p.r, a[ci]), __fmul_rn(p.one_minus_r, g[ci]));
           } else {
-            for (int k = k0; k < k1; ++k) v = __fadd_rn(v, __ldg(p.others + (size_t)k * De + d));
-            if (k1 > k0) v = __fdiv_rn(v, (float)(k1 - k0));
+#pragma unroll
+            for (int ci = 0; ci < kCU; ++ci) v[ci] = 0.f;
+            for (int kb = k0; kb < k1; kb += 2) {
+              float o[2][kCU];
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int ci = 0; ci < kCU; ++ci) {
+                  const int d = d0 + lane + 32 * ci;
+                  o[u][ci] = (kb + u < k1 && d < De) ? __ldg(p.others + (size_t)(kb + u) * De + d) : 0.f;
+                }
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (kb + u < k1) {
+#pragma unroll
+                  for (int ci = 0; ci < kCU; ++ci) v[ci] = __fadd_rn(v[ci], o[u][ci]);
+                }
+            }
+            if (k1 > k0) {
+#pragma unroll
+              for (int ci = 0; ci < kCU; ++ci) v[ci] = __fdiv_rn(v[ci], (float)(k1 - k0));
+            }
           }
-          txt[(kind * kEG + j) * De + d] = v;
-          acc += v * v;
+#pragma unroll
+          for (int ci = 0; ci < kCU; ++ci) {
+            const int d = d0 + lane + 32 * ci;
+            if (d < De) { txt[(kind * kEG + j) * De + d] = v[ci]; acc += v[ci] * v[ci]; }
+          }
         }
         acc = warp_sum(acc);
         if (lane == 0) tnorm[kind * kEG + j] = sqrtf(acc);
@@ -83,6 +135,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_select_kernel(const Score
       float ff = 0.f, dt[kEG], dn[kEG];
 #pragma unroll
       for (int j = 0; j < kEG; ++j) { dt[j] = 0.f; dn[j] = 0.f; }
+#pragma unroll 4
       for (int d0 = lane * 4; d0 < De; d0 += 128) {
         float f[4];
         if (p.feat_bf16) {
@@ -122,8 +175,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_select_kernel(const Score
       }
     }
     cluster_sync_all();                                          // every CTA's scores have landed in rank 0
-    if (rank == 0 && warp < ne)
-      select_tail_warp(p.tail, eg + warp, n, n_lo, sc + warp * max_n, sc + (kEG + warp) * max_n, picks + warp * 9, lane);
+    if (rank == 0) select_tail_block(p.tail, eg, ne, n, n_lo, sc, max_n, picks, box_s, p.tail.score_gem ? sg_s : nullptr, meta_s, warp, lane);
     if (eg + kEG < e_hi) cluster_sync_all();                     // next round overwrites txt (own) and sc (rank 0)
   }
 }
@@ -163,7 +215,7 @@ extern "C" int hgl_score_select(const void* feat, int feat_dtype, const float* s
   p.tail.score_clip = score_clip; p.tail.idx_hybrid = idx_hybrid; p.tail.idx_final = idx_final; p.tail.top_idx = top_idx; p.tail.blended = blended;
   const int per_image = (B == 1) ? std::min(M, max_n) : std::min(max_n, M);
   p.CS = std::max(1, std::min(8, ceil_div(std::max(per_image, 1), 16)));       // >= 2 rows per warp before another CTA pays off
-  const size_t smem = ((size_t)2 * kEG * De + 2 * kEG + (size_t)2 * kEG * max_n) * 4 + (size_t)kScoreWarps * 9 * 4 + 16;
+  const size_t smem = ((size_t)2 * kEG * De + 2 * kEG + (size_t)2 * kEG * max_n) * 4 + (size_t)kEG * kTailPicks * 4 + (size_t)max_n * 32 + (size_t)kEG * max_n * 4 + 2 * kEG * 4 + 16;
   HGL_REQUIRE(smem <= 227 * 1024, "hgl_score_select: De=%d max_n=%d needs %zu B of shared memory", De, max_n, smem);
   {
     const int rc_s = ensure_dyn_smem(reinterpret_cast<const void*>(score_select_kernel), smem, "hgl_score_select");

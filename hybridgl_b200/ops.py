@@ -383,7 +383,7 @@ def heat_tables(heat: torch.Tensor, dirflag: torch.Tensor, H: int, W: int, works
 
 
 def grid_heat_pool_rows(bits: torch.Tensor, width: int, g: int, heat_shape, black: torch.Tensor, mask_off: Optional[torch.Tensor],
-                        expr_off: Optional[torch.Tensor], max_n: int, workspace: torch.Tensor):
+                        expr_off: Optional[torch.Tensor], max_n: int, workspace: torch.Tensor, out=None):
     """Second half of grid_heat_pool: the pass over the packed masks, after heat_tables(...) on the same workspace.
     heat_shape = heat.shape of the tensor given to heat_tables.  Returns (grid, area, score_gem) like grid_heat_pool."""
     _req(bits, torch.int32, "bits", 3)
@@ -395,9 +395,12 @@ def grid_heat_pool_rows(bits: torch.Tensor, width: int, g: int, heat_shape, blac
     B = 1 if mask_off is None else mask_off.numel() - 1
     moff = _offsets(mask_off, B, "mask_off")
     eoff = _offsets(expr_off, B, "expr_off")
-    grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
-    area = torch.empty((M,), dtype=torch.int32, device=bits.device)
-    out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
+    if out is not None:                      # caller-supplied (grid [M,g,g] f32, area [M] i32, score_gem [E,max_n] f32)
+        grid, area, out = out
+    else:
+        grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
+        area = torch.empty((M,), dtype=torch.int32, device=bits.device)
+        out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
     check(_lib.load().hgl_grid_heat_pool_rows(bits.data_ptr(), _ptr(moff), B, M, H, W, g, grid.data_ptr(), area.data_ptr(), hh, hw,
                                               _ptr(eoff), black.data_ptr(), E, max_n, out.data_ptr(), workspace.data_ptr(), _stream()),
           "hgl_grid_heat_pool_rows")
@@ -433,7 +436,7 @@ def pool_score_select(weights: torch.Tensor, tokens: torch.Tensor, sent: torch.T
                       other_off: torch.Tensor, boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],
                       mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
                       logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
-                      want_features: bool = False, dtype: torch.dtype = torch.bfloat16):
+                      want_features: bool = False, dtype: torch.dtype = torch.bfloat16, out=None):
     """mask_pool + score_select in ONE kernel (hgl_pool_score_select): the pooled, normalised rows are scored straight from
     the f32 TMEM accumulators and only leave the SM when want_features is set.  Returns the score_select dict
     (+ "features" [M,D] of `dtype` when want_features)."""
@@ -465,12 +468,16 @@ def pool_score_select(weights: torch.Tensor, tokens: torch.Tensor, sent: torch.T
         if score_gem.shape != (E, max_n):
             raise ValueError("score_gem must be [E, max_n]")
     dev = w.device
-    feats = torch.empty((M, D), dtype=dtype, device=dev) if want_features else None
-    score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
-    idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
-    idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
-    top = torch.empty((E, 3), dtype=torch.int32, device=dev)
-    blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    if out is not None:          # caller-supplied result dict (score_clip, idx_hybrid, idx_final, top_idx, blended[, features])
+        score_clip, idx_h, idx_f, top, blended = (out[k] for k in ("score_clip", "idx_hybrid", "idx_final", "top_idx", "blended"))
+        feats = out.get("features") if want_features else None
+    else:
+        feats = torch.empty((M, D), dtype=dtype, device=dev) if want_features else None
+        score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
+        idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
+        idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
+        top = torch.empty((E, 3), dtype=torch.int32, device=dev)
+        blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
     check(_lib.load().hgl_pool_score_select(w.data_ptr(), tok.data_ptr(), _ptr(moff), _ptr(eoff), B, M, E, max_n, L, D,
                                             sent.data_ptr(), noun.data_ptr(), others.data_ptr(), other_off.data_ptr(),
                                             boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
@@ -488,7 +495,7 @@ def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, oth
                  boxes: torch.Tensor, relaflag: torch.Tensor, score_gem: Optional[torch.Tensor],
                  mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None,
                  max_n: Optional[int] = None, logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
-                 workspace: Optional[torch.Tensor] = None):
+                 workspace: Optional[torch.Tensor] = None, out=None):
     """Hybridgl_main.py:153-196,225-227 for a batch.  Returns dict(score_clip[E,max_n], idx_hybrid[E], idx_final[E],
     top_idx[E,3], blended[E,3])."""
     _req(feat, (torch.float32, torch.bfloat16), "feat", 2)
@@ -514,11 +521,14 @@ def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, oth
         if score_gem.shape != (E, max_n):
             raise ValueError("score_gem must be [E, max_n]")
     dev = feat.device
-    score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
-    idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
-    idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
-    top = torch.empty((E, 3), dtype=torch.int32, device=dev)
-    blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    if out is not None:          # caller-supplied result dict
+        score_clip, idx_h, idx_f, top, blended = (out[k] for k in ("score_clip", "idx_hybrid", "idx_final", "top_idx", "blended"))
+    else:
+        score_clip = torch.empty((E, max_n), dtype=torch.float32, device=dev)
+        idx_h = torch.empty((E,), dtype=torch.int64, device=dev)
+        idx_f = torch.empty((E,), dtype=torch.int64, device=dev)
+        top = torch.empty((E, 3), dtype=torch.int32, device=dev)
+        blended = torch.empty((E, 3), dtype=torch.float32, device=dev)
     check(_lib.load().hgl_score_select(feat.data_ptr(), _dt(feat.dtype), sent.data_ptr(), noun.data_ptr(), others.data_ptr(),
                                        other_off.data_ptr(), boxes.data_ptr(), relaflag.data_ptr(), _ptr(score_gem),
                                        _ptr(moff), _ptr(eoff), B, M, E, De, max_n, float(logit_scale_exp), float(r), float(alpha),
@@ -530,7 +540,7 @@ def score_select(feat: torch.Tensor, sent: torch.Tensor, noun: torch.Tensor, oth
 # ---- (a13) --------------------------------------------------------------------------------------------
 def iou_accumulate(masks: torch.Tensor, target: torch.Tensor, idx_hybrid: torch.Tensor, idx_final: torch.Tensor,
                    cum: Optional[torch.Tensor], mask_off: Optional[torch.Tensor] = None,
-                   expr_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   expr_off: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Compute_IoU utils.py:365-384 for both picks of every expression.  Returns iu int64 [E,4] =
     (I_hybrid, U_hybrid, I_final, U_final) and adds the column sums into cum int64 [4].
     `masks`: bool/u8 [M,H,W], or the packed int32 [M,H,ceil(W/32)] (the frame size is then taken from `target`)."""
@@ -554,7 +564,7 @@ def iou_accumulate(masks: torch.Tensor, target: torch.Tensor, idx_hybrid: torch.
     eoff = _offsets(expr_off, B, "expr_off")
     if cum is not None:
         _req(cum, torch.int64, "cum", 1)
-    iu = torch.empty((E, 4), dtype=torch.int64, device=m.device)
+    iu = out if out is not None else torch.empty((E, 4), dtype=torch.int64, device=m.device)
     fn = _lib.load().hgl_iou_bits if packed else _lib.load().hgl_iou
     check(fn(m.data_ptr(), t.data_ptr(), idx_hybrid.data_ptr(), idx_final.data_ptr(), _ptr(moff), _ptr(eoff),
              B, M, E, H, W, iu.data_ptr(), _ptr(cum), _stream()), "hgl_iou_bits" if packed else "hgl_iou")

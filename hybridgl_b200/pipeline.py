@@ -30,15 +30,18 @@ class ScoringPath:
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
                  feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True,
-                 keep_features: bool = False):
+                 keep_features: bool = False, chunks: int = 2):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
         under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
-        keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"]."""
+        keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"].
+        chunks: groups of images a batch is cut into inside run() (see there); 1 = every stage once per batch."""
         if feature_source not in ("supplied", "tokens"):
             raise ValueError(feature_source)
         self.feature_source = feature_source
         self.keep_features = keep_features
+        self.chunks = max(1, int(chunks))
+        self._plans: Dict[tuple, list] = {}
         ops.device_ok()
         self.size, self.grid = size, grid
         self.prep_dtype, self.antialias, self.background = prep_dtype, antialias, background
@@ -105,26 +108,79 @@ class ScoringPath:
     def _span(self, name: str):
         return ScoringPath._Span(self, name)
 
-    def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    # ---- chunking ------------------------------------------------------------------------------------------------------
+    def _chunk_plan(self, batch, chunks: int, host_off=None):
+        """Cut a batch into `chunks` groups of whole images.  Returns a list of dicts with the image / mask / expression ranges and
+        re-based offset tensors.  Needs the offsets on the host: free when the caller has them (run_host), one small
+        device->host read the first time a device-resident batch is seen otherwise (cached per offsets tensor)."""
+        moff, eoff = batch["mask_off"], batch["expr_off"]
+        B = moff.numel() - 1
+        chunks = max(1, min(chunks, B))
+        key = (moff.data_ptr(), moff._version, eoff.data_ptr(), eoff._version, chunks)
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        if self._capturing:
+            raise RuntimeError("ScoringPath: a batch must run eagerly once before it is captured (capture() does)")
+        mo = (host_off[0] if host_off is not None else moff).tolist()
+        eo = (host_off[1] if host_off is not None else eoff).tolist()
+        bounds = sorted({(c * B) // chunks for c in range(chunks + 1)})
+        plan = []
+        for b0, b1 in zip(bounds[:-1], bounds[1:]):
+            m0, m1, e0, e1 = mo[b0], mo[b1], eo[b0], eo[b1]
+            whole = b0 == 0 and b1 == B
+            plan.append(dict(b=(b0, b1), m=(m0, m1), e=(e0, e1),
+                             mask_off=moff if whole else (moff[b0:b1 + 1] - m0).contiguous(),
+                             expr_off=eoff if whole else (eoff[b0:b1 + 1] - e0).contiguous()))
+        if len(self._plans) > 32:
+            self._plans.clear()
+        self._plans[key] = plan
+        return plan
+
+    @staticmethod
+    def _chunk_view(batch, ch, rle: bool):
+        """The tensors of one chunk: views (no copies) of the batch's tensors; `others` / `rle_counts` stay whole because
+        other_off / rle_off index them absolutely."""
+        (b0, b1), (m0, m1), (e0, e1) = ch["b"], ch["m"], ch["e"]
+        v = dict(image=batch["image"][b0:b1], target=batch["target"][b0:b1], boxes=batch["boxes"][m0:m1],
+                 sent=batch["sent"][e0:e1], noun=batch["noun"][e0:e1], others=batch["others"], other_off=batch["other_off"][e0:e1 + 1],
+                 heat=batch["heat"][e0:e1], dirflag=batch["dirflag"][e0:e1], relaflag=batch["relaflag"][e0:e1], black=batch["black"][e0:e1],
+                 mask_off=ch["mask_off"], expr_off=ch["expr_off"])
+        if rle:
+            v["rle_counts"], v["rle_off"] = batch["rle_counts"], batch["rle_off"][m0:m1 + 1]
+        else:
+            v["masks"] = batch["masks"][m0:m1]
+        if "tokens" in batch:
+            v["tokens"] = batch["tokens"][b0:b1]
+        if "features" in batch:
+            v["features"] = batch["features"][m0:m1]
+        return v
+
+    def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None, host_off=None) -> Dict[str, torch.Tensor]:
         """One pass over a device-resident batch.  Returns device tensors (see OUTPUT_KEYS) plus the prep
         outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M].
 
-        Stage graph (self.overlap=True), four streams forked from / joined to the caller's stream:
-            side  pack (or RLE decode) ---------+--> mask grid + heat-map pooling -> [mask pooling] -> score/select -> IoU
-            pre   blur -> prep setup ------+    |         ^
-            tab   heat-map tables ---------|----|---------+
-            main  (caller's stream)        +----+--> prep main (the bandwidth-bound bulk)
-        The pack runs with a small SM footprint, so the frame-only and heat-map-only kernels run beside it; the small,
-        latency-bound kernels after the pack run at high priority in the shadow of the prep writes.  With overlap=False every
-        stage is launched in order on the caller's stream."""
+        Stage graph (self.overlap=True), four streams forked from / joined to the caller's stream; the batch is cut into
+        self.chunks groups of images (A, B, ...) and every stage is launched once per group, stage by stage:
+            side  pack A, pack B | mask grid + heat-map pooling A, B | pooling + scoring A, B | IoU A, B
+            pre   blur A, prep setup A, blur B, prep setup B
+            tab   heat-map tables A, B
+            main  (caller's stream)  prep main A (after pack A, setup A), prep main B (after pack B, setup B)
+        Only pack and prep main are bandwidth-bound; everything else is small and latency-bound and runs up to 3x slower while HBM
+        is saturated.  With one group the step is pack -> [idle HBM while blur -> setup finish] -> prep -> [idle GPU while the
+        scoring chain finishes]; with two or more, group B's pack and small kernels run in the shadow of group A's prep writes and
+        the bandwidth-bound kernels follow each other without a gap.  With overlap=False every stage is launched in order on the
+        caller's stream."""
         img = batch["image"]
         B, H, W, _ = img.shape
         rle = "rle_counts" in batch          # proposals as SAM uncompressed RLE instead of byte masks
-        masks = None if rle else batch["masks"]
-        M = batch["rle_off"].numel() - 1 if rle else masks.shape[0]
-        moff, eoff = batch["mask_off"], batch["expr_off"]
+        M = batch["rle_off"].numel() - 1 if rle else batch["masks"].shape[0]
+        E = batch["sent"].shape[0]
+        moff = batch["mask_off"]
         lib = ops._lib.load()
-        self._check_max_n(moff, max_n)
+        self._check_max_n(moff, max_n, None if host_off is None else host_off[0])
+        plan = self._chunk_plan(batch, self.chunks if self.overlap else 1, host_off)
+        views = [self._chunk_view(batch, ch, rle) for ch in plan]
         main = torch.cuda.current_stream()
         side = pre = tab = main
         if self.overlap:
@@ -135,95 +191,150 @@ class ScoringPath:
             side, pre, tab = self._side, self._pre, self._tab
             for s_ in (side, pre, tab):
                 s_.wait_stream(main)
+        if self.events is not None and (self.events_only is None or "t0" in self.events_only):
+            t0 = torch.cuda.Event(enable_timing=True, external=self._capturing)      # origin of a stage timeline (bench.py)
+            t0.record(main)
+            self.events.append(("t0", t0, t0))
 
-        # ---- chain S (side): the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
+        def mark():
+            if not self.overlap:
+                return None
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev
+
+        S, g = self.size, self.grid
+        WW = (W + 31) // 32
+        bits = self._get("bits", (M, H, WW), torch.int32)
+        local = self._get("local", (M, 3, S, S), self.prep_dtype)
+        glob = self._get("global", (M, 3, S, S), self.prep_dtype)
+        blur_all = self._get("blur", img.shape, torch.uint8) if self.background == "blur" else None
+        heat = batch["heat"]           # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
+        raw = tuple(heat.shape[1:]) != (H, W)
+        split = self.antialias and E > 0 and M > 0
+        use_tokens = self.feature_source == "tokens" and features is None
+        feats_in = features if features is not None else batch.get("features")
+        n_ch = len(plan)
+
+        # ---- chain S (side), first stage: the one pass that produces the packed masks (from byte masks, or from SAM's RLE)
+        ev_pack = [None] * n_ch
         with torch.cuda.stream(side):
-            bits = self._get("bits", (M, H, (W + 31) // 32), torch.int32)
-            if rle:
-                with self._span("rle"):
-                    ops.rle_to_bits(batch["rle_counts"], batch["rle_off"], H, W, out=bits)
-            else:
-                with self._span("pack"):
-                    ops.pack_masks(masks, out=bits)
-            ev_pack = None
-            if self.overlap:
-                ev_pack = torch.cuda.Event()
-                ev_pack.record()
+            for c, (ch, v) in enumerate(zip(plan, views)):
+                m0, m1 = ch["m"]
+                if rle:
+                    with self._span("rle"):
+                        ops.rle_to_bits(v["rle_counts"], v["rle_off"], H, W, out=bits[m0:m1])
+                else:
+                    with self._span("pack"):
+                        ops.pack_masks(v["masks"], out=bits[m0:m1])
+                ev_pack[c] = mark()
 
         # ---- chain F (frames only): blur -> per-image half of prep (answer planes).  Runs beside the mask pack.
-        local = self._get("local", (M, 3, self.size, self.size), self.prep_dtype)
-        glob = self._get("global", (M, 3, self.size, self.size), self.prep_dtype)
-        pws = self._get("prep_ws", (max(lib.hgl_prep_workspace_bytes(B, self.size, ops._dt(self.prep_dtype)), 1),), torch.uint8)
+        ev_setup = [None] * n_ch
+        pws = []
         with torch.cuda.stream(pre):
-            with self._span("blur"):
-                blur = ops.gaussian_blur15(img, out=self._get("blur", img.shape, torch.uint8)) if self.background == "blur" else None
-            with self._span("prep_setup"):
-                ops.prep_setup(img, blur, self.size, background=self.background, dtype=self.prep_dtype, workspace=pws)
-            ev_setup = None
-            if self.overlap:
-                ev_setup = torch.cuda.Event()
-                ev_setup.record()
+            for c, (ch, v) in enumerate(zip(plan, views)):
+                b0, b1 = ch["b"]
+                pws.append(self._get(f"prep_ws{c}", (max(lib.hgl_prep_workspace_bytes(b1 - b0, S, ops._dt(self.prep_dtype)), 1),), torch.uint8))
+                with self._span("blur"):
+                    blur = ops.gaussian_blur15(v["image"], out=blur_all[b0:b1]) if self.background == "blur" else None
+                with self._span("prep_setup"):
+                    ops.prep_setup(v["image"], blur, S, background=self.background, dtype=self.prep_dtype, workspace=pws[c])
+                ev_setup[c] = mark()
 
         # ---- chain T (heat-maps only): the table half of the pooling pass, also beside the mask pack
-        heat = batch["heat"]           # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
-        E = batch["sent"].shape[0]
-        raw = tuple(heat.shape[1:]) != (H, W)
-        need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, E, H, W, self.grid, max_n, heat.shape[1], heat.shape[2]) if raw
-                else lib.hgl_grid_heat_pool_workspace_bytes(B, M, E, H, W, self.grid, max_n))
-        ws = self._get("heat_ws", (need,), torch.uint8)
-        split = self.antialias and E > 0 and M > 0
-        ev_tables = None
+        ev_tables = [None] * n_ch
+        hws = []
+        for c, (ch, v) in enumerate(zip(plan, views)):
+            (b0, b1), (m0, m1), (e0, e1) = ch["b"], ch["m"], ch["e"]
+            need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n, heat.shape[1], heat.shape[2]) if raw
+                    else lib.hgl_grid_heat_pool_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n))
+            hws.append(self._get(f"heat_ws{c}", (need,), torch.uint8))
         if split:
             with torch.cuda.stream(tab):
-                with self._span("heat_tables"):
-                    ops.heat_tables(heat, batch["dirflag"], H, W, ws)
-                if self.overlap:
-                    ev_tables = torch.cuda.Event()
-                    ev_tables.record()
+                for c, v in enumerate(views):
+                    if v["heat"].shape[0] == 0:
+                        continue
+                    with self._span("heat_tables"):
+                        ops.heat_tables(v["heat"], v["dirflag"], H, W, hws[c])
+                    ev_tables[c] = mark()
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
-            feats = features if features is not None else batch.get("features")
-            if ev_tables is not None:
-                side.wait_event(ev_tables)
-            with self._span("grid_heat_pool"):
-                if split:              # mask grid + heat-map pooling share one pass over the packed masks
-                    grid, area, score_gem = ops.grid_heat_pool_rows(bits, W, self.grid, heat.shape, batch["black"], moff, eoff, max_n, ws)
-                elif self.antialias:
-                    grid, area, score_gem = ops.grid_heat_pool(bits, W, self.grid, heat, batch["dirflag"], batch["black"],
-                                                               moff, eoff, max_n, workspace=ws)
-                else:
-                    if raw:
-                        heat = ops.heat_resize_aa(heat, H, W, out=self._get("heat_full", (E, H, W), torch.float32))
-                    grid, area = ops.masks_to_grid(bits, self.grid, antialias=False, want_area=True, width=W)
-                    score_gem = ops.heat_pool(heat, batch["dirflag"], batch["black"], bits, moff, eoff, max_n, workspace=ws)
+            grid = torch.empty((M, g, g), dtype=torch.float32, device=self.device)
+            area = torch.empty((M,), dtype=torch.int32, device=self.device)
+            score_gem = torch.empty((E, max_n), dtype=torch.float32, device=self.device)
+            res = dict(score_clip=torch.empty((E, max_n), dtype=torch.float32, device=self.device),
+                       idx_hybrid=torch.empty((E,), dtype=torch.int64, device=self.device),
+                       idx_final=torch.empty((E,), dtype=torch.int64, device=self.device),
+                       top_idx=torch.empty((E, 3), dtype=torch.int32, device=self.device),
+                       blended=torch.empty((E, 3), dtype=torch.float32, device=self.device))
+            iu = torch.empty((E, 4), dtype=torch.int64, device=self.device)
+            feats = feats_in
+            if use_tokens and self.keep_features:
+                feats = torch.empty((M, batch["tokens"].shape[2]), dtype=torch.bfloat16, device=self.device)
+            for c, (ch, v) in enumerate(zip(plan, views)):
+                (m0, m1), (e0, e1) = ch["m"], ch["e"]
+                if ev_tables[c] is not None:
+                    side.wait_event(ev_tables[c])
+                cb, ch_moff, ch_eoff = bits[m0:m1], v["mask_off"], v["expr_off"]
+                with self._span("grid_heat_pool"):
+                    if m1 == m0:
+                        pass
+                    elif split and e1 > e0:    # mask grid + heat-map pooling share one pass over the packed masks
+                        ops.grid_heat_pool_rows(cb, W, g, v["heat"].shape, v["black"], ch_moff, ch_eoff, max_n, hws[c],
+                                                out=(grid[m0:m1], area[m0:m1], score_gem[e0:e1]))
+                    elif self.antialias:
+                        g_, a_, s_ = ops.grid_heat_pool(cb, W, g, v["heat"], v["dirflag"], v["black"], ch_moff, ch_eoff, max_n, workspace=hws[c])
+                        grid[m0:m1].copy_(g_); area[m0:m1].copy_(a_); score_gem[e0:e1].copy_(s_)
+                    else:
+                        hv = v["heat"]
+                        if raw:
+                            hv = ops.heat_resize_aa(hv, H, W, out=self._get(f"heat_full{c}", (e1 - e0, H, W), torch.float32))
+                        g_, a_ = ops.masks_to_grid(cb, g, antialias=False, want_area=True, width=W)
+                        grid[m0:m1].copy_(g_); area[m0:m1].copy_(a_)
+                        score_gem[e0:e1].copy_(ops.heat_pool(hv, v["dirflag"], v["black"], cb, ch_moff, ch_eoff, max_n, workspace=hws[c]))
 
         # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
-        if ev_pack is not None:
-            main.wait_event(ev_pack)
-            main.wait_event(ev_setup)
-        with self._span("prep"):
-            ops.prep_main(bits, (B, H, W), self.size, pws, mask_off=moff, max_n=max_n, dtype=self.prep_dtype, out=(local, glob))
+        for c, (ch, v) in enumerate(zip(plan, views)):
+            (b0, b1), (m0, m1) = ch["b"], ch["m"]
+            if ev_pack[c] is not None:
+                main.wait_event(ev_pack[c])
+                main.wait_event(ev_setup[c])
+            if m1 == m0:
+                continue
+            with self._span("prep"):
+                ops.prep_main(bits[m0:m1], (b1 - b0, H, W), S, pws[c], mask_off=v["mask_off"], max_n=max_n, dtype=self.prep_dtype,
+                              out=(local[m0:m1], glob[m0:m1]))
 
-        # ---- chain S, last part: mask pooling -> score/select -> IoU (small kernels, in the shadow of the prep writes)
+        # ---- chain S, last part: pooling + scoring + selection -> IoU (small kernels, in the shadow of the prep writes)
         with torch.cuda.stream(side):
-            if self.feature_source == "tokens" and features is None:
-                # pooling (tcgen05) + cosine scoring + selection tail in ONE launch; the pooled rows stay on the SM unless asked for
-                with self._span("pool_score"):
-                    res = ops.pool_score_select(grid, batch["tokens"], batch["sent"], batch["noun"], batch["others"], batch["other_off"],
-                                                batch["boxes"], batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp,
-                                                self.r, self.alpha, want_features=self.keep_features, dtype=torch.bfloat16)
-                feats = res.pop("features", None)
-            else:
-                with self._span("score_select"):
-                    res = ops.score_select(feats, batch["sent"], batch["noun"], batch["others"], batch["other_off"], batch["boxes"],
-                                           batch["relaflag"], score_gem, moff, eoff, max_n, self.logit_scale_exp, self.r, self.alpha)
-            with self._span("iou"):
-                iu = ops.iou_accumulate(bits if rle else masks, batch["target"], res["idx_hybrid"], res["idx_final"], self.cum, moff, eoff)
+            for c, (ch, v) in enumerate(zip(plan, views)):
+                (m0, m1), (e0, e1) = ch["m"], ch["e"]
+                if e1 == e0:
+                    continue
+                sub = {k: t[e0:e1] for k, t in res.items()}
+                if use_tokens:
+                    # pooling (tcgen05) + cosine scoring + selection tail in ONE launch; the pooled rows stay on the SM unless asked for
+                    if self.keep_features:
+                        sub["features"] = feats[m0:m1]
+                    with self._span("pool_score"):
+                        ops.pool_score_select(grid[m0:m1], v["tokens"], v["sent"], v["noun"], v["others"], v["other_off"], v["boxes"],
+                                              v["relaflag"], score_gem[e0:e1], v["mask_off"], v["expr_off"], max_n, self.logit_scale_exp,
+                                              self.r, self.alpha, want_features=self.keep_features, dtype=torch.bfloat16, out=sub)
+                else:
+                    with self._span("score_select"):
+                        ops.score_select(feats_in[m0:m1], v["sent"], v["noun"], v["others"], v["other_off"], v["boxes"], v["relaflag"],
+                                         score_gem[e0:e1], v["mask_off"], v["expr_off"], max_n, self.logit_scale_exp, self.r, self.alpha, out=sub)
+                with self._span("iou"):
+                    ops.iou_accumulate(bits[m0:m1] if rle else v["masks"], v["target"], sub["idx_hybrid"], sub["idx_final"], self.cum,
+                                       v["mask_off"], v["expr_off"], out=iu[e0:e1])
         if self.overlap:
             main.wait_stream(side)
             main.wait_stream(tab)          # (already ordered before the mask pass; keeps the join explicit when split is off)
-        res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits, features=feats)
+            main.wait_stream(pre)
+        res.update(score_gem=score_gem, iu=iu, local_imgs=local, global_imgs=glob, grid=grid, area=area, bits=bits,
+                   features=feats if (not use_tokens or self.keep_features) else None)
         return res
 
     def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None) -> "GraphStep":
@@ -257,7 +368,7 @@ class ScoringPath:
     LAUNCHES_PER_RUN = 10
 
     def launches_per_run(self) -> int:
-        return self.LAUNCHES_PER_RUN
+        return self.LAUNCHES_PER_RUN * self.chunks        # every stage once per image group
 
     def input_keys(self, host_batch=None):
         skip = {"features" if self.feature_source == "tokens" else "tokens"}
@@ -304,7 +415,7 @@ class ScoringPath:
         st = self._slot_buffers(0, host_batch)
         self._check_max_n(st["in"]["mask_off"], max_n, host_batch["mask_off"])
         self._h2d(st, host_batch)
-        out = self._d2h(st, self.run(st["in"], max_n))
+        out = self._d2h(st, self.run(st["in"], max_n, host_off=(host_batch["mask_off"], host_batch["expr_off"])))
         torch.cuda.current_stream().synchronize()
         return out
 
@@ -332,7 +443,7 @@ class ScoringPath:
                 self._h2d(st, hb)
                 ev = torch.cuda.Event()
                 ev.record()
-            return st, ev
+            return st, ev, hb
 
         it = iter(host_batches)
         hb = next(it, None)
@@ -342,19 +453,21 @@ class ScoringPath:
         pending = []
         k = 0
         while nxt is not None:
-            st, ev_in = nxt
+            st, ev_in, hb_cur = nxt
             hb = next(it, None)
             nxt = stage_in(k + 1, hb) if hb is not None else None      # queue the next batch's copies before this batch's kernels
             main.wait_event(ev_in)
+            offs = (hb_cur["mask_off"], hb_cur["expr_off"])
             if graph:
-                if st["graph"] is None:
+                # a captured step has the image-group boundaries (pointers, sizes) baked in: it serves batches with the SAME offsets
+                same = st["graph"] is not None and all(torch.equal(a, b_) for a, b_ in zip(st["graph_off"], offs))
+                if not same:
                     main.synchronize()                                  # capture() runs the step once eagerly on these inputs
-                    cum0 = self.cum.clone()
                     st["graph"] = self.capture(st["in"], max_n)
-                    self.cum.copy_(cum0)
+                    st["graph_off"] = tuple(t.clone() for t in offs)
                 res = st["graph"].replay()
             else:
-                res = self.run(st["in"], max_n)
+                res = self.run(st["in"], max_n, host_off=offs)
             out = self._d2h(st, res)
             ev_out = torch.cuda.Event()
             ev_out.record()
