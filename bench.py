@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="strong-scaling evaluation sweep (BASELINE.json configs[4]; use with --workload 5)")
     ap.add_argument("--sweep-images", type=int, default=4096)
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
-    ap.add_argument("--chunks", type=int, default=2, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
+    ap.add_argument("--chunks", type=int, default=1, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
                     help="tokens: pool dense patch tokens under the grid masks on the tensor cores (hgl_mask_pool) and score those; "

@@ -28,13 +28,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .clip_text import tokenize  # noqa: F401  (re-export: `clip.tokenize` of the reference's loop, Hybridgl_main.py:146-160)
 
 # name -> (embed_dim, image_resolution, layers, width, patch, heads); last_layer as in model/backbone.py:16-21
 # (ViT-L/14@336 is the SURVEY section 8(c) extension: last_layer=22, heads=16)
+# text tower (clip/model.py CLIP.__init__): context 77, vocabulary 49408, width / heads / layers per model
 ARCH = {
-    "ViT-B/32": dict(embed_dim=512, res=224, layers=12, width=768, patch=32, heads=12, last_layer=10),
-    "ViT-B/16": dict(embed_dim=512, res=224, layers=12, width=768, patch=16, heads=12, last_layer=10),
-    "ViT-L/14@336px": dict(embed_dim=768, res=336, layers=24, width=1024, patch=14, heads=16, last_layer=22),
+    "ViT-B/32": dict(embed_dim=512, res=224, layers=12, width=768, patch=32, heads=12, last_layer=10, text_width=512, text_heads=8, text_layers=12),
+    "ViT-B/16": dict(embed_dim=512, res=224, layers=12, width=768, patch=16, heads=12, last_layer=10, text_width=512, text_heads=8, text_layers=12),
+    "ViT-L/14@336px": dict(embed_dim=768, res=336, layers=24, width=1024, patch=14, heads=16, last_layer=22, text_width=768, text_heads=12,
+                           text_layers=12),
 }
 
 
@@ -71,12 +74,12 @@ class ResBlock(nn.Module):
                                               ("c_proj", nn.Linear(4 * width, width))]))
         self.ln_2 = LayerNormF32(width)
 
-    def attention(self, h: torch.Tensor, cls_bias: Optional[torch.Tensor]) -> torch.Tensor:
+    def attention(self, h: torch.Tensor, cls_bias: Optional[torch.Tensor], causal: bool = False) -> torch.Tensor:
         M, L1, D = h.shape
         hd = D // self.heads
         qkv = F.linear(h, self.attn.in_proj_weight, self.attn.in_proj_bias).view(M, L1, 3, self.heads, hd)
         q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))             # [M, heads, L1, hd]
-        o = F.scaled_dot_product_attention(q, k, v)                             # every query row, unmasked
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal)           # every query row; causal = the text tower's mask
         if cls_bias is not None:
             s = torch.matmul(q[:, :, :1].float(), k.float().transpose(-1, -2)) / math.sqrt(hd)    # [M, heads, 1, L1]
             s = s + cls_bias[:, None, None, :]
@@ -84,8 +87,8 @@ class ResBlock(nn.Module):
             o = torch.cat([o0, o[:, :, 1:]], dim=2)
         return self.attn.out_proj(o.transpose(1, 2).reshape(M, L1, D))
 
-    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-        x = x + self.attention(self.ln_1(x), cls_bias)
+    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None, causal: bool = False) -> torch.Tensor:
+        x = x + self.attention(self.ln_1(x), cls_bias, causal)
         h = self.mlp.c_fc(self.ln_2(x))
         h = h * torch.sigmoid(1.702 * h)                                        # QuickGELU
         return x + self.mlp.c_proj(h)
@@ -124,12 +127,47 @@ class VisionTransformer(nn.Module):
 
 
 class _Clip(nn.Module):
-    """Only what the path touches of clip.model.CLIP: `visual` and `logit_scale` (text encoder: inputs of the path)."""
+    """What the evaluation loop touches of clip.model.CLIP: `visual`, `encode_text` (third_party/modified_CLIP/clip/model.py:414-431) and
+    `logit_scale`, with CLIP's state_dict names (token_embedding, positional_embedding, transformer.resblocks.*, ln_final,
+    text_projection) so that real weights load unchanged."""
 
     def __init__(self, a):
         super().__init__()
         self.visual = VisionTransformer(a["res"], a["patch"], a["width"], a["layers"], a["heads"], a["embed_dim"])
+        tw, th, tl = a.get("text_width", 512), a.get("text_heads", 8), a.get("text_layers", 12)
+        self.context_length, self.vocab_size = a.get("context_length", 77), a.get("vocab_size", 49408)
+        self.token_embedding = nn.Embedding(self.vocab_size, tw)
+        self.positional_embedding = nn.Parameter(torch.empty(self.context_length, tw))
+        self.transformer = _Transformer(tw, tl, th)
+        self.ln_final = LayerNormF32(tw)
+        self.text_projection = nn.Parameter(torch.empty(tw, a["embed_dim"]))
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))     # clip/model.py CLIP.__init__
+        # clip/model.py initialize_parameters (random-init stand-in for the checkpoint that is unavailable offline)
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        nn.init.normal_(self.text_projection, std=tw ** -0.5)
+        proj_std, attn_std, fc_std = (tw ** -0.5) * ((2 * tl) ** -0.5), tw ** -0.5, (2 * tw) ** -0.5
+        for blk in self.transformer.resblocks:
+            nn.init.normal_(blk.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(blk.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(blk.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(blk.mlp.c_proj.weight, std=proj_std)
+
+    @property
+    def dtype(self):
+        return self.visual.conv1.weight.dtype
+
+    @torch.no_grad()
+    def encode_text(self, text: torch.Tensor, target_noun_index=None) -> torch.Tensor:
+        """clip/model.py:414-431: token + positional embedding, causal transformer, ln_final, the <|endoftext|> position (the
+        highest token id of every row; or target_noun_index + 1 when given) projected by text_projection -> [n, embed_dim]."""
+        text = text.to(self.token_embedding.weight.device)
+        x = self.token_embedding(text.long()).to(self.dtype) + self.positional_embedding.to(self.dtype)
+        for blk in self.transformer.resblocks:
+            x = blk(x, causal=True)
+        x = self.ln_final(x).to(self.dtype)
+        pos = (target_noun_index + 1) if target_noun_index else text.argmax(dim=-1)
+        return x[torch.arange(x.shape[0], device=x.device), pos] @ self.text_projection
 
 
 class CLIPViTFM(nn.Module):
@@ -153,12 +191,23 @@ class CLIPViTFM(nn.Module):
         return self.model.visual.conv1.weight.dtype
 
     def load_clip_state_dict(self, sd: dict) -> None:
-        """Load a CLIP state_dict (or just its visual.* part)."""
-        vis = {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")} or dict(sd)
-        self.model.visual.load_state_dict({k: torch.as_tensor(v) for k, v in vis.items()})
+        """Load a CLIP state_dict: `visual.*` (or a bare visual state_dict) plus, when present, the text tower and logit_scale."""
+        sd = {k: torch.as_tensor(v) for k, v in sd.items()}
+        vis = {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}
+        text_keys = ("token_embedding.", "positional_embedding", "transformer.", "ln_final.", "text_projection")
+        if vis:
+            self.model.visual.load_state_dict(vis)
+            txt = {k: v for k, v in sd.items() if k.startswith(text_keys)}
+            if txt:
+                missing, unexpected = self.model.load_state_dict(txt, strict=False)
+                bad = [k for k in missing if k.startswith(text_keys)] + list(unexpected)
+                if bad:
+                    raise KeyError(f"text tower state_dict mismatch: {bad[:5]}")
+        else:
+            self.model.visual.load_state_dict({k: v for k, v in sd.items() if k != "logit_scale"})
         if "logit_scale" in sd:
             with torch.no_grad():
-                self.model.logit_scale.copy_(torch.as_tensor(sd["logit_scale"]))
+                self.model.logit_scale.copy_(sd["logit_scale"])
 
     # ---- model/backbone.py:74-87 -----------------------------------------------------------------------------------
     def calculate_score(self, image_features: torch.Tensor, text_features: torch.Tensor, visual_norm_dim: int = 1) -> torch.Tensor:
@@ -166,7 +215,10 @@ class CLIPViTFM(nn.Module):
         if visual_norm_dim != 1:
             raise ValueError("only visual_norm_dim=1 (the reference's call sites) is supported")
         T = text_features.shape[0]
-        feat = image_features.contiguous()
+        feat = image_features
+        if feat.dtype not in (torch.float32, torch.bfloat16):     # the reference's CUDA model is fp16: score such features in f32
+            feat = feat.float()
+        feat = feat.contiguous()
         txt = text_features.float().contiguous()
         N = feat.shape[0]
         dev = feat.device

@@ -30,12 +30,14 @@ class ScoringPath:
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
                  feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True,
-                 keep_features: bool = False, chunks: int = 2):
+                 keep_features: bool = False, chunks: int = 1):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
         under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
         keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"].
-        chunks: groups of images a batch is cut into inside run() (see there); 1 = every stage once per batch."""
+        chunks: groups of images a batch is cut into inside run() (see there); 1 = every stage once per batch (the default:
+        measured on B200 at the bench shape, 2 / 4 groups are SLOWER -- 0.55 / 0.66 ms against 0.50 ms per pass -- because the
+        small latency-bound kernels a group's prep waits for crawl while another group's pack saturates HBM)."""
         if feature_source not in ("supplied", "tokens"):
             raise ValueError(feature_source)
         self.feature_source = feature_source
@@ -167,10 +169,7 @@ class ScoringPath:
             tab   heat-map tables A, B
             main  (caller's stream)  prep main A (after pack A, setup A), prep main B (after pack B, setup B)
         Only pack and prep main are bandwidth-bound; everything else is small and latency-bound and runs up to 3x slower while HBM
-        is saturated.  With one group the step is pack -> [idle HBM while blur -> setup finish] -> prep -> [idle GPU while the
-        scoring chain finishes]; with two or more, group B's pack and small kernels run in the shadow of group A's prep writes and
-        the bandwidth-bound kernels follow each other without a gap.  With overlap=False every stage is launched in order on the
-        caller's stream."""
+        is saturated (profiles/r2_timeline.md).  With overlap=False every stage is launched in order on the caller's stream."""
         img = batch["image"]
         B, H, W, _ = img.shape
         rle = "rle_counts" in batch          # proposals as SAM uncompressed RLE instead of byte masks

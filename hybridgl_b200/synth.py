@@ -294,3 +294,39 @@ def make_batch_device(seed: int, n_images: int, h: int, w: int, n_masks: int, n_
     if pinned_host:
         out = {k: v.cpu().pin_memory() for k, v in out.items()}
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# seeded CLIP weights (no checkpoints offline): the same numbers on the reference side (tests/golden/gen_golden.py)
+# and on this side (tests), derived from (seed, parameter name) only -- so fixtures store outputs, not weights
+# --------------------------------------------------------------------------------------------------
+def seeded_clip_state_dict(shapes, seed: int):
+    """shapes: {parameter name: shape} (CLIP state_dict names).  Returns {name: float32 ndarray}.
+    LayerNorm weights ~ 1 + 0.05 N(0,1), biases / 1-D tensors ~ 0.02 N(0,1), embeddings ~ 0.02 N(0,1), matrices ~ N(0,1) / sqrt(fan_in)
+    (activations stay O(1) through 24 blocks), logit_scale = log(1 / 0.07)."""
+    import zlib
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(int(v) for v in shapes[name])
+        rng = np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+        if name.endswith("logit_scale"):
+            out[name] = np.array(np.log(1 / 0.07), np.float32).reshape(shape)
+            continue
+        x = rng.standard_normal(shape, dtype=np.float32)
+        if len(shape) <= 1:
+            is_ln_weight = name.endswith(".weight") and (".ln_" in name or name.startswith(("ln_", "visual.ln_")) or "ln_final" in name)
+            x = (1.0 + 0.05 * x) if is_ln_weight else 0.02 * x
+        elif "embedding" in name:
+            x = 0.02 * x
+        elif name.endswith("proj") or name.endswith("text_projection"):      # [width, out]: applied as x @ proj
+            x = x / np.sqrt(shape[0])
+        else:                                                                  # nn.Linear / conv weights: [out, in, ...]
+            x = x / np.sqrt(float(np.prod(shape[1:])))
+        out[name] = x.astype(np.float32)
+    return out
+
+
+def seeded_images(seed: int, n: int, size: int):
+    """Two seeded CLIP input stacks (local, global) f32 [n,3,size,size] ~ N(0,1): stand-ins for the prep outputs."""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, 3, size, size), dtype=np.float32), rng.standard_normal((n, 3, size, size), dtype=np.float32)

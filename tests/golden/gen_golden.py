@@ -277,9 +277,51 @@ def gen_rle():
     np.savez_compressed(os.path.join(HERE, "rle.npz"), **out)
 
 
+BACKBONE_CASES = {
+    # name: (CLIP ctor args, last_layer, heads, masking_block, modes, n masks, seed)  -- model/backbone.py:16-21 for ViT-B/16; the
+    # ViT-L/14@336 row is the SURVEY section 8(c) extension (last_layer=22, num_heads=16, masking_block=21 set by hand)
+    "b16": ((512, 224, 12, 768, 16, 77, 49408, 512, 8, 12), 10, 12, 9, ("G2L", "L2G", "G2L&L2G"), 5, 11),
+    "l14": ((768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12), 22, 16, 21, ("G2L&L2G",), 2, 12),
+}
+TEXT_SENTENCES = ["man in black", "car behind bike", "the left-most zebra's head &amp; neck!!", "a photo of a cat", "woman w/ umbrella, 2nd from right",
+                  "far right giraffe"]
+
+
+def gen_backbone(CLIP, CLIPViTFM):
+    """CLIPViTFM.forward (model/backbone.py:117-306) and CLIP.encode_text (clip/model.py:414-431) of the REAL geometries (12 heads,
+    197 tokens, masking_block=9; 16 heads, 577 tokens, masking_block=21) with weights derived from a seed on both sides."""
+    import clip
+    out = {}
+    for tag, (ctor, last_layer, heads, mb, modes, n, seed) in BACKBONE_CASES.items():
+        m = CLIPViTFM.__new__(CLIPViTFM)
+        torch.nn.Module.__init__(m)
+        m.last_layer, m.num_heads = last_layer, heads
+        m.model = CLIP(*ctor).eval()
+        sd = m.model.state_dict()
+        new = synth.seeded_clip_state_dict({k: v.shape for k, v in sd.items()}, seed)
+        m.model.load_state_dict({k: torch.from_numpy(v) for k, v in new.items()})
+        res = ctor[1]
+        loc, glo = synth.seeded_images(seed, n, res)
+        masks = synth.make_masks(np.random.default_rng(seed), n, 120, 160)
+        out[f"{tag}_meta"] = np.array([seed, n, res, mb, 120, 160], np.int64)
+        out[f"{tag}_masks"] = np.packbits(masks, axis=-1)
+        for mode in modes:
+            y = m(torch.from_numpy(loc), torch.from_numpy(glo), torch.from_numpy(masks), masking_block=mb, fusion_mode=mode)
+            out[f"{tag}_out/{mode}"] = y.numpy()
+            print("backbone", tag, mode, tuple(y.shape), float(y.abs().mean()))
+        tok = clip.tokenize(TEXT_SENTENCES)
+        txt = m.model.encode_text(tok)
+        out[f"{tag}_tokens"] = tok.numpy()
+        out[f"{tag}_text"] = txt.numpy()
+        out[f"{tag}_score"] = m.calculate_score(torch.from_numpy(out[f"{tag}_out/{modes[-1]}"]), txt).numpy()
+        print("text", tag, tuple(txt.shape), float(txt.abs().mean()))
+    out["sentences"] = np.array(TEXT_SENTENCES)
+    np.savez_compressed(os.path.join(HERE, "backbone.npz"), **out)
+
+
 if __name__ == "__main__":
     CLIP, CLIPViTFM, ref_utils = load_reference()
-    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc", "rle"]
+    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc", "rle", "backbone"]
     if "rle" in which:
         gen_rle()
     with torch.no_grad():
@@ -293,3 +335,5 @@ if __name__ == "__main__":
             gen_scoring(CLIPViTFM, ref_utils)
         if "misc" in which:
             gen_misc(ref_utils)
+        if "backbone" in which:
+            gen_backbone(CLIP, CLIPViTFM)

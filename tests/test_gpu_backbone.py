@@ -114,3 +114,36 @@ def test_example_eval_loop_runs_all_fusion_modes(mode):
     spec.loader.exec_module(mod)
     rep = mod.main(["--images", "2", "--masks", "12", "--expr", "2", "--fusion_mode", mode, "--height", "240", "--width", "320"])
     assert rep["n_expressions"] == 4 and 0.0 <= rep["oIoU"] <= 100.0
+
+
+# ------------------------------------------------------------------------------------------------ the real geometries
+@pytest.mark.parametrize("tag,name,modes", [("b16", "ViT-B/16", ("G2L", "L2G", "G2L&L2G")), ("l14", "ViT-L/14@336px", ("G2L&L2G",))])
+def test_forward_real_geometry_matches_reference(golden, tag, name, modes):
+    """CLIPViTFM.forward at ViT-B/16 (12 heads, 197 tokens, masking_block=9) and ViT-L/14@336 (16 heads, 577 tokens, masking_block=21;
+    the SURVEY 8(c) extension) against outputs of the reference's own forward (gen_golden.py::gen_backbone); weights are re-derived
+    from the seed on both sides.  Also the text tower (encode_text) and calculate_score on those features."""
+    from hybridgl_b200 import synth
+    from hybridgl_b200.backbone import CLIPViTFM
+    g = golden("backbone")
+    seed, n, res, mb, h, w = (int(v) for v in g[f"{tag}_meta"])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = CLIPViTFM(name, device=DEV)
+    shapes = {k: tuple(v.shape) for k, v in m.model.state_dict().items()}
+    sd = synth.seeded_clip_state_dict(shapes, seed)
+    m.load_clip_state_dict(sd)
+    loc, glo = synth.seeded_images(seed, n, res)
+    masks = unpack_masks(g[f"{tag}_masks"], w)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    for mode in modes:
+        y = m(cu(loc), cu(glo), cu(masks), masking_block=mb, fusion_mode=mode)
+        ref = g[f"{tag}_out/{mode}"]
+        assert tuple(y.shape) == ref.shape
+        # fp32 on the GPU (TF32 off) vs the reference's CPU fp32 through 12 / 24 blocks: 1e-3 of the feature scale
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref, rtol=2e-3, atol=2e-3 * float(np.abs(ref).mean()))
+    txt = m.model.encode_text(cu(g[f"{tag}_tokens"]))
+    np.testing.assert_allclose(txt.cpu().numpy(), g[f"{tag}_text"], rtol=2e-3, atol=1e-4)
+    score = m.calculate_score(cu(g[f"{tag}_out/{modes[-1]}"]), cu(g[f"{tag}_text"])).cpu().numpy()
+    np.testing.assert_allclose(score, g[f"{tag}_score"], rtol=1e-3, atol=1e-3)
+    half = m.calculate_score(cu(g[f"{tag}_out/{modes[-1]}"]).half(), cu(g[f"{tag}_text"]).half()).cpu().numpy()      # fp16 features are accepted
+    np.testing.assert_allclose(half, g[f"{tag}_score"], rtol=2e-2, atol=2e-2)

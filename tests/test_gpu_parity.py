@@ -736,6 +736,33 @@ def test_captured_step_equals_eager_step(ops):
     assert name == "prep" and e0.elapsed_time(e1) > 0.0
 
 
+@pytest.mark.parametrize("chunks", [2, 3])
+def test_image_groups_inside_a_pass_are_invisible(ops, chunks):
+    """ScoringPath(chunks=k): every stage launched once per group of images (ragged batch, one image without expressions) gives the
+    bits of the one-launch-per-stage pass, eagerly and from a captured graph."""
+    from hybridgl_b200.pipeline import OUTPUT_KEYS, ScoringPath
+    h, w, de, g = 96, 128, 64, 6
+    spec = [(7, 2), (3, 1), (12, 3), (1, 0), (6, 5)]
+    items = [synth.make_item(700 + i, h, w, n, e, de=de) for i, (n, e) in enumerate(spec)]
+    batch = _batch_from_items(items, raw_heat=True)
+    batch["tokens"] = cu(bf16r(np.random.default_rng(1).standard_normal((len(spec), g * g, de)).astype(np.float32)), torch.bfloat16)
+    max_n = 12
+    for src in ("tokens", "supplied"):
+        ref_path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source=src, chunks=1)
+        ref = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ref_path.run(batch, max_n).items()}
+        path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source=src, chunks=chunks)
+        res = path.run(batch, max_n)
+        torch.cuda.synchronize()
+        for k in OUTPUT_KEYS + ("local_imgs", "global_imgs", "grid", "area", "bits"):
+            assert torch.equal(res[k], ref[k]), (src, k)
+        assert path.cum.tolist() == ref_path.cum.tolist()
+        step = path.capture(batch, max_n)
+        out = step.replay()
+        torch.cuda.synchronize()
+        for k in OUTPUT_KEYS:
+            assert torch.equal(out[k], ref[k]), (src, k)
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_run_host_iter_equals_run_host(ops, graph):
     """ScoringPath.run_host_iter (H2D of batch k+1 under the kernels of batch k, D2H awaited one batch late, optionally one CUDA
