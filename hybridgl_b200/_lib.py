@@ -20,9 +20,12 @@ SIGNATURES = {
     "hgl_version": (c_int, []),
     "hgl_check_device": (c_int, []),
     "hgl_pack_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hgl_mask_geometry": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hgl_prep_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "hgl_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hgl_prep_crop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p]),
     "hgl_prep_setup": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_prep_main": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
@@ -32,6 +35,9 @@ SIGNATURES = {
     "hgl_grid_heat_pool_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "hgl_attn_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_attn_bias": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "hgl_cls_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hgl_cls_head": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_int, c_void_p,
+                             c_void_p]),
     "hgl_token_mask_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "hgl_dir_mask": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),

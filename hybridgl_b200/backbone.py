@@ -74,21 +74,25 @@ class ResBlock(nn.Module):
                                               ("c_proj", nn.Linear(4 * width, width))]))
         self.ln_2 = LayerNormF32(width)
 
-    def attention(self, h: torch.Tensor, cls_bias: Optional[torch.Tensor], causal: bool = False) -> torch.Tensor:
+    def attention(self, h: torch.Tensor, cls_bias: Optional[torch.Tensor], causal: bool = False, rows=None) -> torch.Tensor:
+        """cls_bias f32 [M, L1] (0 / -inf): key bias of the CLS query; rows: optional list of (lo, hi) row ranges that carry a
+        non-trivial bias (the other rows' bias is all zero and their CLS output is SDPA's own)."""
         M, L1, D = h.shape
         hd = D // self.heads
-        qkv = F.linear(h, self.attn.in_proj_weight, self.attn.in_proj_bias).view(M, L1, 3, self.heads, hd)
+        qkv3 = F.linear(h, self.attn.in_proj_weight, self.attn.in_proj_bias)     # [M, L1, 3*D], packed (q | k | v) x heads x hd
+        qkv = qkv3.view(M, L1, 3, self.heads, hd)
         q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))             # [M, heads, L1, hd]
         o = F.scaled_dot_product_attention(q, k, v, is_causal=causal)           # every query row; causal = the text tower's mask
         if cls_bias is not None:
-            s = torch.matmul(q[:, :, :1].float(), k.float().transpose(-1, -2)) / math.sqrt(hd)    # [M, heads, 1, L1]
-            s = s + cls_bias[:, None, None, :]
-            o0 = torch.matmul(torch.softmax(s, dim=-1).to(v.dtype), v)          # [M, heads, 1, hd]
-            o = torch.cat([o0, o[:, :, 1:]], dim=2)
+            # only the CLS query is masked in the reference (model/backbone.py:108-115): recompute that one row under the key
+            # bias (hgl_cls_attention, one warp per (proposal, head)) and drop it into SDPA's output in place
+            for lo, hi in (rows if rows is not None else [(0, M)]):
+                if hi > lo:
+                    o[lo:hi, :, 0, :] = ops.cls_attention(qkv3[lo:hi], cls_bias[lo:hi].contiguous(), self.heads)
         return self.attn.out_proj(o.transpose(1, 2).reshape(M, L1, D))
 
-    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None, causal: bool = False) -> torch.Tensor:
-        x = x + self.attention(self.ln_1(x), cls_bias, causal)
+    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None, causal: bool = False, rows=None) -> torch.Tensor:
+        x = x + self.attention(self.ln_1(x), cls_bias, causal, rows)
         h = self.mlp.c_fc(self.ln_2(x))
         h = h * torch.sigmoid(1.702 * h)                                        # QuickGELU
         return x + self.mlp.c_proj(h)
@@ -121,9 +125,11 @@ class VisionTransformer(nn.Module):
         cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
         return self.ln_pre(torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype))
 
-    def head(self, x: torch.Tensor) -> torch.Tensor:
-        """ln_post(CLS) @ proj  (model/backbone.py:254-258)."""
-        return self.ln_post(x[:, 0, :]) @ self.proj
+    def head(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+        """ln_post(CLS) @ proj  (model/backbone.py:254-258) in one launch (hgl_cls_head): f32 [M, De]."""
+        if not x.is_cuda:
+            return self.ln_post(x[:, 0, :]) @ self.proj
+        return ops.cls_head(x.contiguous(), self.ln_post.weight, self.ln_post.bias, self.proj, self.ln_post.eps, out=out, accumulate=accumulate)
 
 
 class _Clip(nn.Module):
@@ -299,22 +305,22 @@ class CLIPViTFM(nn.Module):
                     xhl, xhg = x, x2
             if fusion_mode == "G2L":                                              # model/backbone.py:227-260
                 mixed = ops.token_mask_fuse(x2, x, grid, 2.0, 1.0, layout="NLD")  # 2*tokenmask(x2) + x
-                out = blk(torch.cat([mixed, x2], dim=0), torch.cat([zero, bias], dim=0))
+                out = blk(torch.cat([mixed, x2], dim=0), torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)])
                 x, x2 = out[:N], out[N:]
                 result = x
             elif fusion_mode == "L2G":                                            # model/backbone.py:206-225
                 mixed = ops.token_mask_fuse(x2, x, None, 2.0, 1.0, layout="NLD")  # x_old + 2*x2
-                out = blk(torch.cat([x, mixed], dim=0), torch.cat([zero, bias], dim=0))
+                out = blk(torch.cat([x, mixed], dim=0), torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)])
                 x, x2 = out[:N], out[N:]
                 result = x2
             else:                                                                 # model/backbone.py:262-306
                 mixl = ops.token_mask_fuse(x2, xhl, grid, 2.0, 1.0, layout="NLD")   # xhl + 2*tokenmask(x2)
                 mixg = ops.token_mask_fuse(xhg, x, None, 2.0, 1.0, layout="NLD")    # x + 2*xhg
-                out = blk(torch.cat([x, x2, mixl, mixg], dim=0), torch.cat([zero, bias, zero, bias], dim=0))
+                out = blk(torch.cat([x, x2, mixl, mixg], dim=0), torch.cat([zero, bias, zero, bias], dim=0), rows=[(N, 2 * N), (3 * N, 4 * N)])
                 x, x2, xhl, xhg = out[:N], out[N:2 * N], out[2 * N:3 * N], out[3 * N:]
                 result = None
             if i == final:
                 if fusion_mode == "G2L&L2G":
-                    return vit.head(xhl) + vit.head(xhg)
+                    return vit.head(xhg, out=vit.head(xhl), accumulate=True)      # CLS(xhl) + CLS(xhg), model/backbone.py:296-306
                 return vit.head(result)
         return x.transpose(0, 1)

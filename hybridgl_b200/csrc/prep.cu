@@ -562,6 +562,64 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// crop variant: every proposal is resampled from ITS OWN box (x, y, w, h) instead of the full frame
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference casts SAM's box per proposal and never uses it (Hybridgl_main.py:101): it always resizes the full frame.  The
+// north star names a bounding-box crop, SURVEY 8(b) proposes `crop_xywh` on the prep entry point; this is that option:
+//   global[n] = Normalize_IN( bilinear_S( where(m_n, img, bg)[y:y+h, x:x+w] / 255 ) ),  local[n] likewise on the mean-filled view.
+// Taps differ per proposal, so the per-image answer planes of prep_main do not apply: one thread evaluates one output pixel
+// exactly (the boundary-pixel formula of prep_main, ATen's op order), 4 taps x (1 mask bit + 3 + 3 frame bytes).
+template <bool kBF16>
+__global__ void __launch_bounds__(256) prep_crop_kernel(const uint8_t* __restrict__ image, const uint8_t* __restrict__ blur,
+                                                        const uint32_t* __restrict__ bits, const int32_t* __restrict__ mask_off,
+                                                        const int32_t* __restrict__ crop, int B, int H, int W, int S,
+                                                        void* __restrict__ local_out, void* __restrict__ global_out) {
+  __shared__ float lut[1024];                          // [v] = v/255, [256 + 256*c + v] = Normalize_c(v/255)
+  for (int t = threadIdx.x; t < 1024; t += blockDim.x) lut[t] = t < 256 ? to_unit((uint32_t)t) : to_norm((uint32_t)(t & 255), (t >> 8) - 1);
+  __syncthreads();
+  const int m = blockIdx.y, WW = (W + 31) >> 5, SS = S * S;
+  int b = 0;
+  if (mask_off) { while (b + 1 < B && mask_off[b + 1] <= m) ++b; }
+  const int cx = crop[4 * m], cy = crop[4 * m + 1], cw = crop[4 * m + 2], ch = crop[4 * m + 3];
+  const float sc_y = tap_scale(ch, S), sc_x = tap_scale(cw, S);
+  const uint8_t* img = image + (size_t)b * H * W * 3;
+  const uint8_t* bg = blur ? blur + (size_t)b * H * W * 3 : nullptr;
+  const uint32_t* mb = bits + (size_t)m * H * WW;
+  for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < SS; px += gridDim.x * blockDim.x) {
+    const int i = px / S, j = px - i * S;
+    const Taps ty = make_taps(i, ch, S, sc_y), tx = make_taps(j, cw, S, sc_x);
+    const int ys[2] = {cy + ty.i0, cy + ty.i0 + ty.d}, xs[2] = {cx + tx.i0, cx + tx.i0 + tx.d};
+    float gv[3][4], lv[3][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int yy = ys[t >> 1], xx = xs[t & 1];
+      const bool in = (__ldg(mb + (size_t)yy * WW + (xx >> 5)) >> (xx & 31)) & 1u;
+      const size_t o = ((size_t)yy * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t vi = __ldg(img + o + c);
+        const uint32_t vb = bg ? (uint32_t)__ldg(bg + o + c) : 0u;
+        gv[c][t] = lut[in ? vi : vb];
+        lv[c][t] = in ? lut[256 + 256 * c + vi] : c_clip_mean[c];
+      }
+    }
+    const size_t o = (size_t)m * 3 * SS + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float g = __fdiv_rn(__fsub_rn(bilerp(gv[c][0], gv[c][1], gv[c][2], gv[c][3], tx.w0, tx.w1, ty.w0, ty.w1), c_in_mean[c]), c_in_std[c]);
+      const float l = bilerp(lv[c][0], lv[c][1], lv[c][2], lv[c][3], tx.w0, tx.w1, ty.w0, ty.w1);
+      if (kBF16) {
+        reinterpret_cast<__nv_bfloat16*>(local_out)[o + (size_t)c * SS] = __float2bfloat16_rn(l);
+        reinterpret_cast<__nv_bfloat16*>(global_out)[o + (size_t)c * SS] = __float2bfloat16_rn(g);
+      } else {
+        reinterpret_cast<float*>(local_out)[o + (size_t)c * SS] = l;
+        reinterpret_cast<float*>(global_out)[o + (size_t)c * SS] = g;
+      }
+    }
+  }
+}
+
 struct PrepWs {
   void* planes;
   uint32_t* taps;
@@ -748,4 +806,26 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   }
   if (smem_rc != HGL_OK) return smem_rc;
   return launch_status("hgl_prep(main)");
+}
+
+// per-proposal crop boxes: see prep_crop_kernel.  crop_xywh int32 [M,4] (x, y, w, h), every box inside its frame (w, h >= 1);
+// the boxes are read on the device, so their validity is the caller's contract (ops.prep_visual_prompts checks it on the host side
+// when the boxes are at hand).  No workspace.
+extern "C" int hgl_prep_crop(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off, const int32_t* crop_xywh,
+                             int B, int M, int H, int W, int S, int bg_mode, int out_dtype, void* local_out, void* global_out, void* stream) {
+  using namespace hgl;
+  if (M == 0 && B >= 1) return HGL_OK;
+  HGL_REQUIRE(image && bits && crop_xywh && local_out && global_out, "hgl_prep_crop: null pointer");
+  HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK, "hgl_prep_crop: bg_mode %d", bg_mode);
+  HGL_REQUIRE(bg_mode != HGL_BG_BLUR || blur, "hgl_prep_crop: blur frame required for HGL_BG_BLUR");
+  HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep_crop: out_dtype %d", out_dtype);
+  HGL_REQUIRE(B >= 1 && M >= 0 && H >= 1 && W >= 1 && S >= 1 && S <= 4096, "hgl_prep_crop: bad shape");
+  HGL_REQUIRE(mask_off || B == 1, "hgl_prep_crop: mask_off required when B > 1");
+  HGL_REQUIRE(M <= 65535, "hgl_prep_crop: more than 65535 proposals per launch");
+  const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : nullptr;
+  dim3 grid(std::min(ceil_div(S * S, 256), 64), M);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == HGL_BF16) prep_crop_kernel<true><<<grid, 256, 0, st>>>(image, bgp, bits, mask_off, crop_xywh, B, H, W, S, local_out, global_out);
+  else prep_crop_kernel<false><<<grid, 256, 0, st>>>(image, bgp, bits, mask_off, crop_xywh, B, H, W, S, local_out, global_out);
+  return launch_status("hgl_prep_crop");
 }

@@ -111,6 +111,28 @@ def rle_to_bits(counts: torch.Tensor, rle_off: torch.Tensor, height: int, width:
     return out
 
 
+def mask_geometry(masks: torch.Tensor, width: Optional[int] = None, want_boxes: bool = True, want_chw: bool = False):
+    """SAM's XYWH proposal boxes (amg.py:303-346 + :91-95) and / or mask2chw (utils.py:280-289) of every mask, on the device.
+    `masks`: bool/u8 [M,H,W] (packed internally) or packed int32 [M,H,ceil(W/32)] together with `width`.
+    Returns boxes int64 [M,4] (x, y, w, h), chw int32 [M,4] (center_y, center_x, height, width), or the pair."""
+    if masks.dtype == torch.int32:
+        if width is None:
+            raise ValueError("width is required with packed masks")
+        bits = _req(masks, torch.int32, "bits", 3)
+        W = int(width)
+        if bits.shape[2] != (W + 31) // 32:
+            raise ValueError("packed masks do not match width")
+    else:
+        m = _mask_bytes(masks)
+        W = m.shape[2]
+        bits = pack_masks(m)
+    M, H = bits.shape[0], bits.shape[1]
+    boxes = torch.empty((M, 4), dtype=torch.int64, device=bits.device) if want_boxes else None
+    chw = torch.empty((M, 4), dtype=torch.int32, device=bits.device) if want_chw else None
+    check(_lib.load().hgl_mask_geometry(bits.data_ptr(), M, H, W, _ptr(boxes), _ptr(chw), _stream()), "hgl_mask_geometry")
+    return (boxes, chw) if (want_boxes and want_chw) else (boxes if want_boxes else chw)
+
+
 def _bits(masks_or_bits: torch.Tensor, W: Optional[int] = None) -> torch.Tensor:
     """Accept either byte masks (packed on the fly) or an already packed int32 tensor."""
     if masks_or_bits.dtype == torch.int32:
@@ -185,9 +207,11 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
                         mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None, background: str = "blur",
                         dtype: torch.dtype = torch.float32,
                         out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                        workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                        workspace: Optional[torch.Tensor] = None, crop_xywh: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S].
-    `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks()."""
+    `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks().
+    crop_xywh int32/int64 [M,4]: resample every proposal from its own box (x, y, w, h) instead of the full frame (hgl_prep_crop;
+    the reference always uses the full frame)."""
     img, bl, bg = _prep_frames(image, blur, background)
     B, H, W, _ = img.shape
     bits = _bits(masks)
@@ -204,6 +228,14 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
         glob = torch.empty_like(local)
     else:
         local, glob = out
+    if crop_xywh is not None:
+        _req(crop_xywh, (torch.int32, torch.int64), "crop_xywh", 2)
+        if tuple(crop_xywh.shape) != (M, 4):
+            raise ValueError("crop_xywh must be [M,4]")
+        c = crop_xywh.to(torch.int32).contiguous()
+        check(_lib.load().hgl_prep_crop(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), c.data_ptr(), B, M, H, W, size, bg, _dt(dtype),
+                                        local.data_ptr(), glob.data_ptr(), _stream()), "hgl_prep_crop")
+        return local, glob
     workspace = _prep_workspace(B, size, dtype, img.device, workspace)
     check(_lib.load().hgl_prep(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, bg, _dt(dtype),
                                local.data_ptr(), glob.data_ptr(), workspace.data_ptr(), _stream()), "hgl_prep")
@@ -277,6 +309,49 @@ def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Option
         out = torch.empty_like(src)
     check(_lib.load().hgl_token_mask_fuse(src.data_ptr(), _ptr(add), _ptr(grid), float(a), float(b), L1, M, D, _dt(src.dtype),
                                           lay, out.data_ptr(), _stream()), "hgl_token_mask_fuse")
+    return out
+
+
+def cls_attention(qkv: torch.Tensor, bias: Optional[torch.Tensor], heads: int) -> torch.Tensor:
+    """Attention output of the CLS query alone under the key bias (hgl_cls_attention).  qkv [M, L1, 3*D] (the packed in_proj output,
+    f32 / bf16), bias f32 [M, L1] or None.  Returns [M, heads, hd] of qkv's dtype."""
+    _req(qkv, (torch.float32, torch.bfloat16), "qkv", 3)
+    M, L1, D3 = qkv.shape
+    hd = D3 // (3 * heads)
+    if hd * 3 * heads != D3:
+        raise ValueError("qkv width is not 3 * heads * head_dim")
+    if bias is not None:
+        _req(bias, torch.float32, "bias", 2)
+        if tuple(bias.shape) != (M, L1):
+            raise ValueError("bias must be [M, L1]")
+    out = torch.empty((M, heads, hd), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().hgl_cls_attention(qkv.data_ptr(), _ptr(bias), M, L1, heads, hd, _dt(qkv.dtype), out.data_ptr(), _stream()), "hgl_cls_attention")
+    return out
+
+
+def cls_head(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, proj: torch.Tensor, eps: float = 1e-5,
+             out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """ln_post(x[:, 0, :]) @ proj in one launch (hgl_cls_head).  x [M, L1, Dv] (the CLS token of every row is read in place) or
+    [M, Dv]; gamma / beta [Dv], proj [Dv, De] (all of one dtype, f32 / bf16).  Returns f32 [M, De]; accumulate adds to `out`."""
+    _req(x, (torch.float32, torch.bfloat16), "x")
+    if x.dim() == 3:
+        M, L1, Dv = x.shape
+        stride = L1 * Dv
+    else:
+        M, Dv = x.shape
+        stride = Dv
+    for t, nm in ((gamma, "gamma"), (beta, "beta"), (proj, "proj")):
+        _req(t, proj.dtype, nm)
+    if proj.dtype not in (torch.float32, torch.bfloat16) or proj.shape[0] != Dv or gamma.numel() != Dv or beta.numel() != Dv:
+        raise ValueError("cls_head: inconsistent weights")
+    De = proj.shape[1]
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs `out`")
+        out = torch.empty((M, De), dtype=torch.float32, device=x.device)
+    _req(out, torch.float32, "out", 2)
+    check(_lib.load().hgl_cls_head(x.data_ptr(), stride, gamma.data_ptr(), beta.data_ptr(), proj.data_ptr(), M, Dv, De, float(eps), _dt(x.dtype),
+                                   _dt(proj.dtype), int(bool(accumulate)), out.data_ptr(), _stream()), "hgl_cls_head")
     return out
 
 

@@ -66,3 +66,32 @@ def Compute_IoU(pred, target, cum_I, cum_U, mean_IoU=None):
     cum_U = cum_U + U
     mean_IoU.append(this_iou)
     return this_iou, mean_IoU, cum_I, cum_U
+
+
+def mask2chw(arr):
+    """utils.py:280-289 for a CUDA mask [H,W] (bool / uint8): ((center_y, center_x), height, width), computed by hgl_mask_geometry.
+    Raises ValueError on an empty mask (the reference's np.mean of nothing is NaN and int(NaN) raises there too)."""
+    m = arr if arr.dtype in (torch.bool, torch.uint8) else (arr == 1)
+    cy, cx, h, w = (int(v) for v in ops.mask_geometry(m.contiguous()[None], want_boxes=False, want_chw=True)[0].tolist())
+    if h == 0:
+        raise ValueError("mask2chw: empty mask")
+    return (cy, cx), h, w
+
+
+def apply_visual_prompts(image_array, mask, visual_prompt_type=("blur",), blur_strength=(15, 15)):
+    """utils.py:292-345 on CUDA tensors for the compositing prompt types: 'blur' (sharp inside the mask, cv2.GaussianBlur(15,15)
+    outside) and 'black' (zeros outside), applied in the reference's order.  image_array u8 [H,W,3], mask bool/u8 [H,W];
+    returns u8 [H,W,3].  'circle' (a cv2.ellipse outline at mask2chw's centre) is not built: no driver calls it and it needs
+    OpenCV's fixed-point polygon rasteriser bit for bit."""
+    if tuple(blur_strength) != (15, 15):
+        raise ValueError("only the (15, 15) kernel of the reference's call is built (hgl_gaussian_blur15)")
+    img = image_array
+    keep = (mask != 0)[:, :, None]
+    for kind in ("blur", "circle", "black"):                # the order of the reference's if-chain
+        if kind not in visual_prompt_type:
+            continue
+        if kind == "circle":
+            raise NotImplementedError("visual_prompt_type 'circle' is not built (see docstring)")
+        bg = ops.gaussian_blur15(img.contiguous()) if kind == "blur" else torch.zeros_like(img)
+        img = torch.where(keep, img, bg)
+    return img

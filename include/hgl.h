@@ -64,6 +64,14 @@ HGL_API int hgl_check_device(void);
  * grid and the heat-map pooling all consume the 8x smaller packed tensor. */
 HGL_API int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream);
 
+/* ---- per-mask geometry from the packed masks ------------------------------------------------------------
+ * boxes_xywh int64 [M,4]: SAM's proposal boxes -- batched_mask_to_box + box_xyxy_to_xywh
+ *   (third_party/segment-anything/segment_anything/utils/amg.py:303-346, :91-95): x0, y0, x1 - x0, y1 - y0 of the inclusive
+ *   edges, zeros for an empty mask; the boxes Hybridgl_main.py:89-90 hands to relation_boxes.  May be NULL.
+ * chw int32 [M,4]: mask2chw utils.py:280-289: (center_y, center_x, height, width) = (int(mean(rows)), int(mean(cols)),
+ *   rows.max()-rows.min()+1, cols.max()-cols.min()+1); (-1,-1,0,0) for an empty mask (the reference raises).  May be NULL. */
+HGL_API int hgl_mask_geometry(const uint32_t* bits, int M, int H, int W, int64_t* boxes_xywh, int32_t* chw, void* stream);
+
 /* ---- (a1) per-mask visual-prompt preprocessing ------------------------------------------------------
  * Replaces the Python loop Hybridgl_main.py:92-125 (dups demo.py:79-112) and utils.py:292-345:
  *   global[n] = Normalize_IN(bilinear_S( where(mask_n, image, background) / 255 ))
@@ -75,6 +83,13 @@ HGL_API int64_t hgl_prep_workspace_bytes(int B, int S, int out_dtype);
 HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off,
              int B, int M, int max_n, int H, int W, int S, int bg_mode, int out_dtype,
              void* local_out, void* global_out, void* workspace, void* stream);
+
+/* hgl_prep with a per-proposal crop (the north star's "bounding-box crop"; SURVEY 8(b) `crop_xywh`): proposal n is resampled from
+ * its own box crop_xywh[n] = (x, y, w, h) (int32 [M,4], inside the frame, w, h >= 1) instead of from the full frame:
+ *   global[n] = Normalize_IN(bilinear_S(where(mask_n, image, background)[y:y+h, x:x+w] / 255)), local[n] likewise on the mean-filled
+ * view.  The reference itself never crops (it casts pred_box at Hybridgl_main.py:101 and does not use it).  No workspace. */
+HGL_API int hgl_prep_crop(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off, const int32_t* crop_xywh,
+                  int B, int M, int H, int W, int S, int bg_mode, int out_dtype, void* local_out, void* global_out, void* stream);
 
 /* hgl_prep in its two halves, for callers that overlap stages: hgl_prep_setup needs only the frames (per image: the
  * "all taps inside" / "all taps outside" answer planes and the tap bytes, left in `workspace`) and may be enqueued while
@@ -105,6 +120,21 @@ HGL_API int hgl_attn_mask(const float* grid, int M, int L, int heads, uint8_t* o
 /* Compact equivalent used by the B200 forward: additive key bias for the CLS query only,
  * bias f32 [M, L+1] = 0 or -inf (col 0 always 0). */
 HGL_API int hgl_attn_bias(const float* grid, int M, int L, float* bias, void* stream);
+
+/* ---- (f1) CLS-row attention under the key bitmap ------------------------------------------------------
+ * The only masked row of the reference's attention mask (model/backbone.py:108-115; third_party/modified_CLIP/clip/model.py:220-257)
+ * is the CLS query: out[m,h,:] = softmax_j(q[m,0,h].k[m,j,h] / sqrt(hd) + bias[m,j]) @ v[m,:,h] from the packed projection
+ * qkv [M, L1, 3, heads, hd] of `dtype`; bias f32 [M, L1] (hgl_attn_bias; NULL = unmasked); out [M, heads, hd] of `dtype`.
+ * The other rows come from one unmasked SDPA call; this replaces the N*heads*(L+1)^2 mask tensor. */
+HGL_API int hgl_cls_attention(const void* qkv, const float* bias, int M, int L1, int heads, int hd, int dtype, void* out, void* stream);
+
+/* ---- (a5) CLS head ------------------------------------------------------------------------------------
+ * Replaces ln_post(x[:,0,:]) @ visual.proj (model/backbone.py:254-260, 220-225, 296-306): LayerNorm in f32 (eps, biased variance)
+ * and the projection in one launch.  x: row m starts at x + m * row_stride elements (pass the [M, L+1, Dv] stream and
+ * row_stride = (L+1)*Dv to read the CLS tokens in place); gamma / beta [Dv], proj [Dv, De] of w_dtype; out f32 [M, De],
+ * overwritten or (accumulate != 0) added to -- G2L&L2G sums the heads of its two hybrid streams. */
+HGL_API int hgl_cls_head(const void* x, int64_t row_stride, const void* gamma, const void* beta, const void* proj, int M, int Dv, int De,
+                 double eps, int x_dtype, int w_dtype, int accumulate, float* out, void* stream);
 
 /* ---- (a4) token masking + stream mix ----------------------------------------------------------------
  * Replaces the permute/view/mul/cat chains model/backbone.py:235-249, 214-216, 275-291:

@@ -159,6 +159,25 @@ def prep(image_u8: np.ndarray, blur_u8: np.ndarray, masks: np.ndarray, S: int, b
     return local, glob
 
 
+def prep_crop(image_u8: np.ndarray, blur_u8: np.ndarray, masks: np.ndarray, crop_xywh: np.ndarray, S: int, background: str = "blur"):
+    """prep() with a per-proposal crop box (x, y, w, h): the same two composites, cut to the box, then resized to S x S -- what
+    Hybridgl_main.py:92-125 would compute had it used the pred_box it casts at :101 (it does not: an option of the build, pinned
+    to prep() by the full-frame box)."""
+    masks = np.asarray(masks).astype(bool)
+    n = masks.shape[0]
+    img_norm = imagenet_normalize(to_tensor_u8(image_u8))
+    bg = blur_u8 if background == "blur" else np.zeros_like(image_u8)
+    local = np.zeros((n, 3, S, S), f32); glob = np.zeros((n, 3, S, S), f32)
+    for i in range(n):
+        x, y, w, h = (int(v) for v in crop_xywh[i])
+        m = masks[i, y:y + h, x:x + w]
+        comp = np.where(m[:, :, None], image_u8[y:y + h, x:x + w], bg[y:y + h, x:x + w])
+        glob[i] = imagenet_normalize(resize_bilinear(to_tensor_u8(comp), S, S))
+        masked = np.where(m[None], img_norm[:, y:y + h, x:x + w], CLIP_PIXEL_MEAN[:, None, None]).astype(f32)
+        local[i] = resize_bilinear(masked, S, S)
+    return local, glob
+
+
 def gaussian_kernel_u8(ksize: int = 15) -> np.ndarray:
     """Fixed-point (Q8) 1-D Gaussian taps used by cv2.GaussianBlur on CV_8U for sigma=0 -> derived sigma
     (getGaussianKernel: sigma = 0.3*((ksize-1)*0.5 - 1) + 0.8; softfloat kernel, then quantised so the
@@ -440,3 +459,33 @@ def report(cum_i: int, cum_u: int, ious) -> tuple:
     o = cum_i * 100.0 / cum_u if cum_u else float("nan")
     m = float(np.mean(np.asarray(ious, f32), dtype=f32)) * 100.0 if len(ious) else float("nan")
     return o, m
+
+
+# --------------------------------------------------------------------------------------------------
+# (a1') apply_visual_prompts utils.py:292-345 and its helpers: mask2chw (utils.py:280-289), SAM's boxes, cv2.ellipse outline
+# --------------------------------------------------------------------------------------------------
+def mask2chw(mask: np.ndarray):
+    """utils.py:280-289: ((center_y, center_x), height, width); the reference raises on an empty mask (mean of nothing)."""
+    rows, cols = np.nonzero(np.asarray(mask).astype(bool))
+    if rows.size == 0:
+        raise ValueError("empty mask")
+    return (int(np.mean(rows)), int(np.mean(cols))), int(rows.max() - rows.min() + 1), int(cols.max() - cols.min() + 1)
+
+
+def mask_to_box_xywh(mask: np.ndarray) -> np.ndarray:
+    """amg.py:303-346 batched_mask_to_box + :91-95 box_xyxy_to_xywh for one mask: inclusive edges, w = x1 - x0, h = y1 - y0."""
+    ys, xs = np.nonzero(np.asarray(mask).astype(bool))
+    if ys.size == 0:
+        return np.zeros(4, np.int64)
+    return np.array([xs.min(), ys.min(), xs.max() - xs.min(), ys.max() - ys.min()], np.int64)
+
+
+def apply_visual_prompt(image_u8: np.ndarray, mask: np.ndarray, kind: str, blur_u8: np.ndarray = None) -> np.ndarray:
+    """utils.py:292-345 for the prompt types that are pure compositing: 'blur' (:306-320) and 'black' (:336-341).  image u8 [H,W,3];
+    returns u8 [H,W,3].  ('circle', :322-335, draws cv2.ellipse's fixed-point polygon outline at mask2chw's centre; not restated.)"""
+    m = np.asarray(mask).astype(bool)
+    if kind == "blur":
+        return np.where(m[:, :, None], image_u8, blur_u8 if blur_u8 is not None else gaussian_blur_u8(image_u8))
+    if kind == "black":
+        return np.where(m[:, :, None], image_u8, np.zeros_like(image_u8))
+    raise ValueError(kind)

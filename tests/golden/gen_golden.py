@@ -277,6 +277,35 @@ def gen_rle():
     np.savez_compressed(os.path.join(HERE, "rle.npz"), **out)
 
 
+def gen_geometry(ref_utils):
+    """mask2chw (utils.py:280-289), apply_visual_prompts 'blur' / 'black' (utils.py:306-320, 336-341) and SAM's boxes
+    (amg.py:303-346 batched_mask_to_box + :91-95 box_xyxy_to_xywh), called in place."""
+    sys.path.insert(0, os.path.join(REF, "third_party/segment-anything"))
+    from segment_anything.utils.amg import batched_mask_to_box, box_xyxy_to_xywh
+    out = {}
+    rng = np.random.default_rng(77)
+    for ci, (h, w, n) in enumerate(((48, 64, 6), (97, 131, 5), (480, 640, 8), (33, 32, 4), (600, 800, 3))):
+        m = synth.make_masks(rng, n, h, w, min_area=12)
+        m[0] = False; m[0, h // 3, w // 2] = True              # a single pixel
+        m[1] = True                                             # the full frame
+        if n > 3:
+            m[3] = False; m[3, 0, :] = True; m[3, :, w - 1] = True   # an L along two frame edges
+        boxes = torch.stack([box_xyxy_to_xywh(b) for b in batched_mask_to_box(torch.from_numpy(m))]).numpy().astype(np.int64)
+        chw = np.array([[c[0][0], c[0][1], c[1], c[2]] for c in (ref_utils.mask2chw(mm.astype(np.uint8)) for mm in m)], np.int32)
+        out[f"c{ci}_masks"] = np.packbits(m, axis=-1); out[f"c{ci}_hw"] = np.array([h, w, n], np.int64)
+        out[f"c{ci}_boxes"] = boxes; out[f"c{ci}_chw"] = chw
+        if ci < 2:
+            img = synth.make_image(rng, h, w)
+            out[f"c{ci}_image"] = img
+            for kind in ("blur", "black"):
+                out[f"c{ci}_{kind}"] = np.stack([ref_utils.apply_visual_prompts(img, mm.astype(np.uint8), visual_prompt_type=(kind,)) for mm in m])
+        print("geometry", ci, (h, w, n), boxes[2].tolist(), chw[2].tolist())
+    empty = batched_mask_to_box(torch.zeros((1, 8, 8), dtype=torch.bool))
+    out["empty_box"] = box_xyxy_to_xywh(empty[0]).numpy().astype(np.int64)
+    out["n_cases"] = np.int64(5)
+    np.savez_compressed(os.path.join(HERE, "geometry.npz"), **out)
+
+
 BACKBONE_CASES = {
     # name: (CLIP ctor args, last_layer, heads, masking_block, modes, n masks, seed)  -- model/backbone.py:16-21 for ViT-B/16; the
     # ViT-L/14@336 row is the SURVEY section 8(c) extension (last_layer=22, num_heads=16, masking_block=21 set by hand)
@@ -321,7 +350,7 @@ def gen_backbone(CLIP, CLIPViTFM):
 
 if __name__ == "__main__":
     CLIP, CLIPViTFM, ref_utils = load_reference()
-    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc", "rle", "backbone"]
+    which = sys.argv[1:] or ["prep", "grid", "forward", "scoring", "misc", "rle", "backbone", "geometry"]
     if "rle" in which:
         gen_rle()
     with torch.no_grad():
@@ -337,3 +366,5 @@ if __name__ == "__main__":
             gen_misc(ref_utils)
         if "backbone" in which:
             gen_backbone(CLIP, CLIPViTFM)
+        if "geometry" in which:
+            gen_geometry(ref_utils)

@@ -147,3 +147,39 @@ def test_forward_real_geometry_matches_reference(golden, tag, name, modes):
     np.testing.assert_allclose(score, g[f"{tag}_score"], rtol=1e-3, atol=1e-3)
     half = m.calculate_score(cu(g[f"{tag}_out/{modes[-1]}"]).half(), cu(g[f"{tag}_text"]).half()).cpu().numpy()      # fp16 features are accepted
     np.testing.assert_allclose(half, g[f"{tag}_score"], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,L1,heads,hd,dtype", [(5, 197, 12, 64, torch.float32), (3, 577, 16, 64, torch.bfloat16), (2, 17, 1, 64, torch.float32), (4, 50, 8, 32, torch.bfloat16)])
+def test_cls_attention_kernel_vs_torch(M, L1, heads, hd, dtype):
+    """hgl_cls_attention against softmax(q0 k^T / sqrt(hd) + bias) v computed by torch in f32."""
+    from hybridgl_b200 import ops
+    torch.manual_seed(M * L1)
+    qkv = torch.randn(M, L1, 3 * heads * hd, device=DEV).to(dtype)
+    bias = torch.zeros(M, L1, device=DEV)
+    bias[:, 1:][torch.rand(M, L1 - 1, device=DEV) < 0.5] = float("-inf")
+    got = ops.cls_attention(qkv, bias, heads).float()
+    v5 = qkv.float().view(M, L1, 3, heads, hd)
+    q0, k, v = v5[:, 0, 0], v5[:, :, 1], v5[:, :, 2]
+    s = torch.einsum("mhd,mjhd->mhj", q0, k) / hd ** 0.5 + bias[:, None, :]
+    ref = torch.einsum("mhj,mjhd->mhd", torch.softmax(s, -1), v)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(got, ref, rtol=tol, atol=tol)
+    none = ops.cls_attention(qkv, None, heads).float()
+    ref0 = torch.einsum("mhj,mjhd->mhd", torch.softmax(torch.einsum("mhd,mjhd->mhj", q0, k) / hd ** 0.5, -1), v)
+    torch.testing.assert_close(none, ref0, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("M,L1,Dv,De,dtype", [(100, 197, 768, 512, torch.float32), (7, 5, 64, 32, torch.float32), (33, 577, 1024, 768, torch.bfloat16)])
+def test_cls_head_kernel_vs_torch(M, L1, Dv, De, dtype):
+    """hgl_cls_head == F.layer_norm(x[:, 0, :]) @ proj (f32 reference), plain and accumulated."""
+    from hybridgl_b200 import ops
+    torch.manual_seed(Dv)
+    x = torch.randn(M, L1, Dv, device=DEV).to(dtype)
+    gamma = (1 + 0.1 * torch.randn(Dv, device=DEV)).to(dtype); beta = (0.1 * torch.randn(Dv, device=DEV)).to(dtype)
+    proj = (torch.randn(Dv, De, device=DEV) * Dv ** -0.5).to(dtype)
+    ref = torch.nn.functional.layer_norm(x[:, 0, :].float(), (Dv,), gamma.float(), beta.float(), 1e-5) @ proj.float()
+    got = ops.cls_head(x, gamma, beta, proj, 1e-5)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    torch.testing.assert_close(got, ref, rtol=tol, atol=tol)
+    ops.cls_head(x, gamma, beta, proj, 1e-5, out=got, accumulate=True)
+    torch.testing.assert_close(got, 2 * ref, rtol=tol, atol=2 * tol)

@@ -383,6 +383,65 @@ def test_grid_heat_pool_on_raw_maps_equals_resize_then_pool(ops, hh, hw, h, w):
             np.testing.assert_allclose(s1.cpu().numpy()[e, :n], ref, rtol=1e-3, atol=1e-4)
 
 
+# ------------------------------------------------------------------------------------------------ per-mask geometry, prompt variants
+def test_mask_geometry_matches_reference_golden(ops, golden):
+    """hgl_mask_geometry: SAM's XYWH boxes and mask2chw, bit-exact against the reference's own functions (gen_golden.py::gen_geometry);
+    the host mirrors utils.mask2chw / utils.apply_visual_prompts ('blur', 'black') against recorded outputs."""
+    from hybridgl_b200 import utils as U
+    g = golden("geometry")
+    for ci in range(int(g["n_cases"])):
+        h, w, n = g[f"c{ci}_hw"].tolist()
+        masks = unpack_masks(g[f"c{ci}_masks"], w)
+        boxes, chw = ops.mask_geometry(cu(masks), want_boxes=True, want_chw=True)
+        assert np.array_equal(boxes.cpu().numpy(), g[f"c{ci}_boxes"]) and np.array_equal(chw.cpu().numpy(), g[f"c{ci}_chw"])
+        b2 = ops.mask_geometry(ops.pack_masks(cu(masks)), width=w)                      # packed input
+        assert torch.equal(b2, boxes)
+        (cy, cx), hh, ww = U.mask2chw(cu(masks[2]))
+        assert [cy, cx, hh, ww] == g[f"c{ci}_chw"][2].tolist()
+        if f"c{ci}_image" in g.files:
+            img = cu(g[f"c{ci}_image"])
+            for i in (0, 1, 2):
+                for kind in ("blur", "black"):
+                    got = U.apply_visual_prompts(img, cu(masks[i]), visual_prompt_type=(kind,))
+                    assert np.array_equal(got.cpu().numpy(), g[f"c{ci}_{kind}"][i]), (ci, i, kind)
+    boxes, chw = ops.mask_geometry(torch.zeros((2, 9, 40), dtype=torch.bool, device=DEV), want_chw=True)
+    assert boxes.tolist() == [[0, 0, 0, 0]] * 2 and chw.tolist() == [[-1, -1, 0, 0]] * 2
+    with pytest.raises(ValueError):
+        U.mask2chw(torch.zeros((9, 40), dtype=torch.bool, device=DEV))
+
+
+@pytest.mark.parametrize("h,w,S,dtype", [(120, 160, 64, torch.float32), (97, 131, 48, torch.bfloat16), (480, 640, 224, torch.float32)])
+def test_prep_with_per_proposal_crop(ops, h, w, S, dtype):
+    """hgl_prep_crop: every proposal resampled from its own box; bit-exact against the oracle (f32) / its RNE (bf16), and the
+    full-frame box reproduces the reference's own prep bit for bit."""
+    n = 5
+    it = synth.make_item(41, h, w, n, 0, with_features=False)
+    img, masks = cu(it.image), cu(it.masks)
+    blur = ops.gaussian_blur15(img)
+    boxes = it.boxes.copy()
+    boxes[:, 2:] += 1                                       # SAM's w = x1 - x0: the inclusive box is one pixel larger
+    boxes[0] = (0, 0, w, h)                                 # full frame
+    boxes[1] = (3, 5, 1, 1)                                 # a single source pixel
+    for bgname in ("blur", "black"):
+        loc, glo = ops.prep_visual_prompts(img, blur, masks, S, background=bgname, dtype=dtype, crop_xywh=cu(boxes))
+        rl, rg = O.prep_crop(it.image, blur.cpu().numpy(), it.masks, boxes, S, background=bgname)
+        if dtype == torch.float32:
+            assert np.array_equal(loc.cpu().numpy(), rl) and np.array_equal(glo.cpu().numpy(), rg)
+        else:
+            assert np.array_equal(loc.float().cpu().numpy(), bf16r(rl)) and np.array_equal(glo.float().cpu().numpy(), bf16r(rg))
+        l0, g0 = ops.prep_visual_prompts(img, blur, masks[:1], S, background=bgname, dtype=dtype)
+        assert torch.equal(loc[:1], l0) and torch.equal(glo[:1], g0)
+
+
+def test_device_resident_proposals_rle_to_boxes(ops):
+    """SAM post-processing kept on the device: RLE -> packed masks -> XYWH boxes, identical to the host path."""
+    it = synth.make_item(5, 333, 500, 9, 0, with_features=False)
+    counts, off = synth.masks_to_rle(it.masks)
+    bits = ops.rle_to_bits(cu(counts), cu(off), 333, 500)
+    boxes = ops.mask_geometry(bits, width=500)
+    assert np.array_equal(boxes.cpu().numpy(), it.boxes)
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core mask pooling
 @pytest.mark.parametrize("B,n,L,D,dtype", [(1, 100, 196, 768, torch.float32), (2, 37, 196, 512, torch.float32), (1, 200, 576, 1024, torch.float32),
                                            (3, 130, 49, 64, torch.float32), (1, 5, 16, 32, torch.bfloat16), (2, 150, 196, 768, torch.bfloat16)])

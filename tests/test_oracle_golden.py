@@ -165,3 +165,25 @@ def test_pack_bits_layout():
     for (n, y, x) in [(0, 0, 0), (1, 2, 31), (2, 4, 32), (2, 3, 69)]:
         assert bool((b[n, y, x // 32] >> (x % 32)) & 1) == bool(m[n, y, x])
     assert (b[:, :, 2] >> 6).max() == 0            # bits past W are zero
+
+
+def test_geometry_and_prompts_match_reference(golden):
+    """oracle mask2chw / SAM boxes / apply_visual_prompts('blur' | 'black') against the reference's own functions
+    (gen_golden.py::gen_geometry: utils.mask2chw, utils.apply_visual_prompts, amg.batched_mask_to_box + box_xyxy_to_xywh)."""
+    from conftest import unpack_masks
+    g = golden("geometry")
+    for ci in range(int(g["n_cases"])):
+        h, w, n = g[f"c{ci}_hw"].tolist()
+        masks = unpack_masks(g[f"c{ci}_masks"], w)
+        for i in range(n):
+            (cy, cx), hh, ww = O.mask2chw(masks[i])
+            assert [cy, cx, hh, ww] == g[f"c{ci}_chw"][i].tolist()
+            assert O.mask_to_box_xywh(masks[i]).tolist() == g[f"c{ci}_boxes"][i].tolist()
+            assert synth.masks_to_boxes(masks[i:i + 1])[0].tolist() == g[f"c{ci}_boxes"][i].tolist()     # the synthetic generator's boxes
+        if f"c{ci}_image" in g.files:
+            img = g[f"c{ci}_image"]
+            blur = O.gaussian_blur_u8(img)
+            for i in range(n):
+                assert np.array_equal(O.apply_visual_prompt(img, masks[i], "blur", blur), g[f"c{ci}_blur"][i])
+                assert np.array_equal(O.apply_visual_prompt(img, masks[i], "black"), g[f"c{ci}_black"][i])
+    assert O.mask_to_box_xywh(np.zeros((8, 8), bool)).tolist() == g["empty_box"].tolist() == [0, 0, 0, 0]
