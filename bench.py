@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="strong-scaling evaluation sweep (BASELINE.json configs[4]; use with --workload 5)")
     ap.add_argument("--sweep-images", type=int, default=4096)
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not launch the next batch's frame-only chains (blur, prep setup, heat-map tables) "
+                    "inside the current pass (ScoringPath.run(prefetch=...))")
     ap.add_argument("--chunks", type=int, default=1, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
@@ -389,9 +391,17 @@ def run_ours(args, cfg):
     # The step as a CUDA graph (one per device batch): the four-stream stage graph of ScoringPath.run is captured once and
     # replayed with ONE launch per pass; `prep` is bracketed by two event-record nodes inside the graph.
     graphs = None
+    pf = not args.no_prefetch and path.overlap and args.chunks == 1       # batch k's pass launches batch k+1's frame-only chains
+
+    def capture_pair(stages):
+        if not pf:
+            return [path.capture(b, max_n, time_stages=stages) for b in batches]
+        gs = [path.capture(batches[i], max_n, time_stages=stages, prefetch=batches[1 - i], frames_ready=True) for i in range(2)]
+        path.prime(batches[0], max_n)                                       # the first replay (batch 0) finds its frame chains ready
+        return gs
     if not args.no_graph:
-        graphs = [path.capture(b, max_n, time_stages=("prep",)) for b in batches]
-        for w in range(max(3, args.warmup)):
+        graphs = capture_pair(("prep",))
+        for w in range(2 * max(2, args.warmup // 2)):                       # an even count: the next replay is batch 0 again
             graphs[w % 2].replay()
     # inner repeats: a timed "step" is `inner` passes over alternating batches, sized so that the timed region lasts >= ~0.6 s
     # whatever --steps is (a 10 ms region measures launch jitter and rank skew, not the path)
@@ -401,7 +411,7 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         c0.record()
         for w in range(8):
-            (graphs[w % 2].replay() if graphs else path.run(batches[w % 2], max_n))
+            (graphs[w % 2].replay() if graphs else path.run(batches[w % 2], max_n, prefetch=batches[1 - w % 2] if pf else None))
         c1.record()
         torch.cuda.synchronize()
         t_pass = c0.elapsed_time(c1) / 8.0
@@ -434,7 +444,7 @@ def run_ours(args, cfg):
     else:
         for s in range(passes):
             path.events = []
-            path.run(batches[s % 2], max_n)
+            path.run(batches[s % 2], max_n, prefetch=batches[1 - s % 2] if pf else None)
             top_events.append(path.events)
     path.events = None
     path.events_only = None
@@ -498,7 +508,7 @@ def run_ours(args, cfg):
                 take(path.events)
             path.events = None
         else:
-            gs = [path.capture(b, max_n, time_stages=ALL) for b in batches]
+            gs = capture_pair(ALL) if path.overlap else [path.capture(b, max_n, time_stages=ALL) for b in batches]
             for s in range(reps):
                 g = gs[s % 2]
                 g.replay()
@@ -656,7 +666,7 @@ def run_ours(args, cfg):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if prep_dtype == torch.bfloat16 else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(cfg), **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-                "image_groups_per_pass": args.chunks, "inner_repeats": inner, "passes_timed": passes, "ms_per_pass": ms_total / passes, "timed_region_s": ms_total / 1e3,
+                "image_groups_per_pass": args.chunks, "frame_chain_prefetch": bool(pf), "inner_repeats": inner, "passes_timed": passes, "ms_per_pass": ms_total / passes, "timed_region_s": ms_total / 1e3,
                 "collective_ms": collective_ms,
                 "collective": "one all-reduce(SUM) of the int64[4] IoU accumulators after the last pass (NCCL), timed on its own and charged to the job",
                 "l2": f"two alternating batches; the byte masks alone are {B * cfg['n_masks'] * cfg['h'] * cfg['w'] / 1e6:.0f} MB per batch (> 126 MB L2)",

@@ -44,6 +44,8 @@ class ScoringPath:
         self.keep_features = keep_features
         self.chunks = max(1, int(chunks))
         self._plans: Dict[tuple, list] = {}
+        self._ahead = None                  # frame chains a previous call prefetched: dict(key, slot, ev_setup, ev_tables)
+        self._frame_slots: Dict[tuple, int] = {}
         ops.device_ok()
         self.size, self.grid = size, grid
         self.prep_dtype, self.antialias, self.background = prep_dtype, antialias, background
@@ -158,7 +160,82 @@ class ScoringPath:
             v["features"] = batch["features"][m0:m1]
         return v
 
-    def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None, host_off=None) -> Dict[str, torch.Tensor]:
+    @staticmethod
+    def _frame_key(batch):
+        """Identity of the inputs of the frame-only chains (frames, heat-maps, direction flags)."""
+        return tuple((batch[k].data_ptr(), batch[k]._version, tuple(batch[k].shape)) for k in ("image", "heat", "dirflag"))
+
+    def _frame_chain(self, views, plan, slot: int, max_n: int, H: int, W: int, raw: bool, split: bool, launch: bool):
+        """Buffers of one set (`slot`) of frame-chain outputs and, if `launch`, the chains themselves: blur -> prep setup on the
+        `pre` stream, heat-map tables on the `tab` stream, one launch per image group."""
+        lib = ops._lib.load()
+        S, g = self.size, self.grid
+        pre = self._pre if self.overlap else torch.cuda.current_stream()
+        tab = self._tab if self.overlap else torch.cuda.current_stream()
+        n_ch = len(plan)
+        B_all = plan[-1]["b"][1]
+        blur_all = self._get(f"blur@{slot}", (B_all, H, W, 3), torch.uint8) if self.background == "blur" else None
+        pws, hws = [], []
+        ev_setup, ev_tables = [None] * n_ch, [None] * n_ch
+        for c, ch in enumerate(plan):
+            (b0, b1), (m0, m1), (e0, e1) = ch["b"], ch["m"], ch["e"]
+            pws.append(self._get(f"prep_ws{c}@{slot}", (max(lib.hgl_prep_workspace_bytes(b1 - b0, S, ops._dt(self.prep_dtype)), 1),), torch.uint8))
+            hshape = views[c]["heat"].shape
+            need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n, hshape[1], hshape[2]) if raw
+                    else lib.hgl_grid_heat_pool_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n))
+            hws.append(self._get(f"heat_ws{c}@{slot}", (need,), torch.uint8))
+        if launch:
+            def mark():
+                if not self.overlap:
+                    return None
+                ev = torch.cuda.Event()
+                ev.record()
+                return ev
+            with torch.cuda.stream(pre):
+                for c, (ch, v) in enumerate(zip(plan, views)):
+                    b0, b1 = ch["b"]
+                    with self._span("blur"):
+                        blur = ops.gaussian_blur15(v["image"], out=blur_all[b0:b1]) if self.background == "blur" else None
+                    with self._span("prep_setup"):
+                        ops.prep_setup(v["image"], blur, S, background=self.background, dtype=self.prep_dtype, workspace=pws[c])
+                    ev_setup[c] = mark()
+            if split:
+                with torch.cuda.stream(tab):
+                    for c, v in enumerate(views):
+                        if v["heat"].shape[0] == 0:
+                            continue
+                        with self._span("heat_tables"):
+                            ops.heat_tables(v["heat"], v["dirflag"], H, W, hws[c])
+                        ev_tables[c] = mark()
+        return dict(pws=pws, hws=hws, ev_setup=ev_setup, ev_tables=ev_tables)
+
+    def prime(self, batch: Dict[str, torch.Tensor], max_n: int) -> None:
+        """Run only the frame-only chains of `batch` (what a previous call's `prefetch=batch` would have done): the first pass of a
+        prefetching loop -- or the first replay of graphs captured with frames_ready=True -- then finds them ready."""
+        img = batch["image"]
+        B, H, W, _ = img.shape
+        E = batch["sent"].shape[0]
+        M = batch["rle_off"].numel() - 1 if "rle_counts" in batch else batch["masks"].shape[0]
+        raw = tuple(batch["heat"].shape[1:]) != (H, W)
+        if self.overlap and self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            self._pre = torch.cuda.Stream(device=self.device, priority=-1)
+            self._tab = torch.cuda.Stream(device=self.device, priority=-1)
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            for s_ in (self._pre, self._tab):
+                s_.wait_stream(main)
+        key = self._frame_key(batch)
+        slot = self._frame_slots.setdefault(key, 0)
+        fr = self._frame_chain([dict(image=img, heat=batch["heat"], dirflag=batch["dirflag"])], [dict(b=(0, B), m=(0, M), e=(0, E))], slot, max_n, H, W,
+                               raw, self.antialias and E > 0 and M > 0, launch=True)
+        self._ahead = dict(key=key, slot=slot, ev_setup=fr["ev_setup"], ev_tables=fr["ev_tables"])
+        if self.overlap:
+            main.wait_stream(self._pre)
+            main.wait_stream(self._tab)
+
+    def run(self, batch: Dict[str, torch.Tensor], max_n: int, features: Optional[torch.Tensor] = None, host_off=None,
+            prefetch: Optional[Dict[str, torch.Tensor]] = None, frames_ready: bool = False) -> Dict[str, torch.Tensor]:
         """One pass over a device-resident batch.  Returns device tensors (see OUTPUT_KEYS) plus the prep
         outputs `local_imgs`, `global_imgs` [M,3,S,S], `grid` [M,g,g] and `area` [M].
 
@@ -169,7 +246,13 @@ class ScoringPath:
             tab   heat-map tables A, B
             main  (caller's stream)  prep main A (after pack A, setup A), prep main B (after pack B, setup B)
         Only pack and prep main are bandwidth-bound; everything else is small and latency-bound and runs up to 3x slower while HBM
-        is saturated (profiles/r2_timeline.md).  With overlap=False every stage is launched in order on the caller's stream."""
+        is saturated (profiles/r2_timeline.md).  With overlap=False every stage is launched in order on the caller's stream.
+
+        prefetch: the batch the NEXT call will process.  Its frame-only chains (blur -> prep setup, heat-map tables: they need the
+        frames and the heat-maps, not the masks) are launched now, behind this pass's pack, into a second set of buffers, and run in
+        the shadow of this pass's prep writes; the next call finds them done and starts its prep the moment its pack ends -- the
+        HBM-idle gap between pack and prep (blur -> setup crawling beside the pack) disappears from the steady state.
+        frames_ready: (graph capture only) the frame chains of `batch` were produced by the previous replay's prefetch; skip them."""
         img = batch["image"]
         B, H, W, _ = img.shape
         rle = "rle_counts" in batch          # proposals as SAM uncompressed RLE instead of byte masks
@@ -207,7 +290,6 @@ class ScoringPath:
         bits = self._get("bits", (M, H, WW), torch.int32)
         local = self._get("local", (M, 3, S, S), self.prep_dtype)
         glob = self._get("global", (M, 3, S, S), self.prep_dtype)
-        blur_all = self._get("blur", img.shape, torch.uint8) if self.background == "blur" else None
         heat = batch["heat"]           # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
         raw = tuple(heat.shape[1:]) != (H, W)
         split = self.antialias and E > 0 and M > 0
@@ -228,35 +310,38 @@ class ScoringPath:
                         ops.pack_masks(v["masks"], out=bits[m0:m1])
                 ev_pack[c] = mark()
 
-        # ---- chain F (frames only): blur -> per-image half of prep (answer planes).  Runs beside the mask pack.
-        ev_setup = [None] * n_ch
-        pws = []
-        with torch.cuda.stream(pre):
-            for c, (ch, v) in enumerate(zip(plan, views)):
-                b0, b1 = ch["b"]
-                pws.append(self._get(f"prep_ws{c}", (max(lib.hgl_prep_workspace_bytes(b1 - b0, S, ops._dt(self.prep_dtype)), 1),), torch.uint8))
-                with self._span("blur"):
-                    blur = ops.gaussian_blur15(v["image"], out=blur_all[b0:b1]) if self.background == "blur" else None
-                with self._span("prep_setup"):
-                    ops.prep_setup(v["image"], blur, S, background=self.background, dtype=self.prep_dtype, workspace=pws[c])
-                ev_setup[c] = mark()
-
-        # ---- chain T (heat-maps only): the table half of the pooling pass, also beside the mask pack
-        ev_tables = [None] * n_ch
-        hws = []
-        for c, (ch, v) in enumerate(zip(plan, views)):
-            (b0, b1), (m0, m1), (e0, e1) = ch["b"], ch["m"], ch["e"]
-            need = (lib.hgl_grid_heat_pool_raw_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n, heat.shape[1], heat.shape[2]) if raw
-                    else lib.hgl_grid_heat_pool_workspace_bytes(b1 - b0, m1 - m0, e1 - e0, H, W, g, max_n))
-            hws.append(self._get(f"heat_ws{c}", (need,), torch.uint8))
-        if split:
-            with torch.cuda.stream(tab):
-                for c, v in enumerate(views):
-                    if v["heat"].shape[0] == 0:
-                        continue
-                    with self._span("heat_tables"):
-                        ops.heat_tables(v["heat"], v["dirflag"], H, W, hws[c])
-                    ev_tables[c] = mark()
+        # ---- chains F (frames only: blur -> per-image half of prep) and T (heat-maps only: the table half of the pooling pass).
+        #      Either launched now, beside the mask pack, or found ready because the previous call prefetched them.
+        fkey = self._frame_key(batch)
+        if len(self._frame_slots) > 64:
+            self._frame_slots.clear()
+        ahead = self._ahead if (self._ahead is not None and self._ahead["key"] == fkey and n_ch == 1) else None
+        if frames_ready and self._capturing and n_ch == 1:
+            ahead = dict(key=fkey, slot=self._frame_slots.setdefault(fkey, 0), ev_setup=[None], ev_tables=[None])
+        if ahead is not None:
+            fslot = ahead["slot"]
+            fr = self._frame_chain(views, plan, fslot, max_n, H, W, raw, split, launch=False)
+            fr["ev_setup"], fr["ev_tables"] = ahead["ev_setup"], ahead["ev_tables"]
+        else:
+            fslot = self._frame_slots.setdefault(fkey, 0) if n_ch == 1 else 0
+            fr = self._frame_chain(views, plan, fslot, max_n, H, W, raw, split, launch=True)
+        pws, hws, ev_setup, ev_tables = fr["pws"], fr["hws"], fr["ev_setup"], fr["ev_tables"]
+        self._ahead = None
+        if prefetch is not None and self.overlap and n_ch == 1:
+            pkey = self._frame_key(prefetch)
+            pslot = 1 - fslot
+            self._frame_slots[pkey] = pslot
+            pB = prefetch["image"].shape[0]
+            pplan = [dict(b=(0, pB), m=(0, 0), e=(0, prefetch["sent"].shape[0]))]
+            pview = [dict(image=prefetch["image"], heat=prefetch["heat"], dirflag=prefetch["dirflag"])]
+            pM = prefetch["rle_off"].numel() - 1 if "rle_counts" in prefetch else prefetch["masks"].shape[0]
+            pplan[0]["m"] = (0, pM)
+            praw = tuple(prefetch["heat"].shape[1:]) != tuple(prefetch["image"].shape[1:3])
+            psplit = self.antialias and pplan[0]["e"][1] > 0 and pM > 0
+            for s_ in (pre, tab):                       # start in the shadow of THIS pass's prep, not beside its pack
+                s_.wait_event(ev_pack[-1])
+            pf = self._frame_chain(pview, pplan, pslot, max_n, prefetch["image"].shape[1], prefetch["image"].shape[2], praw, psplit, launch=True)
+            self._ahead = dict(key=pkey, slot=pslot, ev_setup=pf["ev_setup"], ev_tables=pf["ev_tables"])
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
@@ -299,6 +384,7 @@ class ScoringPath:
             (b0, b1), (m0, m1) = ch["b"], ch["m"]
             if ev_pack[c] is not None:
                 main.wait_event(ev_pack[c])
+            if ev_setup[c] is not None:
                 main.wait_event(ev_setup[c])
             if m1 == m0:
                 continue
@@ -336,7 +422,7 @@ class ScoringPath:
                    features=feats if (not use_tokens or self.keep_features) else None)
         return res
 
-    def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None) -> "GraphStep":
+    def capture(self, batch: Dict[str, torch.Tensor], max_n: int, time_stages=None, prefetch=None, frames_ready: bool = False) -> "GraphStep":
         """One step as a CUDA graph: the whole stage graph of run() (four streams, ~12 kernels, memsets, fork / join events) is
         captured once for THESE device buffers and replayed with a single launch; the per-launch host work of run() (~0.3 ms
         of ctypes / torch calls per step, profiles/host_overhead.py) disappears from the step.  `batch` must stay alive and keep
@@ -346,9 +432,12 @@ class ScoringPath:
         saved = (self.events, self.events_only)
         self.events, self.events_only = None, None
         cum0 = self.cum.clone()
-        self.run(batch, max_n)                 # eager once: sizes every workspace, creates the streams, sets kernel attributes
+        self.run(batch, max_n, prefetch=prefetch)    # eager once: sizes every workspace, creates the streams, sets kernel attributes
         torch.cuda.current_stream().synchronize()
         self.cum.copy_(cum0)                   # the warm-up step must not count
+        if frames_ready:                       # the capture below skips this batch's own frame chains: make sure the buffers hold them
+            self.prime(batch, max_n)
+            torch.cuda.current_stream().synchronize()
         graph = torch.cuda.CUDAGraph()
         events = []
         if time_stages:
@@ -356,7 +445,7 @@ class ScoringPath:
         self._capturing = True
         try:
             with torch.cuda.graph(graph):
-                res = self.run(batch, max_n)
+                res = self.run(batch, max_n, prefetch=prefetch, frames_ready=frames_ready)
         finally:
             self._capturing = False
             self.events, self.events_only = saved

@@ -795,6 +795,35 @@ def test_captured_step_equals_eager_step(ops):
     assert name == "prep" and e0.elapsed_time(e1) > 0.0
 
 
+def test_frame_chain_prefetch_is_invisible(ops):
+    """ScoringPath.run(prefetch=next): the next batch's blur / prep setup / heat-map tables run inside the current pass; every pass
+    (eager, and replayed from graphs captured with frames_ready=True) gives the bits of a plain pass."""
+    from hybridgl_b200.pipeline import OUTPUT_KEYS, ScoringPath
+    B, h, w, n, e, de, g = 3, 120, 160, 9, 2, 64, 6
+    batches = [synth.make_batch_device(300 + i, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True) for i in range(3)]
+    keys = OUTPUT_KEYS + ("local_imgs", "global_imgs", "grid", "area")
+    plain = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    refs = []
+    for s in range(6):
+        r = plain.run(batches[s % 3], n)
+        refs.append({k: r[k].clone() for k in keys})
+    path = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    for s in range(6):
+        r = path.run(batches[s % 3], n, prefetch=batches[(s + 1) % 3] if s < 5 else None)
+        for k in keys:
+            assert torch.equal(r[k], refs[s][k]), (s, k)
+    assert path.cum.tolist() == plain.cum.tolist()
+    # graphs: batch 0 <-> batch 1 alternating, each replay prefetching the other's frame chains
+    gp = ScoringPath(size=32, grid=g, prep_dtype=torch.bfloat16, feature_source="tokens")
+    gs = [gp.capture(batches[i], n, prefetch=batches[1 - i], frames_ready=True) for i in range(2)]
+    gp.prime(batches[0], n)
+    for s in range(5):
+        out = gs[s % 2].replay()
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(out[k], refs[s % 2][k]), (s, k)
+
+
 @pytest.mark.parametrize("chunks", [2, 3])
 def test_image_groups_inside_a_pass_are_invisible(ops, chunks):
     """ScoringPath(chunks=k): every stage launched once per group of images (ragged batch, one image without expressions) gives the
