@@ -449,6 +449,7 @@ class ScoringPath:
         finally:
             self._capturing = False
             self.events, self.events_only = saved
+            self._ahead = None          # (a prefetch recorded inside the capture has not run, and its events belong to the graph)
         return GraphStep(graph, res, events, batch)
 
     # launches of OUR kernels per run(): blur 1, pack 1, prep 2, grid_heat_pool 3 (prefix, consts, rows), scoring 1 (hgl_score_select, or
