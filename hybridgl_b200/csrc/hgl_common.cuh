@@ -39,6 +39,18 @@ int sm_count();
 // Returns HGL_OK / HGL_ECUDA (error text set).
 int ensure_dyn_smem(const void* kernel, size_t bytes, const char* what);
 
+// The stream's priority as an explicit launch attribute: a kernel launched with it keeps that priority as a NODE of a captured
+// graph too (the small latency-bound kernels of the scoring chain must win SM slots from the bandwidth-bound prep kernel as
+// its CTAs retire, whether the pass is launched eagerly or replayed).
+static inline cudaLaunchAttribute priority_attr(cudaStream_t st) {
+  cudaLaunchAttribute a;
+  int prio = 0;
+  if (cudaStreamGetPriority(st, &prio) != cudaSuccess) { prio = 0; (void)cudaGetLastError(); }
+  a.id = cudaLaunchAttributePriority;
+  a.val.priority = prio;
+  return a;
+}
+
 // ---- device helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -698,7 +698,12 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
   auto go = [&](auto kern) -> int {
     const int rc2 = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, "mask rows pass");
     if (rc2 != HGL_OK) return rc2;
-    kern<<<ctas, kRowsThreads, smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kRowsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1] = {priority_attr(st)};
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e3 = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e3 != cudaSuccess) { set_error("mask rows pass: cudaLaunchKernelEx: %s", cudaGetErrorString(e3)); return HGL_ECUDA; }
     return launch_status("mask rows pass");
   };
   if (want_grid && want_heat) return go(mask_rows_kernel<true, true>);

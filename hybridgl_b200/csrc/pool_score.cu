@@ -665,10 +665,11 @@ static int pool_score_launch(PoolScoreParams& p, const void* tokens, cudaStream_
   cfg.blockDim = dim3(kPsThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)p.NT; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1] = priority_attr(st);
+  cfg.attrs = attr; cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, pool_score_kernel, tmap, p);
   if (e != cudaSuccess) { set_error("%s: cudaLaunchKernelEx: %s", what, cudaGetErrorString(e)); return HGL_ECUDA; }
   return launch_status(what);

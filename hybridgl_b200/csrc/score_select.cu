@@ -226,10 +226,11 @@ extern "C" int hgl_score_select(const void* feat, int feat_dtype, const float* s
   cfg.blockDim = dim3(kScoreThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)p.CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1] = priority_attr((cudaStream_t)stream);
+  cfg.attrs = attr; cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, score_select_kernel, p);
   if (e != cudaSuccess) { set_error("hgl_score_select: cudaLaunchKernelEx: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
   return launch_status("hgl_score_select");
