@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
     ap.add_argument("--no-prefetch", action="store_true", help="do not launch the next batch's frame-only chains (blur, prep setup, heat-map tables) "
                     "inside the current pass (ScoringPath.run(prefetch=...))")
+    ap.add_argument("--rows-first", type=int, default=0, help="1: prep main waits for the mask pass (grid + heat-map pooling) instead of running beside it")
     ap.add_argument("--chunks", type=int, default=1, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--features", default="tokens", choices=["tokens", "supplied"],
@@ -373,7 +374,7 @@ def run_ours(args, cfg):
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
     path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap,
-                       chunks=args.chunks)
+                       chunks=args.chunks, rows_first=bool(args.rows_first))
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
     batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
                                          grid=cfg["g"], raw_heat=True)

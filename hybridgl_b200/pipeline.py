@@ -30,7 +30,7 @@ class ScoringPath:
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
                  feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True,
-                 keep_features: bool = False, chunks: int = 1):
+                 keep_features: bool = False, chunks: int = 1, rows_first: bool = False):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
         under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
@@ -43,6 +43,7 @@ class ScoringPath:
         self.feature_source = feature_source
         self.keep_features = keep_features
         self.chunks = max(1, int(chunks))
+        self.rows_first = bool(rows_first)   # prep main waits for the mask pass (both then run at their stand-alone speed, one after the other)
         self._plans: Dict[tuple, list] = {}
         self._ahead = None                  # frame chains a previous call prefetched: dict(key, slot, ev_setup, ev_tables)
         self._frame_slots: Dict[tuple, int] = {}
@@ -378,6 +379,10 @@ class ScoringPath:
                         g_, a_ = ops.masks_to_grid(cb, g, antialias=False, want_area=True, width=W)
                         grid[m0:m1].copy_(g_); area[m0:m1].copy_(a_)
                         score_gem[e0:e1].copy_(ops.heat_pool(hv, v["dirflag"], v["black"], cb, ch_moff, ch_eoff, max_n, workspace=hws[c]))
+
+            ev_rows = mark() if self.rows_first else None
+        if self.rows_first and self.overlap and ev_rows is not None:
+            main.wait_event(ev_rows)
 
         # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
         for c, (ch, v) in enumerate(zip(plan, views)):
