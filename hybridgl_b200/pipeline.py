@@ -328,21 +328,6 @@ class ScoringPath:
             fr = self._frame_chain(views, plan, fslot, max_n, H, W, raw, split, launch=True)
         pws, hws, ev_setup, ev_tables = fr["pws"], fr["hws"], fr["ev_setup"], fr["ev_tables"]
         self._ahead = None
-        if prefetch is not None and self.overlap and n_ch == 1:
-            pkey = self._frame_key(prefetch)
-            pslot = 1 - fslot
-            self._frame_slots[pkey] = pslot
-            pB = prefetch["image"].shape[0]
-            pplan = [dict(b=(0, pB), m=(0, 0), e=(0, prefetch["sent"].shape[0]))]
-            pview = [dict(image=prefetch["image"], heat=prefetch["heat"], dirflag=prefetch["dirflag"])]
-            pM = prefetch["rle_off"].numel() - 1 if "rle_counts" in prefetch else prefetch["masks"].shape[0]
-            pplan[0]["m"] = (0, pM)
-            praw = tuple(prefetch["heat"].shape[1:]) != tuple(prefetch["image"].shape[1:3])
-            psplit = self.antialias and pplan[0]["e"][1] > 0 and pM > 0
-            for s_ in (pre, tab):                       # start in the shadow of THIS pass's prep, not beside its pack
-                s_.wait_event(ev_pack[-1])
-            pf = self._frame_chain(pview, pplan, pslot, max_n, prefetch["image"].shape[1], prefetch["image"].shape[2], praw, psplit, launch=True)
-            self._ahead = dict(key=pkey, slot=pslot, ev_setup=pf["ev_setup"], ev_tables=pf["ev_tables"])
 
         # ---- chain S continued: everything that only needs the packed masks
         with torch.cuda.stream(side):
@@ -381,8 +366,24 @@ class ScoringPath:
                         score_gem[e0:e1].copy_(ops.heat_pool(hv, v["dirflag"], v["black"], cb, ch_moff, ch_eoff, max_n, workspace=hws[c]))
 
             ev_rows = mark() if self.rows_first else None
-        if self.rows_first and self.overlap and ev_rows is not None:
+        if ev_rows is not None:
             main.wait_event(ev_rows)
+
+        if prefetch is not None and self.overlap and n_ch == 1:
+            pkey = self._frame_key(prefetch)
+            pslot = 1 - fslot
+            self._frame_slots[pkey] = pslot
+            pB = prefetch["image"].shape[0]
+            pplan = [dict(b=(0, pB), m=(0, 0), e=(0, prefetch["sent"].shape[0]))]
+            pview = [dict(image=prefetch["image"], heat=prefetch["heat"], dirflag=prefetch["dirflag"])]
+            pM = prefetch["rle_off"].numel() - 1 if "rle_counts" in prefetch else prefetch["masks"].shape[0]
+            pplan[0]["m"] = (0, pM)
+            praw = tuple(prefetch["heat"].shape[1:]) != tuple(prefetch["image"].shape[1:3])
+            psplit = self.antialias and pplan[0]["e"][1] > 0 and pM > 0
+            for s_ in (pre, tab):                       # start in the shadow of THIS pass's prep: not beside its pack, nor its mask pass
+                s_.wait_event(ev_rows if ev_rows is not None else ev_pack[-1])
+            pf = self._frame_chain(pview, pplan, pslot, max_n, prefetch["image"].shape[1], prefetch["image"].shape[2], praw, psplit, launch=True)
+            self._ahead = dict(key=pkey, slot=pslot, ev_setup=pf["ev_setup"], ev_tables=pf["ev_tables"])
 
         # ---- chain P (caller's stream): the per-mask half of prep, the bandwidth-bound bulk of the step
         for c, (ch, v) in enumerate(zip(plan, views)):
