@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="strong-scaling evaluation sweep (BASELINE.json configs[4]; use with --workload 5)")
     ap.add_argument("--sweep-images", type=int, default=4096)
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
-    ap.add_argument("--no-prefetch", action="store_true", help="do not launch the next batch's frame-only chains (blur, prep setup, heat-map tables) "
-                    "inside the current pass (ScoringPath.run(prefetch=...))")
+    ap.add_argument("--prefetch", action="store_true", help="launch the next batch's frame-only chains (blur, prep setup, heat-map tables) inside the "
+                    "current pass (ScoringPath.run(prefetch=...)); measured no faster on B200: the step is the SUM of the kernels' stand-alone times")
     ap.add_argument("--rows-first", type=int, default=0, help="1: prep main waits for the mask pass (grid + heat-map pooling) instead of running beside it")
     ap.add_argument("--chunks", type=int, default=1, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
@@ -392,7 +392,7 @@ def run_ours(args, cfg):
     # The step as a CUDA graph (one per device batch): the four-stream stage graph of ScoringPath.run is captured once and
     # replayed with ONE launch per pass; `prep` is bracketed by two event-record nodes inside the graph.
     graphs = None
-    pf = not args.no_prefetch and path.overlap and args.chunks == 1       # batch k's pass launches batch k+1's frame-only chains
+    pf = args.prefetch and path.overlap and args.chunks == 1       # batch k's pass launches batch k+1's frame-only chains
 
     def capture_pair(stages):
         if not pf:

@@ -38,9 +38,10 @@ constexpr int kPsThreads = 512;   // 16 warps (4 per scheduler: a lone warp issu
                                   // bound): all stage A; thread 0 issues TMA + MMA; warps w, w+4, w+8, w+12 share TMEM lanes 32*(w%4)..
 constexpr int kPsM = 128;         // proposals per row tile (UMMA M)
 constexpr int kPsKC = 64;         // tokens per ring stage (4 MMA k-steps)
-constexpr int kPsER = 4;          // expressions per scoring round
+constexpr int kPsER = 4;          // expressions per scoring round (== kPsThreads / kPsM: the reduction maps a thread to (row, expression))
 constexpr int kPsMaxTiles = 4;    // row tiles per image (512 proposals)
 constexpr int kPsMaxStages = 8;
+static_assert(kPsThreads / kPsM == kPsER, "rank-0 reduction: one thread per (row, expression of the round)");
 constexpr uint32_t kPsAHalf = kPsM * kPsKC * 2;   // one bf16 [128 x 64] operand block (hi or lo)
 constexpr uint32_t kPsBBox = kPsKC * 64 * 2;      // one TMA box: 64 tokens x 64 columns bf16
 constexpr int kPsPiece = 64;      // output columns staged through shared memory per round of the feature pass
@@ -508,40 +509,31 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
       PS_TRACE(9);
       cluster_sync_all();                                        // every CTA's partial sums have landed in rank 0
       PS_TRACE(10);
-      if (rank == 0 && tid < kPsM) {
-        const float* src = gather + tid;
-        const int grow = tile * kPsM + tid;
-        float acc[kNP], tn[2 * kPsER];                           // independent accumulators: the loads of a slice overlap
-#pragma unroll
-        for (int k = 0; k < kNP; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2 * kPsER; ++k) tn[k] = 0.f;
+      if (rank == 0) {
+        // thread (row, j): the row's scores against expression j of the round -- all 16 warps share the reduction
+        const int row = tid & (kPsM - 1), j = tid >> 7;          // kPsThreads / kPsM == kPsER
+        const float* src = gather + row;
+        const int grow = tile * kPsM + row;
+        float ss = 0.f, a = 0.f, g = 0.f, ta = 0.f, tg = 0.f;
 #pragma unroll 4
         for (int c = 0; c < NT; ++c) {
-          if (rd == 0) acc[0] += src[(size_t)c * kNP * kPsM];
-#pragma unroll
-          for (int j = 0; j < kPsER; ++j) {
-            if (j < ne) {
-              acc[1 + j] += src[((size_t)c * kNP + 1 + j) * kPsM];
-              acc[1 + kPsER + j] += src[((size_t)c * kNP + 1 + kPsER + j) * kPsM];
-              tn[j] += gather_tn[c * 2 * kPsER + j];
-              tn[kPsER + j] += gather_tn[c * 2 * kPsER + kPsER + j];
-            }
+          if (rd == 0) ss += src[(size_t)c * kNP * kPsM];
+          if (j < ne) {
+            a += src[((size_t)c * kNP + 1 + j) * kPsM];
+            g += src[((size_t)c * kNP + 1 + kPsER + j) * kPsM];
+            ta += gather_tn[c * 2 * kPsER + j];
+            tg += gather_tn[c * 2 * kPsER + kPsER + j];
           }
         }
-        float fnorm;
-        if (rd == 0) { fnorm = sqrtf(acc[0]); inv_s[grow] = fnorm; }     // |row|; turned into 1/|row| (or 1) by the feature pass
-        else fnorm = inv_s[grow];
-#pragma unroll
-        for (int j = 0; j < kPsER; ++j) {
-          if (j < ne) {
-            // scale * (f/|f|) . (t/|t|); a zero 'neg' vector gives 0/0 = NaN exactly like the reference (App. B-5)
-            const float s_pos = p.scale * __fdiv_rn(__fdiv_rn(acc[1 + j], fnorm), sqrtf(tn[j]));
-            const float s_neg = p.scale * __fdiv_rn(__fdiv_rn(acc[1 + kPsER + j], fnorm), sqrtf(tn[kPsER + j]));
-            sc[j * rows_pad + grow] = s_pos;
-            sc[(kPsER + j) * rows_pad + grow] = s_neg;
-            if (grow < n) p.tail.score_clip[(size_t)(e_lo + rd * kPsER + j) * p.max_n + grow] = s_pos;
-          }
+        const float fnorm = (rd == 0) ? sqrtf(ss) : inv_s[grow];
+        if (rd == 0 && j == 0) inv_s[grow] = fnorm;              // |row|; turned into 1/|row| (or 1) by the feature pass
+        if (j < ne) {
+          // scale * (f/|f|) . (t/|t|); a zero 'neg' vector gives 0/0 = NaN exactly like the reference (App. B-5)
+          const float s_pos = p.scale * __fdiv_rn(__fdiv_rn(a, fnorm), sqrtf(ta));
+          const float s_neg = p.scale * __fdiv_rn(__fdiv_rn(g, fnorm), sqrtf(tg));
+          sc[j * rows_pad + grow] = s_pos;
+          sc[(kPsER + j) * rows_pad + grow] = s_neg;
+          if (grow < n) p.tail.score_clip[(size_t)(e_lo + rd * kPsER + j) * p.max_n + grow] = s_pos;
         }
       }
       // another exchange follows (next tile / round) or the peers still need the row norms: rank 0 must be done reading first
