@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--sweep-pool", type=int, default=4, help="distinct synthetic batches the sweep cycles through")
     ap.add_argument("--prefetch", action="store_true", help="launch the next batch's frame-only chains (blur, prep setup, heat-map tables) inside the "
                     "current pass (ScoringPath.run(prefetch=...)); measured no faster on B200: the step is the SUM of the kernels' stand-alone times")
+    ap.add_argument("--gem-space", default="pixel", choices=["pixel", "token"], help="score_gem from heat-map tables in pixel space (the reference's "
+                    "formulation) or on the raw GEM map's token grid (hgl_gem_token_pool, no frame-sized tables); the other one is timed next to it")
     ap.add_argument("--rows-first", type=int, default=0, help="1: prep main waits for the mask pass (grid + heat-map pooling) instead of running beside it")
     ap.add_argument("--chunks", type=int, default=1, help="image groups a batch is cut into inside ScoringPath.run (stage pipelining within a pass)")
     ap.add_argument("--prep-dtype", default="bf16", choices=["bf16", "f32"])
@@ -374,7 +376,7 @@ def run_ours(args, cfg):
     B = args.images
     prep_dtype = torch.bfloat16 if args.prep_dtype == "bf16" else torch.float32
     path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap,
-                       chunks=args.chunks, rows_first=bool(args.rows_first))
+                       chunks=args.chunks, rows_first=bool(args.rows_first), gem_space=args.gem_space)
     # two distinct device batches, alternated, each far larger than the 126 MB L2 (masks alone: B*N*H*W bytes)
     batches = [synth.make_batch_device(1000 + 17 * rank + i, B, cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["De"], device=dev,
                                          grid=cfg["g"], raw_heat=True)
@@ -650,6 +652,35 @@ def run_ours(args, cfg):
             del rhost
         path.cum.copy_(cum_bytes)
 
+    # ---- the other formulation of the GEM pooling, timed next to the one the headline uses
+    other = "token" if args.gem_space == "pixel" else "pixel"
+    alt_path = ScoringPath(size=cfg["S"], grid=cfg["g"], prep_dtype=prep_dtype, feature_source=args.features, overlap=not args.no_overlap,
+                           gem_space=other)
+    alt_info = None
+    try:
+        ag = [alt_path.capture(b, max_n, time_stages=("grid_heat_pool", "heat_tables")) for b in batches]
+        for w in range(4):
+            ag[w % 2].replay()
+        barrier()
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for s in range(100):
+            ag[s % 2].replay()
+        a1.record()
+        barrier()
+        st_ms = {}
+        for g_ in ag:
+            for name, e0, e1 in g_.events:
+                st_ms[name] = st_ms.get(name, 0.0) + e0.elapsed_time(e1) / len(ag)
+        alt_info = {"gem_space": other, "ms_per_pass": a0.elapsed_time(a1) / 100, "value": expr_per_pass / (a0.elapsed_time(a1) / 100 / 1e3) / world * world,
+                    "stage_ms_in_step": {k: round(v, 4) for k, v in st_ms.items()},
+                    "note": "same pass with score_gem computed by the other formulation; results agree to 1e-3 "
+                            "(tests/test_gpu_parity.py::test_pipeline_token_space_gem_equals_pixel_space_picks)"}
+        del ag
+    except Exception as ex:
+        alt_info = {"gem_space": other, "unavailable": f"{type(ex).__name__}: {ex}"}
+    del alt_path
+
     with_backbone = None
     if rank == 0 and world == 1 and not args.no_backbone_view:
         try:
@@ -677,6 +708,7 @@ def run_ours(args, cfg):
                 "streams": ("4 (prep on the caller's stream; pack -> mask pass -> pooling+scoring -> IoU, blur -> prep setup, heat-map tables on "
                             "high-priority helper streams)" if path.overlap else "1"),
                 "ms_per_pass_serial": ms_serial,
+                "gem_space": args.gem_space, "gem_other_formulation": alt_info,
                 "roofline": roofline, "kernels": kernels, "timeline_ms": timelines, "rle_input": rle_info, "cpu_baseline": cpu,
                 "iou": {"cum_I": c[0], "cum_U": c[1], "cum_I_final": c[2], "cum_U_final": c[3],
                         "oIoU": c[0] * 100.0 / max(c[1], 1), "oIoU_final": c[2] * 100.0 / max(c[3], 1)}}

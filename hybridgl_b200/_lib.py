@@ -51,6 +51,9 @@ SIGNATURES = {
     "hgl_grid_heat_pool_raw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),
+    "hgl_gem_token_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "hgl_gem_token_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p]),
     "hgl_heat_tables": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_grid_heat_pool_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -243,7 +243,7 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
 
 
 # ---- (a2)-(a4) ----------------------------------------------------------------------------------------
-def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area: bool = False, width: Optional[int] = None):
+def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area: bool = False, width: Optional[int] = None, out=None):
     """TF.resize(pred_masks.float(), (g, g)) model/backbone.py:160 -> f32 [M,g,g] (and int32 areas [M]).
     `masks`: bool/u8 [M,H,W] (packed internally) or packed int32 [M,H,ceil(W/32)] together with `width`."""
     if masks.dtype == torch.int32:
@@ -257,8 +257,11 @@ def masks_to_grid(masks: torch.Tensor, g: int, antialias: bool = True, want_area
         m = _mask_bytes(masks)
         M, H, W = m.shape
         bits = pack_masks(m)
-    grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
-    area = torch.empty((M,), dtype=torch.int32, device=bits.device) if want_area else None
+    if out is not None:                      # caller-supplied (grid [M,g,g] f32, area [M] i32 or None)
+        grid, area = out
+    else:
+        grid = torch.empty((M, g, g), dtype=torch.float32, device=bits.device)
+        area = torch.empty((M,), dtype=torch.int32, device=bits.device) if want_area else None
     ws = None
     if antialias:
         ws = torch.empty((max(_lib.load().hgl_mask_grid_workspace_bytes(M, g), 1),), dtype=torch.uint8, device=bits.device)
@@ -444,6 +447,40 @@ def grid_heat_pool(bits: torch.Tensor, width: int, g: int, heat: torch.Tensor, d
                                  heat.data_ptr(), _ptr(eoff), dirflag.data_ptr(), black.data_ptr(), E, max_n,
                                  out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_grid_heat_pool")
     return grid, area, out
+
+
+def gem_token_pool(bits: torch.Tensor, width: int, heat_raw: torch.Tensor, dirflag: torch.Tensor, black: torch.Tensor,
+                   mask_off: Optional[torch.Tensor] = None, expr_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None,
+                   workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """score_gem f32 [E,max_n] of Hybridgl_main.py:200-223 computed in TOKEN space (hgl_gem_token_pool): the packed masks are
+    resampled onto the raw GEM map's grid by the adjoint of the up-sampler and contracted with the raw maps; no frame-sized
+    heat-map or table exists.  bits int32 [M,H,ceil(W/32)], heat_raw f32 [E,hh,hw] (the map as the GEM model returns it)."""
+    _req(bits, torch.int32, "bits", 3)
+    _req(heat_raw, torch.float32, "heat_raw", 3)
+    _req(dirflag, torch.int32, "dirflag", 1)
+    _req(black, torch.float32, "black", 1)
+    M, H, W = bits.shape[0], bits.shape[1], int(width)
+    E, hh, hw = heat_raw.shape
+    if bits.shape[2] != (W + 31) // 32:
+        raise ValueError("packed masks and width disagree")
+    B = 1 if mask_off is None else mask_off.numel() - 1
+    moff = _offsets(mask_off, B, "mask_off")
+    eoff = _offsets(expr_off, B, "expr_off")
+    if max_n is None:
+        if B != 1:
+            raise ValueError("max_n is required for batched calls")
+        max_n = max(M, 1)
+    lib = _lib.load()
+    need = lib.hgl_gem_token_workspace_bytes(B, M, E, H, W, hh, hw, max_n)
+    if need < 0:
+        raise ValueError("gem_token_pool: unsupported shape")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=bits.device)
+    if out is None:
+        out = torch.empty((E, max_n), dtype=torch.float32, device=bits.device)
+    check(lib.hgl_gem_token_pool(bits.data_ptr(), _ptr(moff), B, M, H, W, heat_raw.data_ptr(), hh, hw, _ptr(eoff), dirflag.data_ptr(),
+                                 black.data_ptr(), E, max_n, out.data_ptr(), workspace.data_ptr(), _stream()), "hgl_gem_token_pool")
+    return out
 
 
 def heat_tables(heat: torch.Tensor, dirflag: torch.Tensor, H: int, W: int, workspace: torch.Tensor) -> None:

@@ -30,12 +30,14 @@ class ScoringPath:
     def __init__(self, size: int = 224, grid: int = 14, prep_dtype: torch.dtype = torch.bfloat16, antialias: bool = True,
                  background: str = "blur", logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
                  feature_source: str = "supplied", device: Optional[torch.device] = None, overlap: bool = True,
-                 keep_features: bool = False, chunks: int = 1, rows_first: bool = False):
+                 keep_features: bool = False, chunks: int = 1, rows_first: bool = False, gem_space: str = "pixel"):
         """feature_source: "supplied" -> batch["features"] [M,De] (the hybrid CLIP features of CLIPViTFM.forward) are scored;
         "tokens" -> batch["tokens"] [B,L,De] (dense patch tokens, third_party/modified_CLIP/clip/model.py:302-307) are pooled
         under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
         keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"].
         chunks: groups of images a batch is cut into inside run() (see there); 1 = every stage once per batch (the default:
+        gem_space: "pixel" = heat-map tables + one fused pass over the masks (hgl_heat_tables + hgl_grid_heat_pool_rows); "token" =
+        score_gem computed on the raw GEM map's token grid (hgl_gem_token_pool; needs raw maps) next to hgl_mask_grid.
         measured on B200 at the bench shape, 2 / 4 groups are SLOWER -- 0.55 / 0.66 ms against 0.50 ms per pass -- because the
         small latency-bound kernels a group's prep waits for crawl while another group's pack saturates HBM)."""
         if feature_source not in ("supplied", "tokens"):
@@ -43,6 +45,9 @@ class ScoringPath:
         self.feature_source = feature_source
         self.keep_features = keep_features
         self.chunks = max(1, int(chunks))
+        if gem_space not in ("pixel", "token"):
+            raise ValueError(gem_space)
+        self.gem_space = gem_space           # "token": score_gem from the raw GEM maps in token space (hgl_gem_token_pool): no frame-sized tables
         self.rows_first = bool(rows_first)   # prep main waits for the mask pass (both then run at their stand-alone speed, one after the other)
         self._plans: Dict[tuple, list] = {}
         self._ahead = None                  # frame chains a previous call prefetched: dict(key, slot, ev_setup, ev_tables)
@@ -293,7 +298,8 @@ class ScoringPath:
         glob = self._get("global", (M, 3, S, S), self.prep_dtype)
         heat = batch["heat"]           # frame-sized [E,H,W], or the raw GEM map [E,h,w] (resized like Hybridgl_main.py:201 on the fly)
         raw = tuple(heat.shape[1:]) != (H, W)
-        split = self.antialias and E > 0 and M > 0
+        gem_token = self.gem_space == "token" and raw and self.antialias and E > 0 and M > 0
+        split = self.antialias and E > 0 and M > 0 and not gem_token
         use_tokens = self.feature_source == "tokens" and features is None
         feats_in = features if features is not None else batch.get("features")
         n_ch = len(plan)
@@ -351,6 +357,13 @@ class ScoringPath:
                 with self._span("grid_heat_pool"):
                     if m1 == m0:
                         pass
+                    elif gem_token:            # token-space GEM pooling: mask grid (antialiased) + adjoint-resampled masks . raw maps
+                        ops.masks_to_grid(cb, g, antialias=True, want_area=True, width=W, out=(grid[m0:m1], area[m0:m1]))
+                        if e1 > e0:
+                            ops.gem_token_pool(cb, W, v["heat"], v["dirflag"], v["black"], ch_moff, ch_eoff, max_n,
+                                               workspace=self._get(f"gem_ws{c}", (max(lib.hgl_gem_token_workspace_bytes(
+                                                   ch["b"][1] - ch["b"][0], m1 - m0, e1 - e0, H, W, heat.shape[1], heat.shape[2], max_n), 1),), torch.uint8),
+                                               out=score_gem[e0:e1])
                     elif split and e1 > e0:    # mask grid + heat-map pooling share one pass over the packed masks
                         ops.grid_heat_pool_rows(cb, W, g, v["heat"].shape, v["black"], ch_moff, ch_eoff, max_n, hws[c],
                                                 out=(grid[m0:m1], area[m0:m1], score_gem[e0:e1]))

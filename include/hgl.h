@@ -192,6 +192,18 @@ HGL_API int hgl_grid_heat_pool_rows(const uint32_t* bits, const int32_t* mask_of
                             float* grid, int32_t* area, int hh, int hw, const int32_t* expr_off, const float* black, int E,
                             int max_n, float* score_gem, void* workspace, void* stream);
 
+/* ---- (f3) GEM heat-map pooling in token space ---------------------------------------------------------
+ * The same score_gem as hgl_grid_heat_pool_raw (Hybridgl_main.py:200-223) WITHOUT the frame-sized heat-map: the resize of
+ * Hybridgl_main.py:201 is linear, so sum_p m_n(p) A''(p) = kk * (G_n . h - mn * sum(G_n)) with G_n = the mask resampled onto the
+ * raw map's token grid by the adjoint of the up-sampler (direction ramp folded in) and mn / kk per-expression scalars
+ * (SURVEY.md Appendix A-2).  No [E,H,W] tables are written or gathered from.  Results agree with the pixel-space entry points
+ * to float rounding (tests: 1e-3 relative).  heat_raw f32 [E,hh,hw] with hh <= H, hw <= W (an up-sampled map), hh, hw <= 128.
+ * workspace: hgl_gem_token_workspace_bytes(...) bytes, 16-byte aligned, zeroing not required. */
+HGL_API int64_t hgl_gem_token_workspace_bytes(int B, int M, int E, int H, int W, int hh, int hw, int max_n);
+HGL_API int hgl_gem_token_pool(const uint32_t* bits, const int32_t* mask_off, int B, int M, int H, int W,
+                       const float* heat_raw, int hh, int hw, const int32_t* expr_off, const int32_t* dirflag, const float* black, int E,
+                       int max_n, float* score_gem, void* workspace, void* stream);
+
 /* ---- (b3') token-space mask pooling + L2 normalisation (tensor cores) ---------------------------------
  * The masks x tokens x D contraction of the north star; token-space form of the pooling loop Hybridgl_main.py:218-223
  * (S_in = (M~ . F^) . t) with the normalisation of model/backbone.py:79 fused:

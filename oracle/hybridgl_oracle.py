@@ -350,6 +350,34 @@ def gem_pool(cond_heatmap: np.ndarray, masks: np.ndarray, black: float) -> np.nd
         return ((2 - black) * s_in / area - black * (s_tot - s_in) / (hw - area)).astype(f32)
 
 
+def aa_matrix(in_size: int, out_size: int) -> np.ndarray:
+    """The antialiased bilinear filter of aa_taps() as a dense [out_size, in_size] float64 matrix."""
+    U = np.zeros((out_size, in_size), f64)
+    for i, (xmin, wt) in enumerate(aa_taps(in_size, out_size)):
+        U[i, xmin:xmin + wt.size] = wt
+    return U
+
+
+def gem_pool_token_space(heat_raw: np.ndarray, masks: np.ndarray, dirflag: str, black: float) -> np.ndarray:
+    """Hybridgl_main.py:200-223 evaluated in token space: with A = Uy h Ux^T the pooled sums are
+    S_in[n] = kk * (G_n . h - mn * sum G_n),  G_n = Uy^T (m_n * ramp) Ux,  kk = H*W / (C . h - mn * sum C),  C = G of the full frame,
+    mn = min A, S_tot = H*W.  The matrix form of resize_bilinear_aa -> condition_heatmap -> gem_pool; tests pin it to that chain."""
+    h = np.asarray(heat_raw, f64)
+    m = np.asarray(masks).astype(bool)
+    n, H, W = m.shape
+    Uy, Ux = aa_matrix(h.shape[0], H), aa_matrix(h.shape[1], W)
+    A = Uy @ h @ Ux.T
+    ramp = gen_dir_mask(dirflag, 1, W)[0].astype(f64)
+    mn = A.min()
+    G = np.einsum("yi,nyx,xj->nij", Uy, m * ramp[None, None, :], Ux)
+    C = np.einsum("yi,x,xj->ij", Uy, ramp, Ux)
+    kk = H * W / ((C * h).sum() - mn * C.sum())
+    s_in = kk * ((G * h[None]).sum((1, 2)) - mn * G.sum((1, 2)))
+    area = m.reshape(n, -1).sum(1).astype(f64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return ((2 - black) * s_in / area - black * (H * W - s_in) / (H * W - area)).astype(f32)
+
+
 def score_and_select(features, sentence_feat, noun_feat, other_feats, boxes, relaflag,
                      score_gem=None, logit_scale_exp: float = 100.0, r: float = 0.5, alpha: float = 0.6,
                      k1: int = 3, k2: int = 6):

@@ -442,6 +442,53 @@ def test_device_resident_proposals_rle_to_boxes(ops):
     assert np.array_equal(boxes.cpu().numpy(), it.boxes)
 
 
+# ------------------------------------------------------------------------------------------------ token-space GEM pooling (f3)
+@pytest.mark.parametrize("h,w,hh,hw,spec", [(96, 128, 14, 19, [(7, 2), (3, 1), (12, 3), (1, 2)]), (480, 640, 28, 37, [(20, 3), (9, 2)]),
+                                            (600, 800, 28, 37, [(6, 5)]), (97, 131, 9, 11, [(5, 1), (4, 4)])])
+def test_gem_token_pool_vs_pixel_space(ops, h, w, hh, hw, spec):
+    """hgl_gem_token_pool (no frame-sized heat-map) against the pixel-space kernels and the oracle chain, 1e-3 relative, for every
+    direction ramp and black value; ragged batch."""
+    rng = np.random.default_rng(h + hw)
+    items = [synth.make_item(800 + i, h, w, n, e, de=16) for i, (n, e) in enumerate(spec)]
+    masks = np.concatenate([it.masks for it in items])
+    masks[0] = False; masks[0, h // 3:h // 3 + 3, w // 2:w // 2 + 5] = True            # a tiny mask
+    moff = np.cumsum([0] + [n for n, _ in spec]).astype(np.int32); eoff = np.cumsum([0] + [e for _, e in spec]).astype(np.int32)
+    E = int(eoff[-1]); max_n = max(n for n, _ in spec)
+    raw = rng.random((E, hh, hw), dtype=np.float32)
+    dirs = (np.arange(E) % 6).astype(np.int32)
+    black = np.array([(1.8, 1.95, 1.5)[i % 3] for i in range(E)], np.float32)
+    bits = ops.pack_masks(cu(masks))
+    got = ops.gem_token_pool(bits, w, cu(raw), cu(dirs), cu(black), cu(moff), cu(eoff), max_n).cpu().numpy()
+    _, _, pix = ops.grid_heat_pool(bits, w, 6, cu(raw), cu(dirs), cu(black), cu(moff), cu(eoff), max_n)
+    pix = pix.cpu().numpy()
+    for b, (n, e_cnt) in enumerate(spec):
+        for e in range(eoff[b], eoff[b + 1]):
+            np.testing.assert_allclose(got[e, :n], pix[e, :n], rtol=1e-3, atol=2e-4, err_msg=f"expr {e}")
+            assert np.all(got[e, n:] == 0)
+            if h * w <= 20000:
+                ref = O.gem_pool_token_space(raw[e], masks[moff[b]:moff[b + 1]], synth.DIRFLAGS[int(dirs[e])], float(black[e]))
+                np.testing.assert_allclose(got[e, :n], ref, rtol=1e-3, atol=2e-4)
+
+
+def test_pipeline_token_space_gem_equals_pixel_space_picks(ops):
+    """ScoringPath(gem_space="token") against gem_space="pixel": same grid / scores / IoU inputs, score_gem within 1e-3, same picks
+    wherever the blended margins are clear."""
+    from hybridgl_b200.pipeline import ScoringPath
+    B, h, w, n, e, de, g = 3, 240, 320, 20, 3, 64, 6
+    batch = synth.make_batch_device(55, B, h, w, n, e, de, device=DEV, grid=g, raw_heat=True)
+    a = ScoringPath(size=32, grid=g, feature_source="tokens", gem_space="pixel").run(batch, n)
+    a = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.items()}
+    b = ScoringPath(size=32, grid=g, feature_source="tokens", gem_space="token").run(batch, n)
+    torch.cuda.synchronize()
+    for k in ("grid", "area", "score_clip", "idx_hybrid", "local_imgs", "global_imgs"):
+        assert torch.equal(a[k], b[k]), k
+    np.testing.assert_allclose(b["score_gem"].cpu().numpy(), a["score_gem"].cpu().numpy(), rtol=1e-3, atol=2e-4)
+    bl = a["blended"].cpu().numpy()
+    clear = np.sort(bl, 1)[:, -1] - np.sort(bl, 1)[:, -2] > 5e-3
+    assert clear.sum() >= len(clear) // 2
+    assert np.array_equal(a["idx_final"].cpu().numpy()[clear], b["idx_final"].cpu().numpy()[clear])
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core mask pooling
 @pytest.mark.parametrize("B,n,L,D,dtype", [(1, 100, 196, 768, torch.float32), (2, 37, 196, 512, torch.float32), (1, 200, 576, 1024, torch.float32),
                                            (3, 130, 49, 64, torch.float32), (1, 5, 16, 32, torch.bfloat16), (2, 150, 196, 768, torch.bfloat16)])

@@ -187,3 +187,14 @@ def test_geometry_and_prompts_match_reference(golden):
                 assert np.array_equal(O.apply_visual_prompt(img, masks[i], "blur", blur), g[f"c{ci}_blur"][i])
                 assert np.array_equal(O.apply_visual_prompt(img, masks[i], "black"), g[f"c{ci}_black"][i])
     assert O.mask_to_box_xywh(np.zeros((8, 8), bool)).tolist() == g["empty_box"].tolist() == [0, 0, 0, 0]
+
+
+def test_token_space_gem_pooling_equals_pixel_space_chain():
+    """O.gem_pool_token_space (the oracle of hgl_gem_token_pool: masks resampled onto the raw GEM map's grid, affine conditioning as
+    per-expression scalars) against the pinned pixel-space chain resize_bilinear_aa -> condition_heatmap -> gem_pool, 1e-3."""
+    it = synth.make_item(3, 96, 128, 6, 6, de=32)
+    it.masks[0] = False; it.masks[0, 40:44, 60:70] = True
+    for ex, d, bl in zip(it.expressions, synth.DIRFLAGS, (1.8, 1.95, 1.5, 1.8, 1.8, 1.5)):
+        full = O.resize_bilinear_aa(ex.heat_raw[None], 96, 128)[0]
+        ref = O.gem_pool(O.condition_heatmap(full, d), it.masks, bl)
+        np.testing.assert_allclose(O.gem_pool_token_space(ex.heat_raw, it.masks, d, bl), ref, rtol=1e-3, atol=1e-4)
