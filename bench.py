@@ -144,16 +144,41 @@ def _oracle_one_image(args):
     return time.perf_counter() - t0
 
 
+def _ref_available() -> bool:
+    try:
+        from oracle import ref_runner
+        return ref_runner.ref_root() is not None
+    except Exception:
+        return False
+
+
+def _reference_one_image(args):
+    """The same image through the REAL reference code (oracle/_ref, copied by oracle/make_ref.py): Hybridgl_main.py:92-125 and
+    :153-230 exec'd in place + TF.resize of the masks (model/backbone.py:160), one thread."""
+    seed, cfg, n_masks = args
+    from oracle import ref_runner
+    return ref_runner.run_image(seed, cfg, n_masks, threads=1)["seconds"]
+
+
+def _cpu_arm():
+    """(worker function, kind, description) of the CPU arm: the reference's own code when oracle/_ref travelled, else the numpy port."""
+    if _ref_available():
+        return _reference_one_image, "reference", ("the reference's own code (oracle/_ref: Hybridgl_main.py:92-125 prep loop, model/backbone.py:160 mask "
+                                                  "resize, Hybridgl_main.py:153-230 scoring / guidance / IoU per expression; CLIP features, GEM maps and "
+                                                  "spaCy flags are inputs), torch CPU + cv2, one thread per worker")
+    return _oracle_one_image, "port", "numpy oracle port (oracle/hybridgl_oracle.py); oracle/_ref (the reference's own files) is not present"
+
+
 def cpu_baseline_sample(cfg, budget_s: float = 20.0):
-    """Rank 0, N=1: the oracle port on ONE host core over a bounded sample (whole images of the workload)."""
+    """Rank 0, N=1: the reference path on ONE host core over a bounded sample (whole images of the workload)."""
+    fn, kind, what = _cpu_arm()
     n_masks = cfg["n_masks"]
-    t_first = _oracle_one_image((9000, cfg, n_masks))
+    t_first = fn((9000, cfg, n_masks))
     imgs, total = 1, t_first
     while total + t_first < budget_s and imgs < 10:
-        total += _oracle_one_image((9000 + imgs, cfg, n_masks)); imgs += 1
-    return {"value": imgs * cfg["n_expr"] / total, "unit": METRIC, "cores": 1, "kind": "port",
-            "sample": f"{imgs} image(s) x {n_masks} masks x {cfg['n_expr']} expressions of the same workload, numpy oracle port "
-                      f"(oracle/hybridgl_oracle.py), {total:.1f} s on 1 core; the Python reference itself cannot travel to the GPU box"}
+        total += fn((9000 + imgs, cfg, n_masks)); imgs += 1
+    return {"value": imgs * cfg["n_expr"] / total, "unit": METRIC, "cores": 1, "kind": kind,
+            "sample": f"{imgs} image(s) x {n_masks} masks x {cfg['n_expr']} expressions of the same workload, {total:.1f} s on 1 core; {what}"}
 
 
 def run_reference(args, cfg):
@@ -165,8 +190,9 @@ def run_reference(args, cfg):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 32))
+    fn, kind, what = _cpu_arm()
     n_masks = cfg["n_masks"]
-    t_img = _oracle_one_image((8000, cfg, n_masks))
+    t_img = fn((8000, cfg, n_masks))
     # keep the whole run within ~4 minutes: shrink the per-image mask count if one image per step would not fit
     budget = 240.0 / max(1, args.steps + args.warmup)
     scale = 1.0
@@ -176,21 +202,21 @@ def run_reference(args, cfg):
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         for w in range(args.warmup):
-            pool.map(_oracle_one_image, [(7000 + w * workers + i, cfg, n_masks) for i in range(workers)])
+            pool.map(fn, [(7000 + w * workers + i, cfg, n_masks) for i in range(workers)])
         t0 = time.perf_counter()
         for s in range(args.steps):
-            pool.map(_oracle_one_image, [(6000 + s * workers + i, cfg, n_masks) for i in range(workers)])
+            pool.map(fn, [(6000 + s * workers + i, cfg, n_masks) for i in range(workers)])
         dt = time.perf_counter() - t0
     # throughput in expressions/s of the FULL workload: a step with n_masks' < n_masks does n_masks'/n_masks of the work
     eff = n_masks / cfg["n_masks"]
     value = args.steps * workers * cfg["n_expr"] * eff / dt
     sample = (f"{workers} images per step (one per worker process), {n_masks}/{cfg['n_masks']} masks per image"
-              f"{' (throughput scaled by that fraction; per-mask work dominates)' if eff < 1 else ''}, numpy oracle port")
+              f"{' (throughput scaled by that fraction; per-mask work dominates)' if eff < 1 else ''}; {what}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg), **{k: cfg[k] for k in ("h", "w", "n_masks", "n_expr", "S", "g", "De")}},
-            "cpu_baseline": {"value": value, "unit": METRIC, "cores": workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": METRIC, "cores": workers, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
