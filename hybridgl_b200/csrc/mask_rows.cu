@@ -71,6 +71,38 @@ __device__ void aa_fill_warp(int i, int in_size, int out_size, int maxk, int* xm
   if (lane == 0) { *xmin_out = xmin; *xsize_out = xsize; }
 }
 
+// The tap tables of the mask pass, built ONCE per launch instead of once per CTA: block t < g = vertical table t, block g + i =
+// horizontal table i plus the double-precision prefix sums of its taps.  The block written at `out` has exactly the layout of the
+// mask pass's shared-memory header (ymin | ysize | xlo | xhi as int[kMaxG] each, then wy, wx, psum at the given byte offsets), so
+// a CTA of the pass copies it in with 16-byte loads.
+__global__ void __launch_bounds__(32) aa_tables_kernel(int H, int W, int g, int maxky, int maxkx, int off_wy, int off_wx, int off_psum,
+                                                        uint8_t* __restrict__ out) {
+  extern __shared__ float aa_w[];
+  __shared__ int lo_s, size_s;
+  const int t = blockIdx.x, lane = threadIdx.x;
+  int* ints = reinterpret_cast<int*>(out);
+  if (t < g) {
+    aa_fill_warp(t, H, g, maxky, &lo_s, &size_s, aa_w, lane);
+    __syncwarp();
+    float* wy = reinterpret_cast<float*>(out + off_wy) + (size_t)t * maxky;
+    for (int j = lane; j < maxky; j += 32) wy[j] = aa_w[j];
+    if (lane == 0) { ints[t] = lo_s; ints[kMaxG + t] = size_s; }
+  } else {
+    const int i = t - g;
+    aa_fill_warp(i, W, g, maxkx, &lo_s, &size_s, aa_w, lane);
+    __syncwarp();
+    float* wx = reinterpret_cast<float*>(out + off_wx) + (size_t)i * maxkx;
+    for (int j = lane; j < maxkx; j += 32) wx[j] = aa_w[j];
+    if (lane == 0) {
+      double* ps = reinterpret_cast<double*>(out + off_psum) + (size_t)i * (maxkx + 1);
+      double run = 0.0;
+      ps[0] = 0.0;
+      for (int k = 0; k < maxkx; ++k) { run += (double)aa_w[k]; ps[k + 1] = run; }
+      ints[2 * kMaxG + i] = lo_s; ints[3 * kMaxG + i] = lo_s + size_s;
+    }
+  }
+}
+
 static int aa_maxk(int in_size, int out_size) {
   const float scale = (float)in_size / (float)out_size;
   const float support = scale >= 1.f ? scale : 1.f;
@@ -315,8 +347,19 @@ __global__ void __launch_bounds__(256) heat_resize_aa_kernel(const float* __rest
 
 // ---- the pass over the packed masks ----------------------------------------------------------------------------------
 constexpr int kBands = 8;                              // row bands (= independent warp tasks) per mask
+#ifndef HGL_ROWS_FRONT
+#define HGL_ROWS_FRONT 1
+#endif
+#ifndef HGL_ROWS_GBATCH
+#define HGL_ROWS_GBATCH 1
+#endif
+constexpr int kRowVecChunk = 5;                        // 16-byte loads in flight per lane while a bit row is scanned (5 = a 640-pixel row)
+constexpr int kRowWordChunk = 13;                      // same for rows that are not 16-byte multiples (13 + 12 words = an 800-pixel row)
+
+constexpr size_t kAaTabBytes = 224 * 1024;             // room for the tap-table block (never larger than the pass's shared memory)
 
 struct RowsScratch {         // global scratch of one launch (byte offsets 256-aligned)
+  uint8_t* aatab;            // [kAaTabBytes]  tap tables of the antialiased resize (aa_tables_kernel), grid passes only
   int32_t* tickets;          // [M + 1]        zero at launch; entry M is the task counter of the dynamic scheduler
   int32_t* pcnt;             // [M][kBands]    pixels per band
   float* pgrid;              // [M][kBands][g*g]
@@ -328,6 +371,7 @@ static RowsScratch rows_carve(void* ws, int M, int g, int E, int max_n) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~size_t(255); return o; };
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  r.aatab = base + take(g > 0 ? kAaTabBytes : 0);
   r.tickets = reinterpret_cast<int32_t*>(base + take((size_t)(M + 1) * 4));
   r.pcnt = reinterpret_cast<int32_t*>(base + take((size_t)M * kBands * 4));
   r.pgrid = reinterpret_cast<float*>(base + take((size_t)M * kBands * g * g * 4));
@@ -361,7 +405,6 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
   int* xlo = ysize + kMaxG;
   int* xhi = xlo + kMaxG;
   float* wy = reinterpret_cast<float*>(smem + p.off_wy);        // [g][maxky]
-  float* wx = reinterpret_cast<float*>(smem + p.off_wx);        // [g][maxkx]
   double* psum = reinterpret_cast<double*>(smem + p.off_psum);  // [g][maxkx+1] prefix sums of wx (double: tiny edge taps survive)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, WW = p.WW, g = p.g, gg = g * g;
@@ -370,21 +413,10 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
   float* pgrid = reinterpret_cast<float*>(smem + p.off_pgrid) + (size_t)warp * gg;        // [g][g] this band's share of the grid
   const int pk = p.maxkx + 1;
   float inv_sx = 0.f;
-  if (kGrid) {
-    for (int t = warp; t < 2 * g; t += kRowsThreads / 32) {       // one warp per table (28 for g = 14), instead of one thread
-      if (t < g) {
-        aa_fill_warp(t, H, g, p.maxky, &ymin[t], &ysize[t], wy + t * p.maxky, lane);
-      } else {
-        const int i = t - g;
-        aa_fill_warp(i, W, g, p.maxkx, &xlo[i], &xhi[i], wx + i * p.maxkx, lane);       // xhi holds the size for a moment
-        if (lane == 0) {
-          xhi[i] += xlo[i];
-          double run = 0.0;
-          psum[i * pk] = 0.0;
-          for (int k = 0; k < p.maxkx; ++k) { run += (double)wx[i * p.maxkx + k]; psum[i * pk + k + 1] = run; }
-        }
-      }
-    }
+  if (kGrid) {                                                     // the tap tables come ready-made from aa_tables_kernel
+    const uint4* src = reinterpret_cast<const uint4*>(p.sc.aatab);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int t = tid; t < (p.off_hbuf >> 4); t += kRowsThreads) dst[t] = __ldg(src + t);
     inv_sx = (float)g / (float)W;
     __syncthreads();
   }
@@ -395,11 +427,13 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
   const float hw = (float)((size_t)H * W);
   const int total_tasks = p.M * kBands;
   // dynamic scheduling: masks differ a lot in how many rows they touch, so warps pull (mask, band) tasks from a counter
+  // (the ticket of the NEXT task is drawn before the current one is processed, so its round trip is never waited for)
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(p.sc.tickets + p.M, 1);
   for (;;) {
-    int task = 0;
-    if (lane == 0) task = atomicAdd(p.sc.tickets + p.M, 1);
-    task = __shfl_sync(0xffffffffu, task, 0);
+    const int task = __shfl_sync(0xffffffffu, ticket, 0);
     if (task >= total_tasks) break;
+    if (lane == 0) ticket = atomicAdd(p.sc.tickets + p.M, 1);
     const int m = task / kBands, band = task - m * kBands;
     const int y_begin = band * band_rows, y_end = min(H, y_begin + band_rows);
     int b = 0, n_lo = 0, e_lo = 0, e_hi = 0;
@@ -437,6 +471,40 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
             if (v != (0u - prev)) im |= 1ull << w;                    // neither "all outside" after a 0 nor "all inside" after a 1
             prev = v >> 31;
           };
+#if HGL_ROWS_FRONT
+          // every load of a chunk is issued before the first word is looked at: one memory round trip per chunk (a 640-pixel
+          // row is one chunk) instead of one per 16 bytes -- the round trips, not the bytes, are what this pass waits for
+          if (vec) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(rowp);
+            const int nu = WW >> 2;
+            for (int u0 = 0; u0 < nu; u0 += kRowVecChunk) {
+              uint4 q[kRowVecChunk];
+#pragma unroll
+              for (int k = 0; k < kRowVecChunk; ++k) q[k] = (u0 + k < nu) ? __ldg(r4 + u0 + k) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int k = 0; k < kRowVecChunk; ++k) {
+                const int u = u0 + k;
+                if (u >= nu) break;
+                const uint4 v = q[k];
+                // 128 pixels on one side of the outline (most of a frame for a blob): nothing to record
+                if ((v.x | v.y | v.z | v.w) == 0u && prev == 0u) continue;
+                if ((v.x & v.y & v.z & v.w) == 0xffffffffu && prev == 1u) { c_row += 128; continue; }
+                look(v.x, 4 * u); look(v.y, 4 * u + 1); look(v.z, 4 * u + 2); look(v.w, 4 * u + 3);
+              }
+            }
+          } else {
+            for (int w0 = 0; w0 < WW; w0 += kRowWordChunk) {
+              uint32_t q[kRowWordChunk];
+#pragma unroll
+              for (int k = 0; k < kRowWordChunk; ++k) q[k] = (w0 + k < WW) ? __ldg(rowp + w0 + k) : 0u;
+#pragma unroll
+              for (int k = 0; k < kRowWordChunk; ++k) {
+                if (w0 + k >= WW) break;
+                look(q[k], w0 + k);
+              }
+            }
+          }
+#else
           if (vec) {
             const uint4* r4 = reinterpret_cast<const uint4*>(rowp);
             for (int u = 0; u < (WW >> 2); ++u) {
@@ -449,6 +517,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
           } else {
             for (int w = 0; w < WW; ++w) look(__ldg(rowp + w), w);
           }
+#endif
           if (prev) im |= 1ull << WW;                                 // run open at the frame edge: closed by the virtual zero word WW
         }
         if (first) cnt += c_row;
@@ -493,6 +562,21 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
                 }
                 bx_hi = max(bx_hi, i - 1);
               }
+#if HGL_ROWS_GBATCH
+              if (kHeat && ne > 0) {                                  // all table reads of the run are in flight before the first add
+                float c1[kEB], c0[kEB], r1[kEB], r0[kEB];
+#pragma unroll
+                for (int j = 0; j < kEB; ++j) {                       // predicated loads, no branches between them
+                  const bool on = j < ne;
+                  c1[j] = on ? __ldg(crow[j] + e0) : 0.f; c0[j] = on ? __ldg(crow[j] + s0) : 0.f;
+                  r1[j] = on ? __ldg(rrow[j] + e0) : 0.f; r0[j] = on ? __ldg(rrow[j] + s0) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kEB; ++j) {
+                  if (j < ne) { acc[j] += c1[j] - c0[j]; accr[j] += r1[j] - r0[j]; }
+                }
+              }
+#else
               if (kHeat) {
 #pragma unroll
                 for (int j = 0; j < kEB; ++j) {
@@ -502,6 +586,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) mask_rows_kernel(const RowsPa
                   }
                 }
               }
+#endif
             }
           }
         }
@@ -653,6 +738,12 @@ static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scrat
   p.off_pgrid = take(want_grid ? (size_t)warps * p.g * p.g * 4 : 0, 16);
   const size_t smem = off;
   HGL_REQUIRE(smem <= 220 * 1024, "mask rows pass: frame %dx%d (g=%d) needs %zu B of shared memory", p.H, p.W, p.g, smem);
+  if (want_grid) {
+    const size_t tab_smem = (size_t)std::max(p.maxky, p.maxkx) * 4;
+    aa_tables_kernel<<<2 * p.g, 32, tab_smem, st>>>(p.H, p.W, p.g, p.maxky, p.maxkx, p.off_wy, p.off_wx, p.off_psum, p.sc.aatab);
+    const int rc1 = launch_status("mask rows pass (tap tables)");
+    if (rc1 != HGL_OK) return rc1;
+  }
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
   per_sm = std::max(1, std::min(per_sm, tuning_int("HGL_ROWS_CTAS_PER_SM", per_sm)));
   const int ctas = std::min(ceil_div(p.M * kBands, warps), sm_count() * per_sm);

@@ -50,7 +50,7 @@ def timeit(fn, iters=20, warm=3, flush=True):
 cfg = synth.CONFIGS[int(os.environ.get("KB_CFG", "2"))]
 B = int(os.environ.get("KB_IMAGES", "16"))
 H, W, N, E, S, g, De = cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["S"], cfg["g"], cfg["De"]
-batch = synth.make_batch_device(1234, B, H, W, N, E, De, device="cuda", grid=g)
+batch = synth.make_batch_device(1234, B, H, W, N, E, De, device="cuda", grid=g, raw_heat=True)
 counts, roff = synth.masks_to_rle_device(batch["masks"])
 path = ScoringPath(size=S, grid=g, feature_source="tokens", overlap=False, keep_features=True)
 res = path.run(batch, N)
@@ -64,7 +64,7 @@ lib = ops._lib.load()
 bits2 = torch.empty_like(bits)
 loc = torch.empty((M, 3, S, S), dtype=torch.bfloat16, device="cuda"); glo = torch.empty_like(loc)
 pws = torch.empty((max(lib.hgl_prep_workspace_bytes(B, S, ops.HGL_BF16), 1),), dtype=torch.uint8, device="cuda")
-hws = torch.empty((lib.hgl_grid_heat_pool_workspace_bytes(B, M, B * E, H, W, g, N),), dtype=torch.uint8, device="cuda")
+hws = torch.empty((lib.hgl_grid_heat_pool_raw_workspace_bytes(B, M, B * E, H, W, g, N, batch["heat"].shape[1], batch["heat"].shape[2]),), dtype=torch.uint8, device="cuda")
 cum = torch.zeros(4, dtype=torch.int64, device="cuda")
 WW = (W + 31) // 32
 stages = {
@@ -75,6 +75,11 @@ stages = {
              M * H * WW * 4 + 2 * B * H * W * 3 + 2 * M * 3 * S * S * 2),
     "grid_heat_pool": (lambda: ops.grid_heat_pool(bits, W, g, batch["heat"], batch["dirflag"], batch["black"], moff, eoff, N, workspace=hws),
                        M * H * WW * 4 + M * g * g * 4 + 2 * B * E * H * W * 4 + B * E * N * 4),
+    "grid_all": (lambda: ops.masks_to_grid(bits, g, width=W), M * H * WW * 4 + M * g * g * 4),
+    "grid_one": (lambda: ops.masks_to_grid(bits[:1], g, width=W), H * WW * 4 + g * g * 4),
+    "tables": (lambda: ops.heat_tables(batch["heat"], batch["dirflag"], H, W, hws), 2 * B * E * H * W * 4),
+    "rows": (lambda: ops.grid_heat_pool_rows(bits, W, g, tuple(batch["heat"].shape), batch["black"], moff, eoff, N, hws),
+             M * H * WW * 4 + M * g * g * 4 + B * E * N * 4),
     "mask_pool": (lambda: ops.mask_pool(grid, batch["tokens"], moff, N, normalize=True, dtype=torch.bfloat16),
                   M * g * g * 4 + B * g * g * De * 2 + M * De * 2),
     "pool_score": (lambda: ops.pool_score_select(grid, batch["tokens"], batch["sent"], batch["noun"], batch["others"], batch["other_off"],

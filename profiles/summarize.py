@@ -22,8 +22,8 @@ PROF = os.path.join(ROOT, "profiles")
 
 # bench.py stage name -> kernels that belong to it
 STAGES = {
-    "blur": ["blur15"], "pack": ["pack_masks"], "prep_setup": ["prep_setup"], "prep": ["prep_main"], "heat_tables": ["heat_prefix", "heat_consts", "heat_resize"], "grid_heat_pool": ["mask_rows", "mask_grid", "mask_area"], "score_select": ["score_select", "score_text"], "iou": ["iou_zero", "iou_kernel"],
-    "mask_pool": ["mask_pool"], "token_mask_fuse": ["token_mask_fuse"],
+    "blur": ["blur15"], "pack": ["pack_masks"], "prep_setup": ["prep_setup"], "prep": ["prep_main"], "heat_tables": ["heat_prefix", "heat_consts", "heat_resize"], "grid_heat_pool": ["mask_rows", "mask_grid", "mask_area"], "pool_score": ["pool_score"], "score_select": ["score_select", "score_text"], "iou": ["iou_zero", "iou_kernel"],
+    "mask_pool": ["mask_pool"], "token_mask_fuse": ["token_mask_fuse"], "rle_to_bits": ["rle_"], "gem_token": ["gem_"],
 }
 
 
@@ -102,8 +102,18 @@ def ncu_full(tag):
              "| kernel | us | DRAM rd MB | DRAM wr MB | DRAM GB/s | DRAM % | SM % | L2 % | warps active % | regs | grid x block | top stalls (cycles per issue) |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
+    tensor_rows = []
     for r in body:
         name = short(r[col["Kernel Name"]])
+        if get(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) > 0.0:
+            tensor_rows.append(
+                f"| {name} | {us_of(r):.1f} | {get(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.2f} | "
+                f"{get(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.2f} | "
+                f"{get(r, 'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active'):.2f} | "
+                f"{get(r, 'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active'):.3f} | "
+                f"{get(r, 'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active'):.3f} | "
+                f"{get(r, 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.2f} | "
+                f"{get(r, 'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active'):.2f} |")
         us = us_of(r)
         rd, wr = bytes_of(r, "dram__bytes_read.sum"), bytes_of(r, "dram__bytes_write.sum")
         st = sorted(((get(r, s, 0.0), s[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for s in stalls), reverse=True)[:3]
@@ -117,6 +127,12 @@ def ncu_full(tag):
         stg = stage_of(name)
         traffic.setdefault(stg, {"bytes": 0.0, "kernels": {}})
         traffic[stg]["kernels"][name] = rd + wr
+    if tensor_rows:
+        lines += ["", "Tensor pipe (tcgen05) kernels -- % of peak: `sm__pipe_tensor_cycles_active` (sustained active / elapsed), its hmma sub-pipe, "
+                  "`sm__inst_executed_pipe_tensor_subpipe_hmma`, `sm__inst_executed_pipe_tmem`, `sm__mem_tensor_cycles_active`, "
+                  "`sm__inst_executed_pipe_uniform`:", "",
+                  "| kernel | us | pipe_tensor active % | pipe_tensor elapsed % | hmma sub-pipe active % | inst pipe_tensor hmma % | inst pipe_tmem % | mem_tensor active % | inst pipe_uniform % |",
+                  "|---|---|---|---|---|---|---|---|---|"] + tensor_rows
     for stg, d in traffic.items():
         d["bytes"] = sum(d["kernels"].values())
     with open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w") as f:
