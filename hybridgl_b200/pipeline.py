@@ -36,10 +36,10 @@ class ScoringPath:
         under every proposal's soft grid mask on the tensor cores and scored in the same kernel (hgl_pool_score_select);
         keep_features: also write the pooled, normalised rows [M,De] (bf16) to HBM and return them as res["features"].
         chunks: groups of images a batch is cut into inside run() (see there); 1 = every stage once per batch (the default:
-        gem_space: "pixel" = heat-map tables + one fused pass over the masks (hgl_heat_tables + hgl_grid_heat_pool_rows); "token" =
-        score_gem computed on the raw GEM map's token grid (hgl_gem_token_pool; needs raw maps) next to hgl_mask_grid.
         measured on B200 at the bench shape, 2 / 4 groups are SLOWER -- 0.55 / 0.66 ms against 0.50 ms per pass -- because the
-        small latency-bound kernels a group's prep waits for crawl while another group's pack saturates HBM)."""
+        small latency-bound kernels a group's prep waits for crawl while another group's pack saturates HBM).
+        gem_space: "pixel" = heat-map tables + one fused pass over the masks (hgl_heat_tables + hgl_grid_heat_pool_rows); "token" =
+        score_gem computed on the raw GEM map's token grid (hgl_gem_token_pool; needs raw maps) next to hgl_mask_grid."""
         if feature_source not in ("supplied", "tokens"):
             raise ValueError(feature_source)
         self.feature_source = feature_source
