@@ -182,8 +182,8 @@ def cpu_baseline_sample(cfg, budget_s: float = 20.0):
 
 
 def run_reference(args, cfg):
-    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference is Python and does
-    not exist on the GPU box) on all host cores: one image per worker process per step."""
+    """`--impl reference`: the reference's own CPU code for the path (oracle/_ref, copied from the reference checkout by
+    oracle/make_ref.py; the numpy port of it only when that copy is absent) on all host cores: one image per worker process per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return

@@ -21,8 +21,8 @@
 //   D = acc  [128 x Nw] f32 per row tile in TMEM (up to 4 row tiles = 512 proposals per image share the B stream).
 //   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Nw, K=16) issued by ONE thread; tcgen05.commit releases ring slots.
 //   Epilogue: tcgen05.ld 32x32b -- a thread owns one proposal row -- accumulates |row|^2 and the dots with <= 4 text / 4
-//   negative vectors (this CTA's column slice, in shared memory); partial sums meet in the cluster's rank-0 CTA through
-//   distributed shared memory (mapa + ld.shared::cluster), which finishes the scores and runs the selection tail.
+//   negative vectors (this CTA's column slice, in shared memory); every CTA PUSHES its partial sums into the rank-0 CTA's
+//   shared memory (mapa + st.shared::cluster, one barrier.cluster), which finishes the scores and runs the selection tail.
 // Arithmetic intensity is low (2*N*L*D flop over ~2*(N*L + L*D) bytes): the kernel is a latency chain
 // (TMA -> MMA -> TMEM -> DSMEM -> tail), sized to run wide (B*NT CTAs) rather than to saturate the tensor pipe.
 #include <cuda.h>   // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
