@@ -479,8 +479,12 @@ def run_ours(args, cfg):
     path.events_only = None
     t_end.record()
     # the path's only collective, timed on its own: all-reduce of the IoU accumulators (32 bytes)
+    # (an untimed all-reduce first lines the ranks up: without it k0 -> k1 on a fast rank is the wait for the slowest rank's
+    # loop -- 10 ms at 8 ranks -- which the max over ranks of the loop time below already contains)
     cum = path.cum.clone()
     k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.all_reduce(torch.zeros(4, dtype=torch.int64, device=dev))
     k0.record()
     if world > 1:
         dist.all_reduce(cum)
