@@ -20,6 +20,7 @@ SIGNATURES = {
     "hgl_version": (c_int, []),
     "hgl_check_device": (c_int, []),
     "hgl_pack_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hgl_pack_masks_bool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_mask_geometry": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hgl_prep_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "hgl_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

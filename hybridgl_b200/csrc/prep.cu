@@ -79,12 +79,18 @@ __device__ __forceinline__ uint32_t nibble_of(uint32_t v) {
   const uint32_t t = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
   return (t * 0x00204081u) >> 28;
 }
+// the same for bytes that are known to be 0 or 1 (torch.bool storage): the four bits sit at 0 / 8 / 16 / 24 and one multiply by
+// 2^28 + 2^21 + 2^14 + 2^7 lines them up in the top nibble (every partial product lands on its own bit: no carries)
+__device__ __forceinline__ uint32_t nibble_of_bool(uint32_t v) { return (v * 0x10204080u) >> 28; }
+template <bool kBool>
 __device__ __forceinline__ uint32_t half_of(const uint4 v) {   // 16 mask bytes -> 16 bits
+  if (kBool) return nibble_of_bool(v.x) | (nibble_of_bool(v.y) << 4) | (nibble_of_bool(v.z) << 8) | (nibble_of_bool(v.w) << 12);
   return nibble_of(v.x) | (nibble_of(v.y) << 4) | (nibble_of(v.z) << 8) | (nibble_of(v.w) << 12);
 }
 
 // W % 32 == 0 and 16-byte aligned base: the masks are one flat byte stream, word w = pixels [32w, 32w+32).
 // lane loads 16 B (fully coalesced 512 B per warp), neighbours pair up through one shuffle, even lanes store.
+template <bool kBool>
 __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __restrict__ src, size_t n16, uint32_t* __restrict__ bits) {
   constexpr int kU = 8;   // independent 16-byte loads in flight per thread
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __res
     for (int u = 0; u < kU; ++u) v[u] = ldg_stream(src + i + u * stride);
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const uint32_t h = half_of(v[u]);
+      const uint32_t h = half_of<kBool>(v[u]);
       const uint32_t o = __shfl_xor_sync(0xffffffffu, h, 1);
       if (!(threadIdx.x & 1)) bits[(i + u * stride) >> 1] = h | (o << 16);
     }
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __res
     const bool in = i < n16;
     const unsigned act = __ballot_sync(0xffffffffu, in);
     if (in) {
-      const uint32_t h = half_of(ldg_stream(src + i));
+      const uint32_t h = half_of<kBool>(ldg_stream(src + i));
       const uint32_t o = __shfl_xor_sync(act, h, 1);
       if (!(threadIdx.x & 1)) bits[i >> 1] = h | (o << 16);
     }
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(256) pack_masks_flat_kernel(const uint4* __res
 }
 
 // general widths: one thread per (mask row, 32-pixel word)
+template <bool kBool>
 __global__ void __launch_bounds__(256) pack_masks_rows_kernel(const uint8_t* __restrict__ masks, size_t rows_total, int W, uint32_t* __restrict__ bits) {
   const int WW = (W + 31) >> 5;
   const size_t total = rows_total * WW;
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(256) pack_masks_rows_kernel(const uint8_t* __r
     if (nv == 32 && (reinterpret_cast<uintptr_t>(sp) & 3) == 0) {
       const uint32_t* s4 = reinterpret_cast<const uint32_t*>(sp);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) word |= nibble_of(ldg_stream32(s4 + q)) << (4 * q);
+      for (int q = 0; q < 8; ++q) word |= (kBool ? nibble_of_bool(ldg_stream32(s4 + q)) : nibble_of(ldg_stream32(s4 + q))) << (4 * q);
     } else {
       for (int q = 0; q < nv; ++q) word |= (uint32_t)(sp[q] != 0) << q;
     }
@@ -646,7 +653,7 @@ static PrepWs prep_carve(void* ws, int B, int S, int out_dtype) {
 
 }  // namespace hgl
 
-extern "C" int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream) {
+static int pack_masks_impl(const uint8_t* masks, int M, int H, int W, uint32_t* bits, bool is_bool, void* stream) {
   using namespace hgl;
   if (M == 0) return HGL_OK;
   HGL_REQUIRE(masks && bits, "hgl_pack_masks: null pointer");
@@ -662,14 +669,24 @@ extern "C" int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_
 #ifdef HGL_TUNING
     if (const char* pv = getenv("HGL_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(pv)));
 #endif
-    const int blocks = (int)std::min<size_t>((n16 + 256 * 8 - 1) / (256 * 8), (size_t)sm_count() * per_sm);
-    pack_masks_flat_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const uint4*>(masks), n16, bits);
+    const int blocks = std::max(1, (int)std::min<size_t>((n16 + 256 * 8 - 1) / (256 * 8), (size_t)sm_count() * per_sm));
+    if (is_bool) pack_masks_flat_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(masks), n16, bits);
+    else pack_masks_flat_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(masks), n16, bits);
   } else {
     const size_t total = rows * ((W + 31) >> 5);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
-    pack_masks_rows_kernel<<<blocks, 256, 0, st>>>(masks, rows, W, bits);
+    if (is_bool) pack_masks_rows_kernel<true><<<blocks, 256, 0, st>>>(masks, rows, W, bits);
+    else pack_masks_rows_kernel<false><<<blocks, 256, 0, st>>>(masks, rows, W, bits);
   }
   return launch_status("hgl_pack_masks");
+}
+
+extern "C" int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream) {
+  return pack_masks_impl(masks, M, H, W, bits, false, stream);
+}
+
+extern "C" int hgl_pack_masks_bool(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream) {
+  return pack_masks_impl(masks, M, H, W, bits, true, stream);
 }
 
 extern "C" int64_t hgl_prep_workspace_bytes(int B, int S, int out_dtype) {

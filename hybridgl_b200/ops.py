@@ -87,7 +87,10 @@ def pack_masks(masks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
         _req(out, torch.int32, "bits", 3)
         if tuple(out.shape) != (M, H, (W + 31) // 32):
             raise ValueError(f"bits must be [M,H,ceil(W/32)] int32, got {tuple(out.shape)}")
-    check(_lib.load().hgl_pack_masks(m.data_ptr(), M, H, W, out.data_ptr(), _stream()), "hgl_pack_masks")
+    lib = _lib.load()
+    # torch.bool storage is one byte of 0 / 1 per element: the cheaper squeeze applies; uint8 masks may hold any non-zero value
+    fn = lib.hgl_pack_masks_bool if masks.dtype == torch.bool else lib.hgl_pack_masks
+    check(fn(m.data_ptr(), M, H, W, out.data_ptr(), _stream()), "hgl_pack_masks")
     return out
 
 

@@ -63,6 +63,10 @@ HGL_API int hgl_check_device(void);
  * The byte masks of SAM (torch.bool [M,H,W], Hybridgl_main.py:86-87) are read exactly once, here; prep, the mask
  * grid and the heat-map pooling all consume the 8x smaller packed tensor. */
 HGL_API int hgl_pack_masks(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream);
+/* The same for masks whose bytes are known to be 0 or 1 -- the storage of torch.bool, i.e. exactly what Hybridgl_main.py:86-87
+ * builds (torch.from_numpy of SAM's bool 'segmentation' arrays): a cheaper byte -> bit squeeze (40 % fewer instructions; the pass
+ * shares the SMs with the frame-only kernels of the path).  Any other byte value gives undefined bits: use hgl_pack_masks for uint8. */
+HGL_API int hgl_pack_masks_bool(const uint8_t* masks, int M, int H, int W, uint32_t* bits, void* stream);
 
 /* ---- per-mask geometry from the packed masks ------------------------------------------------------------
  * boxes_xywh int64 [M,4]: SAM's proposal boxes -- batched_mask_to_box + box_xyxy_to_xywh

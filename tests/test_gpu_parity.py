@@ -115,8 +115,11 @@ def test_packed_masks_and_prep_from_bits(ops, h, w, S, n):
     it.masks[0, 0, :] = True; it.masks[0, -1, :] = True; it.masks[-1, :, 0] = True; it.masks[-1, :, -1] = True
     ref = _pack_ref(it.masks)
     masks = cu(it.masks)
-    got = ops.pack_masks(masks).cpu().numpy().view(np.uint32)
+    got = ops.pack_masks(masks).cpu().numpy().view(np.uint32)                            # torch.bool: the 0 / 1 byte squeeze
     assert np.array_equal(got, ref)
+    vals = torch.tensor([1, 2, 128, 255, 77], dtype=torch.uint8, device=masks.device)     # uint8 masks: any non-zero byte is inside
+    m8 = masks.to(torch.uint8) * vals[torch.arange(masks.numel(), device=masks.device).reshape(masks.shape) % 5]
+    assert np.array_equal(ops.pack_masks(m8).cpu().numpy().view(np.uint32), ref)
     blur = O.gaussian_blur_u8(it.image)
     loc, glo = ops.prep_visual_prompts(cu(it.image), cu(blur), ops.pack_masks(masks), S)   # prep straight from packed masks
     ol, og = O.prep(it.image, blur, it.masks, S)
