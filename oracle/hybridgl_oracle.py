@@ -131,13 +131,15 @@ def imagenet_normalize(x_chw: np.ndarray) -> np.ndarray:
     return ((x_chw - IMAGENET_MEAN[:, None, None]).astype(f32) / IMAGENET_STD[:, None, None]).astype(f32)
 
 
-def prep(image_u8: np.ndarray, blur_u8: np.ndarray, masks: np.ndarray, S: int, background: str = "blur"):
+def prep(image_u8: np.ndarray, blur_u8: np.ndarray, masks: np.ndarray, S: int, background: str = "blur", circle: bool = False):
     """Hybridgl_main.py:92-125.  Returns (local_imgs, global_imgs), both f32 [N,3,S,S].
 
     global_n = Normalize(Resize(ToTensor(where(m_n, img, background))))     lines 103-118
     local_n  = Resize(img_norm * m_n + (1 - m_n) * pixel_mean)              lines 120-122
     ``background`` selects what replaces the pixels outside the mask in the global view:
-    'blur' (the drivers, and apply_visual_prompts 'blur' utils.py:306-320), 'black' (utils.py:336-341).
+    'blur' (the drivers, and apply_visual_prompts 'blur' utils.py:306-320), 'black' (utils.py:336-341), 'none' (the frame itself).
+    ``circle``: the global view also carries the 'circle' prompt (utils.py:322-335), drawn after the blur composite and before the
+    black one, as apply_visual_prompts orders them.
     """
     masks = np.asarray(masks).astype(bool)
     n = masks.shape[0]
@@ -148,11 +150,17 @@ def prep(image_u8: np.ndarray, blur_u8: np.ndarray, masks: np.ndarray, S: int, b
         bg = blur_u8
     elif background == "black":
         bg = np.zeros_like(image_u8)
+    elif background == "none":
+        bg = image_u8
     else:
         raise ValueError(background)
     for i in range(n):
         m = masks[i]
-        comp = np.where(m[:, :, None], image_u8, bg)                     # u8 composite, lines 106-113
+        if circle:
+            kinds = {"blur": ("blur", "circle"), "black": ("circle", "black"), "none": ("circle",)}[background]
+            comp = apply_visual_prompt(image_u8, m, kinds, blur_u8)
+        else:
+            comp = np.where(m[:, :, None], image_u8, bg)                 # u8 composite, lines 106-113
         glob[i] = imagenet_normalize(resize_bilinear(to_tensor_u8(comp), S, S))
         masked = np.where(m[None], img_norm, CLIP_PIXEL_MEAN[:, None, None]).astype(f32)  # line 120
         local[i] = resize_bilinear(masked, S, S)
@@ -508,12 +516,133 @@ def mask_to_box_xywh(mask: np.ndarray) -> np.ndarray:
     return np.array([xs.min(), ys.min(), xs.max() - xs.min(), ys.max() - ys.min()], np.int64)
 
 
-def apply_visual_prompt(image_u8: np.ndarray, mask: np.ndarray, kind: str, blur_u8: np.ndarray = None) -> np.ndarray:
-    """utils.py:292-345 for the prompt types that are pure compositing: 'blur' (:306-320) and 'black' (:336-341).  image u8 [H,W,3];
-    returns u8 [H,W,3].  ('circle', :322-335, draws cv2.ellipse's fixed-point polygon outline at mask2chw's centre; not restated.)"""
+# ---- cv2.ellipse outline (the 'circle' visual prompt, utils.py:322-335) ---------------------------------------------
+# OpenCV is a binary dependency of the reference (no source in its tree): cv2.ellipse(img, center, axes, 0, 0, 360, color, 1) as
+# shipped in this container (4.13) is restated from OpenCV's published algorithm (imgproc/src/drawing.cpp: ellipse -> EllipseEx ->
+# ellipse2Poly -> PolyLine -> ThickLine -> Line -> LineIterator) and pinned against cv2 itself: tests/test_oracle_golden.py draws
+# thousands of random ellipses and integer lines with cv2 when it is importable, and the reference's own apply_visual_prompts
+# outputs are in tests/golden/geometry.npz.  What the algorithm does at thickness 1, LINE_8:
+#   * polygon vertices every `delta` degrees (delta from the larger axis: < 3 -> 90, < 10 -> 30, < 15 -> 18, else 5), computed in
+#     16.16 fixed point as double: c*2^16 + (axis*2^16) * (double)SinTable[deg] (SinTable = sin of whole degrees as 7-decimal float
+#     literals), rounded half-to-even, then to the nearest pixel with (v + 2^15) >> 16;
+#   * every edge is an integer 8-connected Bresenham line drawn LEFT TO RIGHT (LineIterator(..., leftToRight=true)) after
+#     cv::clipLine moved the end points that lie outside the frame onto its border (double arithmetic, truncated).
+_SIN_TABLE = None
+
+
+def _sin_table():
+    global _SIN_TABLE
+    if _SIN_TABLE is None:
+        import math
+        _SIN_TABLE = np.array([f32(f"{math.sin(math.radians(d)):.7f}") for d in range(451)], f32)
+    return _SIN_TABLE
+
+
+def _clip_line(W, H, x1, y1, x2, y2):
+    """cv::clipLine on integer end points; returns (visible, x1, y1, x2, y2)."""
+    right, bottom = W - 1, H - 1
+
+    def code(x, y):
+        return (x < 0) + (x > right) * 2 + (y < 0) * 4 + (y > bottom) * 8
+    c1, c2 = code(x1, y1), code(x2, y2)
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += int(float(a - y1) * (x2 - x1) / (y2 - y1)); y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += int(float(a - y2) * (x2 - x1) / (y2 - y1)); y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += int(float(a - x1) * (y2 - y1) / (x2 - x1)); x1 = a; c1 = 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += int(float(a - x2) * (y2 - y1) / (x2 - x1)); x2 = a; c2 = 0
+    return (c1 | c2) == 0, x1, y1, x2, y2
+
+
+def line8_pixels(H, W, p1, p2):
+    """Pixels (y, x) of cv2.line(img, p1, p2, color, 1, LINE_8) on an H x W frame (points are (x, y), may lie outside)."""
+    ok, x1, y1, x2, y2 = _clip_line(W, H, int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]))
+    if not ok:
+        return []
+    dx, dy = x2 - x1, y2 - y1
+    if dx < 0:                                     # left to right
+        x1, y1, x2, y2 = x2, y2, x1, y1
+        dx, dy = -dx, -dy
+    sy = 1 if dy >= 0 else -1
+    dy = abs(dy)
+    x, y, out = x1, y1, []
+    if dy > dx:                                    # y is the major axis
+        err, plus, minus = dy - 2 * dx, 2 * dy, -2 * dx
+        for _ in range(dy + 1):
+            out.append((y, x))
+            if err < 0:
+                err += minus + plus; x += 1
+            else:
+                err += minus
+            y += sy
+    else:
+        err, plus, minus = dx - 2 * dy, 2 * dx, -2 * dy
+        for _ in range(dx + 1):
+            out.append((y, x))
+            if err < 0:
+                err += minus + plus; y += sy
+            else:
+                err += minus
+            x += 1
+    return out
+
+
+def ellipse_vertices(cx: int, cy: int, ax: int, ay: int):
+    """Pixel vertices (x, y) of the polygon cv2.ellipse draws for centre (cx, cy), half axes (ax, ay), angle 0, full arc."""
+    st = _sin_table()
+    m = max(ax, ay)
+    delta = 90 if m < 3 else 30 if m < 10 else 18 if m < 15 else 5
+    pts = []
+    for i in range(0, 360 + delta, delta):
+        ang = min(i, 360)
+        vx = float(cx * 65536) + float(ax * 65536) * float(st[450 - ang])      # two roundings, like the C++ expression
+        vy = float(cy * 65536) + float(ay * 65536) * float(st[ang])
+        pts.append(((int(np.rint(vx)) + 32768) >> 16, (int(np.rint(vy)) + 32768) >> 16))
+    return pts
+
+
+def ellipse_outline(H: int, W: int, cx: int, cy: int, ax: int, ay: int) -> np.ndarray:
+    """bool [H,W]: the pixels cv2.ellipse(img, (cx, cy), (ax, ay), 0, 0, 360, color, 1) sets."""
+    out = np.zeros((H, W), bool)
+    v = ellipse_vertices(cx, cy, ax, ay)
+    for p0, p1 in zip(v[:-1], v[1:]):
+        for y, x in line8_pixels(H, W, p0, p1):
+            out[y, x] = True
+    return out
+
+
+def circle_outline_of_mask(mask: np.ndarray) -> np.ndarray:
+    """utils.py:322-335: the ellipse at mask2chw's centre with half axes (width // 2, height // 2)."""
+    (cy, cx), h, w = mask2chw(mask)
+    return ellipse_outline(mask.shape[0], mask.shape[1], cx, cy, w // 2, h // 2)
+
+
+CIRCLE_COLOR = np.array([255, 0, 0], np.uint8)      # utils.py:298 default colour
+
+
+def apply_visual_prompt(image_u8: np.ndarray, mask: np.ndarray, kind, blur_u8: np.ndarray = None) -> np.ndarray:
+    """utils.py:292-345.  image u8 [H,W,3]; `kind` a prompt type or a tuple of them, applied in the reference's order
+    'blur' (:306-320) -> 'circle' (:322-335) -> 'black' (:336-341); returns u8 [H,W,3]."""
+    kinds = (kind,) if isinstance(kind, str) else tuple(kind)
+    for k in kinds:
+        if k not in ("blur", "circle", "black"):
+            raise ValueError(k)
     m = np.asarray(mask).astype(bool)
-    if kind == "blur":
-        return np.where(m[:, :, None], image_u8, blur_u8 if blur_u8 is not None else gaussian_blur_u8(image_u8))
-    if kind == "black":
-        return np.where(m[:, :, None], image_u8, np.zeros_like(image_u8))
-    raise ValueError(kind)
+    img = image_u8
+    if "blur" in kinds:
+        img = np.where(m[:, :, None], img, blur_u8 if blur_u8 is not None else gaussian_blur_u8(img))
+    if "circle" in kinds:
+        img = np.where(circle_outline_of_mask(m)[:, :, None], CIRCLE_COLOR, img)
+    if "black" in kinds:
+        img = np.where(m[:, :, None], img, np.zeros_like(img))
+    return img.astype(np.uint8)

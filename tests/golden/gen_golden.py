@@ -278,7 +278,7 @@ def gen_rle():
 
 
 def gen_geometry(ref_utils):
-    """mask2chw (utils.py:280-289), apply_visual_prompts 'blur' / 'black' (utils.py:306-320, 336-341) and SAM's boxes
+    """mask2chw (utils.py:280-289), apply_visual_prompts 'blur' / 'circle' / 'black' (utils.py:306-341) and SAM's boxes
     (amg.py:303-346 batched_mask_to_box + :91-95 box_xyxy_to_xywh), called in place."""
     sys.path.insert(0, os.path.join(REF, "third_party/segment-anything"))
     from segment_anything.utils.amg import batched_mask_to_box, box_xyxy_to_xywh
@@ -299,6 +299,9 @@ def gen_geometry(ref_utils):
             out[f"c{ci}_image"] = img
             for kind in ("blur", "black"):
                 out[f"c{ci}_{kind}"] = np.stack([ref_utils.apply_visual_prompts(img, mm.astype(np.uint8), visual_prompt_type=(kind,)) for mm in m])
+            # 'circle' (utils.py:322-335: cv2.ellipse at mask2chw's centre), alone and combined the way the if-chain orders the types
+            for tag, kinds in (("circle", ("circle",)), ("blur_circle", ("blur", "circle")), ("circle_black", ("circle", "black"))):
+                out[f"c{ci}_{tag}"] = np.stack([ref_utils.apply_visual_prompts(img, mm.astype(np.uint8), visual_prompt_type=kinds) for mm in m])
         print("geometry", ci, (h, w, n), boxes[2].tolist(), chw[2].tolist())
     empty = batched_mask_to_box(torch.zeros((1, 8, 8), dtype=torch.bool))
     out["empty_box"] = box_xyxy_to_xywh(empty[0]).numpy().astype(np.int64)

@@ -186,7 +186,33 @@ def test_geometry_and_prompts_match_reference(golden):
             for i in range(n):
                 assert np.array_equal(O.apply_visual_prompt(img, masks[i], "blur", blur), g[f"c{ci}_blur"][i])
                 assert np.array_equal(O.apply_visual_prompt(img, masks[i], "black"), g[f"c{ci}_black"][i])
+                # the 'circle' prompt: cv2.ellipse at mask2chw's centre, alone and in the if-chain's order with the other two
+                assert np.array_equal(O.apply_visual_prompt(img, masks[i], "circle"), g[f"c{ci}_circle"][i])
+                assert np.array_equal(O.apply_visual_prompt(img, masks[i], ("blur", "circle"), blur), g[f"c{ci}_blur_circle"][i])
+                assert np.array_equal(O.apply_visual_prompt(img, masks[i], ("circle", "black")), g[f"c{ci}_circle_black"][i])
     assert O.mask_to_box_xywh(np.zeros((8, 8), bool)).tolist() == g["empty_box"].tolist() == [0, 0, 0, 0]
+
+
+def test_ellipse_outline_equals_cv2():
+    """The restated rasteriser of the 'circle' prompt against OpenCV itself (a binary dependency of the reference: no source in its
+    tree): random ellipses -- tiny, frame-sized, centred near the border so that edges are clipped -- and random integer lines."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for t in range(400):
+        H, W = int(rng.integers(20, 200)), int(rng.integers(20, 260))
+        p = rng.integers(-30, [W + 30, H + 30, W + 30, H + 30])
+        a = np.zeros((H, W), np.uint8)
+        cv2.line(a, (int(p[0]), int(p[1])), (int(p[2]), int(p[3])), 255, 1, cv2.LINE_8, 0)
+        b = np.zeros((H, W), bool)
+        for y, x in O.line8_pixels(H, W, (p[0], p[1]), (p[2], p[3])):
+            b[y, x] = True
+        assert np.array_equal(a > 0, b), (H, W, p.tolist())
+    for t in range(600):
+        H, W = ((480, 640), (97, 131), (600, 800), (33, 32))[t % 4] if t % 3 == 0 else (int(rng.integers(20, 200)), int(rng.integers(20, 260)))
+        cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
+        ax, ay = (int(rng.integers(0, 16)), int(rng.integers(0, 16))) if t % 5 == 0 else (int(rng.integers(0, W // 2 + 1)), int(rng.integers(0, H // 2 + 1)))
+        ref = cv2.ellipse(np.zeros((H, W, 3), np.uint8), (cx, cy), (ax, ay), 0, 0, 360, (255, 0, 0), 1)[:, :, 0] > 0
+        assert np.array_equal(ref, O.ellipse_outline(H, W, cx, cy, ax, ay)), (H, W, cx, cy, ax, ay)
 
 
 def test_token_space_gem_pooling_equals_pixel_space_chain():
