@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HGL_LIB") or os.path.join(_PKG, "libhgl.so")     # HGL_LIB: profiling builds (build.py, HGL_BUILD_TUNING=1)
 
 HGL_F32, HGL_BF16 = 0, 1
-HGL_BG_BLUR, HGL_BG_BLACK = 0, 1
+HGL_BG_BLUR, HGL_BG_BLACK, HGL_BG_NONE = 0, 1, 2
 HGL_LND, HGL_NLD = 0, 1
 REL_CODES = {"none": 0, "left": 1, "right": 2, "up": 3, "down": 4, "big": 5, "small": 6, "within": 7}
 DIR_CODES = {"none": 0, "left": 1, "right": 2, "middle": 3, "up": 4, "down": 5}
@@ -27,6 +27,9 @@ SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgl_prep_crop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p]),
+    "hgl_ellipse_outline": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hgl_prep_circle": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_prep_setup": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_prep_main": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),

@@ -23,53 +23,12 @@
 #include <stdlib.h>
 
 #include "hgl_common.cuh"
+#include "prep_math.cuh"
 
 namespace hgl {
 
 constexpr int kPrepPx = 4;        // adjacent output pixels per thread
 constexpr int kPrepThreads = 256;
-
-struct Taps {
-  int i0, d;       // first source index, i1 - i0 (0 or 1)
-  float w0, w1;
-};
-
-// ATen area_pixel_compute_source_index + compute_source_index_and_lambda (float, align_corners=False)
-__device__ __forceinline__ float tap_scale(int in_size, int out_size) { return __fdiv_rn((float)in_size, (float)out_size); }
-// `scale` = tap_scale(in_size, out_size): one correctly-rounded division shared by every pixel of an axis
-__device__ __forceinline__ Taps make_taps(int dst, int in_size, int out_size, float scale) {
-  Taps t;
-  if (in_size == out_size) {
-    t.i0 = dst; t.d = 0; t.w0 = 1.f; t.w1 = 0.f;
-    return t;
-  }
-  float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
-  src = fmaxf(src, 0.f);
-  int i0 = (int)src;
-  i0 = min(i0, in_size - 1);
-  t.i0 = i0;
-  t.d = (i0 < in_size - 1) ? 1 : 0;
-  float w1 = __fsub_rn(src, (float)i0);
-  w1 = fminf(fmaxf(w1, 0.f), 1.f);
-  t.w1 = w1;
-  t.w0 = __fsub_rn(1.f, w1);
-  return t;
-}
-
-__device__ __forceinline__ float bilerp(float a, float b, float c, float d, float wx0, float wx1, float wy0, float wy1) {
-  const float top = __fmaf_rn(a, wx0, __fmul_rn(b, wx1));
-  const float bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
-  return __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
-}
-
-__device__ __forceinline__ Taps make_taps(int dst, int in_size, int out_size) { return make_taps(dst, in_size, out_size, tap_scale(in_size, out_size)); }
-
-__constant__ float c_in_mean[3] = {0.485f, 0.456f, 0.406f};
-__constant__ float c_in_std[3] = {0.229f, 0.224f, 0.225f};
-__constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-
-__device__ __forceinline__ float to_unit(uint32_t v) { return __fdiv_rn((float)v, 255.f); }                       // T.ToTensor
-__device__ __forceinline__ float to_norm(uint32_t v, int c) { return __fdiv_rn(__fsub_rn(to_unit(v), c_in_mean[c]), c_in_std[c]); }  // + T.Normalize
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pack: byte masks -> bit masks
@@ -699,7 +658,7 @@ extern "C" int hgl_prep_setup(const uint8_t* image, const uint8_t* blur, int B, 
                               void* workspace, void* stream) {
   using namespace hgl;
   HGL_REQUIRE(image && workspace, "hgl_prep: null pointer");
-  HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK, "hgl_prep: bg_mode %d", bg_mode);
+  HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK || bg_mode == HGL_BG_NONE, "hgl_prep: bg_mode %d", bg_mode);
   HGL_REQUIRE(bg_mode != HGL_BG_BLUR || blur, "hgl_prep: blur frame required for HGL_BG_BLUR");
   HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep: out_dtype %d", out_dtype);
   HGL_REQUIRE(B >= 1 && H >= 1 && W >= 1, "hgl_prep: bad shape B=%d H=%d W=%d", B, H, W);
@@ -709,7 +668,7 @@ extern "C" int hgl_prep_setup(const uint8_t* image, const uint8_t* blur, int B, 
   cudaStream_t st = (cudaStream_t)stream;
   const int SS = S * S;
   PrepWs ws = prep_carve(workspace, B, S, out_dtype);
-  const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : nullptr;
+  const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : bg_mode == HGL_BG_NONE ? image : nullptr;   // NONE: the frame is its own background
   if (out_dtype == HGL_BF16)
     prep_setup_kernel<true><<<dim3(ceil_div(SS, 256), B), 256, 0, st>>>(image, bgp, H, W, S, ws.planes, ws.taps, ws.lut);
   else
@@ -839,13 +798,13 @@ extern "C" int hgl_prep_crop(const uint8_t* image, const uint8_t* blur, const ui
   using namespace hgl;
   if (M == 0 && B >= 1) return HGL_OK;
   HGL_REQUIRE(image && bits && crop_xywh && local_out && global_out, "hgl_prep_crop: null pointer");
-  HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK, "hgl_prep_crop: bg_mode %d", bg_mode);
+  HGL_REQUIRE(bg_mode == HGL_BG_BLUR || bg_mode == HGL_BG_BLACK || bg_mode == HGL_BG_NONE, "hgl_prep_crop: bg_mode %d", bg_mode);
   HGL_REQUIRE(bg_mode != HGL_BG_BLUR || blur, "hgl_prep_crop: blur frame required for HGL_BG_BLUR");
   HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep_crop: out_dtype %d", out_dtype);
   HGL_REQUIRE(B >= 1 && M >= 0 && H >= 1 && W >= 1 && S >= 1 && S <= 4096, "hgl_prep_crop: bad shape");
   HGL_REQUIRE(mask_off || B == 1, "hgl_prep_crop: mask_off required when B > 1");
   HGL_REQUIRE(M <= 65535, "hgl_prep_crop: more than 65535 proposals per launch");
-  const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : nullptr;
+  const uint8_t* bgp = bg_mode == HGL_BG_BLUR ? blur : bg_mode == HGL_BG_NONE ? image : nullptr;   // NONE: the frame is its own background
   dim3 grid(std::min(ceil_div(S * S, 256), 64), M);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == HGL_BF16) prep_crop_kernel<true><<<grid, 256, 0, st>>>(image, bgp, bits, mask_off, crop_xywh, B, H, W, S, local_out, global_out);

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import DIR_CODES, HGL_BF16, HGL_BG_BLACK, HGL_BG_BLUR, HGL_F32, REL_CODES, check  # noqa: F401
+from ._lib import DIR_CODES, HGL_BF16, HGL_BG_BLACK, HGL_BG_BLUR, HGL_BG_NONE, HGL_F32, REL_CODES, check  # noqa: F401
 
 
 def _stream() -> int:
@@ -146,7 +146,7 @@ def _bits(masks_or_bits: torch.Tensor, W: Optional[int] = None) -> torch.Tensor:
 def _prep_frames(image: torch.Tensor, blur: Optional[torch.Tensor], background: str):
     img = image[None] if image.dim() == 3 else image
     _req(img, torch.uint8, "image", 4)
-    bg = {"blur": HGL_BG_BLUR, "black": HGL_BG_BLACK}[background]
+    bg = {"blur": HGL_BG_BLUR, "black": HGL_BG_BLACK, "none": HGL_BG_NONE}[background]
     bl = None
     if bg == HGL_BG_BLUR:
         if blur is None:
@@ -210,11 +210,17 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
                         mask_off: Optional[torch.Tensor] = None, max_n: Optional[int] = None, background: str = "blur",
                         dtype: torch.dtype = torch.float32,
                         out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                        workspace: Optional[torch.Tensor] = None, crop_xywh: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                        workspace: Optional[torch.Tensor] = None, crop_xywh: Optional[torch.Tensor] = None,
+                        circle: bool = False, circle_color=(255, 0, 0)) -> Tuple[torch.Tensor, torch.Tensor]:
     """The prep loop Hybridgl_main.py:92-125 for a whole batch.  Returns (local_imgs, global_imgs) [M,3,S,S].
     `masks` is bool/u8 [M,H,W] (packed internally) or the packed int32 [M,H,ceil(W/32)] from pack_masks().
+    background: what replaces the frame outside the mask in the global view -- "blur" | "black" | "none" (the frame itself).
     crop_xywh int32/int64 [M,4]: resample every proposal from its own box (x, y, w, h) instead of the full frame (hgl_prep_crop;
-    the reference always uses the full frame)."""
+    the reference always uses the full frame).
+    circle: the global view also carries the 'circle' prompt of utils.apply_visual_prompts (cv2.ellipse at mask2chw's centre,
+    utils.py:322-335), applied in the reference's order blur -> circle -> black (hgl_mask_geometry + hgl_prep_circle)."""
+    if circle and crop_xywh is not None:
+        raise ValueError("circle and crop_xywh cannot be combined")
     img, bl, bg = _prep_frames(image, blur, background)
     B, H, W, _ = img.shape
     bits = _bits(masks)
@@ -242,7 +248,25 @@ def prep_visual_prompts(image: torch.Tensor, blur: Optional[torch.Tensor], masks
     workspace = _prep_workspace(B, size, dtype, img.device, workspace)
     check(_lib.load().hgl_prep(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), B, M, max_n, H, W, size, bg, _dt(dtype),
                                local.data_ptr(), glob.data_ptr(), workspace.data_ptr(), _stream()), "hgl_prep")
+    if circle and M > 0:
+        chw = mask_geometry(bits, width=W, want_boxes=False, want_chw=True)
+        r, g, b = (int(v) for v in circle_color)
+        check(_lib.load().hgl_prep_circle(img.data_ptr(), _ptr(bl), bits.data_ptr(), _ptr(off), chw.data_ptr(), B, M, H, W, size, bg,
+                                          _dt(dtype), r, g, b, glob.data_ptr(), _stream()), "hgl_prep_circle")
     return local, glob
+
+
+def ellipse_outline(images: torch.Tensor, chw: torch.Tensor, color=(255, 0, 0)) -> torch.Tensor:
+    """cv2.ellipse(image_m, (cx, cy), (w // 2, h // 2), 0, 0, 360, color, 1) drawn IN PLACE into images u8 [M,H,W,3] for
+    chw int32 [M,4] = (center_y, center_x, height, width) per image (mask_geometry(..., want_chw=True)); utils.py:322-335."""
+    _req(images, torch.uint8, "images", 4)
+    _req(chw, torch.int32, "chw", 2)
+    M, H, W, C = images.shape
+    if C != 3 or tuple(chw.shape) != (M, 4):
+        raise ValueError("images must be [M,H,W,3] and chw [M,4]")
+    r, g, b = (int(v) for v in color)
+    check(_lib.load().hgl_ellipse_outline(images.data_ptr(), chw.data_ptr(), M, H, W, r, g, b, _stream()), "hgl_ellipse_outline")
+    return images
 
 
 # ---- (a2)-(a4) ----------------------------------------------------------------------------------------

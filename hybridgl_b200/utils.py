@@ -78,20 +78,24 @@ def mask2chw(arr):
     return (cy, cx), h, w
 
 
-def apply_visual_prompts(image_array, mask, visual_prompt_type=("blur",), blur_strength=(15, 15)):
-    """utils.py:292-345 on CUDA tensors for the compositing prompt types: 'blur' (sharp inside the mask, cv2.GaussianBlur(15,15)
-    outside) and 'black' (zeros outside), applied in the reference's order.  image_array u8 [H,W,3], mask bool/u8 [H,W];
-    returns u8 [H,W,3].  'circle' (a cv2.ellipse outline at mask2chw's centre) is not built: no driver calls it and it needs
-    OpenCV's fixed-point polygon rasteriser bit for bit."""
+def apply_visual_prompts(image_array, mask, visual_prompt_type=("circle",), color=(255, 0, 0), thickness=1, blur_strength=(15, 15)):
+    """utils.py:292-345 on CUDA tensors, the prompt types applied in the reference's order: 'blur' (sharp inside the mask,
+    cv2.GaussianBlur(15,15) outside), 'circle' (cv2.ellipse outline at mask2chw's centre with half axes (width // 2, height // 2):
+    hgl_mask_geometry + hgl_ellipse_outline, OpenCV's pixels) and 'black' (zeros outside).  image_array u8 [H,W,3], mask bool/u8
+    [H,W]; returns u8 [H,W,3].  Same defaults as the reference (visual_prompt_type=('circle',), red, thickness 1)."""
     if tuple(blur_strength) != (15, 15):
         raise ValueError("only the (15, 15) kernel of the reference's call is built (hgl_gaussian_blur15)")
+    if thickness != 1:
+        raise ValueError("only thickness 1 (the reference's default and only use) is built")
     img = image_array
     keep = (mask != 0)[:, :, None]
     for kind in ("blur", "circle", "black"):                # the order of the reference's if-chain
         if kind not in visual_prompt_type:
             continue
         if kind == "circle":
-            raise NotImplementedError("visual_prompt_type 'circle' is not built (see docstring)")
+            chw = ops.mask_geometry((mask != 0)[None].contiguous(), want_boxes=False, want_chw=True)
+            img = ops.ellipse_outline(img.contiguous().clone()[None], chw, color)[0]
+            continue
         bg = ops.gaussian_blur15(img.contiguous()) if kind == "blur" else torch.zeros_like(img)
         img = torch.where(keep, img, bg)
     return img

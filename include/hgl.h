@@ -47,6 +47,7 @@ extern "C" {
 /* background of the global view outside the mask (utils.py:292-345 apply_visual_prompts option set) */
 #define HGL_BG_BLUR 0     /* Gaussian-blurred frame  (Hybridgl_main.py:99-113; utils.py:306-320) */
 #define HGL_BG_BLACK 1    /* zeros                   (utils.py:336-341) */
+#define HGL_BG_NONE 2     /* the frame itself: nothing is replaced outside the mask (the 'circle' prompt on its own) */
 
 /* relation words of utils.py:240-268 (extract_rela_word, utils.py:207-237) */
 enum { HGL_REL_NONE = 0, HGL_REL_LEFT, HGL_REL_RIGHT, HGL_REL_UP, HGL_REL_DOWN, HGL_REL_BIG, HGL_REL_SMALL, HGL_REL_WITHIN };
@@ -94,6 +95,23 @@ HGL_API int hgl_prep(const uint8_t* image, const uint8_t* blur, const uint32_t* 
  * view.  The reference itself never crops (it casts pred_box at Hybridgl_main.py:101 and does not use it).  No workspace. */
 HGL_API int hgl_prep_crop(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off, const int32_t* crop_xywh,
                   int B, int M, int H, int W, int S, int bg_mode, int out_dtype, void* local_out, void* global_out, void* stream);
+
+/* ---- the 'circle' visual prompt (utils.py:322-335) -------------------------------------------------------
+ *   (cy, cx), h, w = mask2chw(mask);  cv2.ellipse(image, (cx, cy), (w // 2, h // 2), 0, 0, 360, color = (255, 0, 0), thickness = 1)
+ * chw int32 [M,4] = (center_y, center_x, height, width) per proposal, as hgl_mask_geometry writes it.  The outline is OpenCV's,
+ * pixel for pixel (polygon vertices in 16.16 fixed point, cv::clipLine, 8-connected left-to-right Bresenham edges; pinned against
+ * cv2 4.13 by the oracle).  An empty proposal (height or width 0; the reference raises) draws nothing.
+ *
+ * hgl_ellipse_outline: draws IN PLACE into images u8 [M,H,W,3]; image m gets the ellipse of chw[m] in colour (r, g, b).
+ * hgl_prep_circle: the batched form on the prep outputs.  Call after hgl_prep / hgl_prep_main with the same image, blur, bits,
+ *   mask_off, S, bg_mode and out_dtype: the pixels of global_out[n] whose bilinear taps touch proposal n's outline are re-evaluated
+ *   with the prompt applied in the reference's order (blur composite -> circle -> black composite), so that
+ *   global_out[n] == Normalize(Resize(ToTensor(apply_visual_prompts(frame, mask_n, types)))) (Hybridgl_main.py:103-118 with
+ *   utils.py:292-345 in place of the inline composite).  local_out does not see the prompt.  H * ceil(W/32) * 4 <= 200 KB. */
+HGL_API int hgl_ellipse_outline(uint8_t* images, const int32_t* chw, int M, int H, int W, int r, int g, int b, void* stream);
+HGL_API int hgl_prep_circle(const uint8_t* image, const uint8_t* blur, const uint32_t* bits, const int32_t* mask_off, const int32_t* chw,
+                            int B, int M, int H, int W, int S, int bg_mode, int out_dtype, int r, int g, int b, void* global_out,
+                            void* stream);
 
 /* hgl_prep in its two halves, for callers that overlap stages: hgl_prep_setup needs only the frames (per image: the
  * "all taps inside" / "all taps outside" answer planes and the tap bytes, left in `workspace`) and may be enqueued while

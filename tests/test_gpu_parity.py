@@ -389,7 +389,7 @@ def test_grid_heat_pool_on_raw_maps_equals_resize_then_pool(ops, hh, hw, h, w):
 # ------------------------------------------------------------------------------------------------ per-mask geometry, prompt variants
 def test_mask_geometry_matches_reference_golden(ops, golden):
     """hgl_mask_geometry: SAM's XYWH boxes and mask2chw, bit-exact against the reference's own functions (gen_golden.py::gen_geometry);
-    the host mirrors utils.mask2chw / utils.apply_visual_prompts ('blur', 'black') against recorded outputs."""
+    the host mirrors utils.mask2chw / utils.apply_visual_prompts ('blur', 'circle', 'black' and their combinations) against recorded outputs."""
     from hybridgl_b200 import utils as U
     g = golden("geometry")
     for ci in range(int(g["n_cases"])):
@@ -403,14 +403,67 @@ def test_mask_geometry_matches_reference_golden(ops, golden):
         assert [cy, cx, hh, ww] == g[f"c{ci}_chw"][2].tolist()
         if f"c{ci}_image" in g.files:
             img = cu(g[f"c{ci}_image"])
-            for i in (0, 1, 2):
-                for kind in ("blur", "black"):
-                    got = U.apply_visual_prompts(img, cu(masks[i]), visual_prompt_type=(kind,))
-                    assert np.array_equal(got.cpu().numpy(), g[f"c{ci}_{kind}"][i]), (ci, i, kind)
+            for i in range(n):
+                for tag, kinds in (("blur", ("blur",)), ("black", ("black",)), ("circle", ("circle",)), ("blur_circle", ("blur", "circle")),
+                                   ("circle_black", ("circle", "black"))):
+                    got = U.apply_visual_prompts(img, cu(masks[i]), visual_prompt_type=kinds)
+                    assert np.array_equal(got.cpu().numpy(), g[f"c{ci}_{tag}"][i]), (ci, i, tag)
     boxes, chw = ops.mask_geometry(torch.zeros((2, 9, 40), dtype=torch.bool, device=DEV), want_chw=True)
     assert boxes.tolist() == [[0, 0, 0, 0]] * 2 and chw.tolist() == [[-1, -1, 0, 0]] * 2
     with pytest.raises(ValueError):
         U.mask2chw(torch.zeros((9, 40), dtype=torch.bool, device=DEV))
+
+
+@pytest.mark.parametrize("h,w", [(48, 64), (97, 131), (480, 640), (600, 800), (33, 32)])
+def test_ellipse_outline_equals_cv2_restated(ops, h, w):
+    """hgl_ellipse_outline against the oracle's restatement of cv2.ellipse (itself pinned against cv2 and the reference goldens):
+    tiny, frame-filling and partly off-frame ellipses (clipped edges), degenerate axes."""
+    rng = np.random.default_rng(h + w)
+    n = 48
+    chw = np.zeros((n, 4), np.int32)
+    chw[:, 0] = rng.integers(0, h, n); chw[:, 1] = rng.integers(0, w, n)
+    chw[:, 2] = rng.integers(1, h + 1, n); chw[:, 3] = rng.integers(1, w + 1, n)
+    chw[:8, 2:] = rng.integers(1, 30, (8, 2))                       # small ones: every delta class
+    chw[8] = (0, 0, h, w); chw[9] = (h - 1, w - 1, h, w)            # centred on a corner: three quarters off the frame
+    chw[10] = (h // 2, w // 2, 1, 1); chw[11] = (h // 2, w // 2, h, 1)
+    chw[12] = (5, 5, 0, 0)                                          # empty proposal: nothing drawn
+    imgs = torch.zeros((n, h, w, 3), dtype=torch.uint8, device=DEV)
+    ops.ellipse_outline(imgs, cu(chw), (255, 7, 3))
+    got = imgs.cpu().numpy()
+    for i in range(n):
+        cy, cx, hh, ww = chw[i].tolist()
+        ref = O.ellipse_outline(h, w, cx, cy, ww // 2, hh // 2) if hh > 0 and ww > 0 else np.zeros((h, w), bool)
+        assert np.array_equal(got[i, :, :, 0] == 255, ref), (i, chw[i].tolist())
+        assert np.array_equal(got[i][ref], np.broadcast_to(np.array([255, 7, 3], np.uint8), (int(ref.sum()), 3)))
+        assert not got[i][~ref].any()
+
+
+@pytest.mark.parametrize("h,w,S,dtype,bgname", [(120, 160, 64, torch.float32, "none"), (97, 131, 48, torch.float32, "blur"),
+                                                (97, 131, 48, torch.bfloat16, "black"), (480, 640, 224, torch.float32, "blur"),
+                                                (480, 640, 224, torch.bfloat16, "none")])
+def test_prep_with_circle_prompt(ops, h, w, S, dtype, bgname):
+    """prep + hgl_prep_circle: global[n] == Normalize(Resize(apply_visual_prompts(frame, mask_n, types))) with the prompt types in
+    the reference's order (blur -> circle -> black); bit-exact against the oracle chain (f32) / its RNE (bf16).  Ragged two-image
+    batch; one proposal hugs the frame edge so that its ellipse is clipped."""
+    n0, n1 = 4, 3
+    a = synth.make_item(61, h, w, n0, 0, with_features=False)
+    b = synth.make_item(62, h, w, n1, 0, with_features=False)
+    a.masks[1] = False; a.masks[1, : h // 2, : w // 5] = True; a.masks[1, 0, :] = True       # centroid far from the box centre
+    img = cu(np.stack([a.image, b.image]))
+    masks = cu(np.concatenate([a.masks, b.masks]))
+    blur = ops.gaussian_blur15(img)
+    off = cu(np.array([0, n0, n0 + n1], np.int32))
+    loc, glo = ops.prep_visual_prompts(img, blur, masks, S, mask_off=off, max_n=n0, background=bgname, dtype=dtype, circle=True)
+    l0, g0 = ops.prep_visual_prompts(img, blur, masks, S, mask_off=off, max_n=n0, background=bgname, dtype=dtype)
+    assert torch.equal(loc, l0) and not torch.equal(glo, g0)        # the local view does not see the prompt
+    bl = blur.cpu().numpy()
+    for k, it in enumerate((a, b)):
+        rl, rg = O.prep(it.image, bl[k], it.masks, S, background=bgname, circle=True)
+        sl = slice(0, n0) if k == 0 else slice(n0, n0 + n1)
+        if dtype == torch.float32:
+            assert np.array_equal(glo[sl].cpu().numpy(), rg) and np.array_equal(loc[sl].cpu().numpy(), rl)
+        else:
+            assert np.array_equal(glo[sl].float().cpu().numpy(), bf16r(rg))
 
 
 @pytest.mark.parametrize("h,w,S,dtype", [(120, 160, 64, torch.float32), (97, 131, 48, torch.bfloat16), (480, 640, 224, torch.float32)])
