@@ -36,6 +36,8 @@ def main(argv=None):
     ap.add_argument("--fusion_mode", default="G2L&L2G", choices=["G2L", "L2G", "G2L&L2G"])
     ap.add_argument("--masking_block", type=int, default=9)
     ap.add_argument("--bf16", action="store_true", help="run the ViT blocks and the prep outputs in bf16")
+    ap.add_argument("--unfused-ln", action="store_true", help="token masking, torch.cat and ln_1 as separate passes (the round-1 forward) "
+                    "instead of hgl_token_mask_fuse_ln")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     a = ap.parse_args(argv)
@@ -43,6 +45,7 @@ def main(argv=None):
     dev = torch.device("cuda", torch.cuda.current_device())
     dt = torch.bfloat16 if a.bf16 else torch.float32
     model = CLIPViTFM("ViT-B/16", device=dev, dtype=dt)                               # Hybridgl_main.py:47
+    model.fused_ln = not a.unfused_ln
     S, g, de = 224, 14, 512
     cum = torch.zeros(4, dtype=torch.int64, device=dev)                              # cum_I, cum_U, cum_I_final, cum_U_final (:52-55)
     rows = []

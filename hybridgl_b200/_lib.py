@@ -42,6 +42,8 @@ SIGNATURES = {
     "hgl_cls_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hgl_cls_head": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_int, c_void_p,
                              c_void_p]),
+    "hgl_token_mask_fuse_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p]),
     "hgl_token_mask_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "hgl_dir_mask": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -91,8 +91,10 @@ class ResBlock(nn.Module):
                     o[lo:hi, :, 0, :] = ops.cls_attention(qkv3[lo:hi], cls_bias[lo:hi].contiguous(), self.heads)
         return self.attn.out_proj(o.transpose(1, 2).reshape(M, L1, D))
 
-    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None, causal: bool = False, rows=None) -> torch.Tensor:
-        x = x + self.attention(self.ln_1(x), cls_bias, causal, rows)
+    def forward(self, x: torch.Tensor, cls_bias: Optional[torch.Tensor] = None, causal: bool = False, rows=None,
+                h: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """h: ln_1(x) when the caller already has it (hgl_token_mask_fuse_ln writes it together with the fused streams)."""
+        x = x + self.attention(self.ln_1(x) if h is None else h, cls_bias, causal, rows)
         h = self.mlp.c_fc(self.ln_2(x))
         h = h * torch.sigmoid(1.702 * h)                                        # QuickGELU
         return x + self.mlp.c_proj(h)
@@ -245,6 +247,25 @@ class CLIPViTFM(nn.Module):
         return ops.make_attn_mask(pred_masks.float().contiguous(), self.num_heads)
 
     # ---- model/backbone.py:117-309 ---------------------------------------------------------------------------------
+    fused_ln = True      # False: hgl_token_mask_fuse + torch.cat + the block's own LayerNorm (the round-1 path; examples/eval_synthetic.py times both)
+
+    def _fuse_ln(self, blk, streams):
+        """streams: [(src, add, grid, a, b)] of equal shape [N, L1, D].  Returns (x, ln_1(x)) of the concatenated batch [len * N, L1, D],
+        every stream fused and normalised by one launch straight into its slice."""
+        if not self.fused_ln:
+            parts = [src if (add is None and grid is None) else ops.token_mask_fuse(src.contiguous(), add, grid, a, b, layout="NLD")
+                     for src, add, grid, a, b in streams]
+            return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)), None
+        src0 = streams[0][0].contiguous()
+        N = src0.shape[0]
+        xcat = torch.empty((len(streams) * N,) + tuple(src0.shape[1:]), dtype=src0.dtype, device=src0.device)
+        hcat = torch.empty_like(xcat)
+        gam, bet = blk.ln_1.weight.float().contiguous(), blk.ln_1.bias.float().contiguous()
+        for k, (src, add, grid, a, b) in enumerate(streams):
+            ops.token_mask_fuse_ln(src.contiguous(), None if add is None else add.contiguous(), grid, a, b, gam, bet, blk.ln_1.eps,
+                                   out_x=xcat[k * N:(k + 1) * N], out_ln=hcat[k * N:(k + 1) * N])
+        return xcat, hcat
+
     @torch.no_grad()
     def forward(self, local_imgs, global_imgs, pred_masks, masking_block: Optional[int] = None, fusion_mode: str = "G2L"):
         if masking_block is None:
@@ -269,7 +290,8 @@ class CLIPViTFM(nn.Module):
                 if i >= masking_block:
                     if x.shape[0] != N:
                         x = x.expand(N, -1, -1).contiguous()
-                    x = blk(ops.token_mask_fuse(x, None, grid, 1.0, 0.0, layout="NLD"))
+                    xf, h = self._fuse_ln(blk, [(x, None, grid, 1.0, 0.0)])          # token masking + ln_1 in one pass
+                    x = blk(xf, h=h)
                     if i == final:
                         return vit.head(x)
                 else:
@@ -303,20 +325,25 @@ class CLIPViTFM(nn.Module):
                 x, x2 = both[:N], both[N:]
                 if fusion_mode == "G2L&L2G":
                     xhl, xhg = x, x2
+            # Each stream of the block is written ONCE, already mixed, into its slice of the block's batch together with its ln_1
+            # (hgl_token_mask_fuse_ln): no torch.cat copy, no separate LayerNorm pass.  (src, add, grid, a, b) = a*tokenmask(src) + b*add
             if fusion_mode == "G2L":                                              # model/backbone.py:227-260
-                mixed = ops.token_mask_fuse(x2, x, grid, 2.0, 1.0, layout="NLD")  # 2*tokenmask(x2) + x
-                out = blk(torch.cat([mixed, x2], dim=0), torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)])
+                xcat, hcat = self._fuse_ln(blk, [(x2, x, grid, 2.0, 1.0),         # 2*tokenmask(x2) + x
+                                                 (x2, None, None, 1.0, 0.0)])
+                out = blk(xcat, torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)], h=hcat)
                 x, x2 = out[:N], out[N:]
                 result = x
             elif fusion_mode == "L2G":                                            # model/backbone.py:206-225
-                mixed = ops.token_mask_fuse(x2, x, None, 2.0, 1.0, layout="NLD")  # x_old + 2*x2
-                out = blk(torch.cat([x, mixed], dim=0), torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)])
+                xcat, hcat = self._fuse_ln(blk, [(x, None, None, 1.0, 0.0),
+                                                 (x2, x, None, 2.0, 1.0)])        # x_old + 2*x2
+                out = blk(xcat, torch.cat([zero, bias], dim=0), rows=[(N, 2 * N)], h=hcat)
                 x, x2 = out[:N], out[N:]
                 result = x2
             else:                                                                 # model/backbone.py:262-306
-                mixl = ops.token_mask_fuse(x2, xhl, grid, 2.0, 1.0, layout="NLD")   # xhl + 2*tokenmask(x2)
-                mixg = ops.token_mask_fuse(xhg, x, None, 2.0, 1.0, layout="NLD")    # x + 2*xhg
-                out = blk(torch.cat([x, x2, mixl, mixg], dim=0), torch.cat([zero, bias, zero, bias], dim=0), rows=[(N, 2 * N), (3 * N, 4 * N)])
+                xcat, hcat = self._fuse_ln(blk, [(x, None, None, 1.0, 0.0), (x2, None, None, 1.0, 0.0),
+                                                 (x2, xhl, grid, 2.0, 1.0),       # xhl + 2*tokenmask(x2)
+                                                 (xhg, x, None, 2.0, 1.0)])       # x + 2*xhg
+                out = blk(xcat, torch.cat([zero, bias, zero, bias], dim=0), rows=[(N, 2 * N), (3 * N, 4 * N)], h=hcat)
                 x, x2, xhl, xhg = out[:N], out[N:2 * N], out[2 * N:3 * N], out[3 * N:]
                 result = None
             if i == final:

@@ -99,7 +99,123 @@ __global__ void __launch_bounds__(256) token_mask_fuse_kernel(const void* __rest
   }
 }
 
+// (f1) the same fuse with the LayerNorm that follows it (ln_1 of the masked block, clip/model.py:244-257) in the same pass: a WARP
+// owns a token row (NLD layout), keeps the fused row in registers, stores it (rounded to the stream dtype, like the unfused path),
+// and normalises the STORED values in f32 (CLIP's LayerNorm runs in fp32 whatever the stream dtype, clip/model.py:188-195):
+// two-pass mean / variance over the registers, y = (x - mean) * rsqrt(var + eps) * gamma + beta.
+constexpr int kLnMaxV = 8;                     // 8-element vectors per lane: D <= 2048
+template <bool kBF16>
+__global__ void __launch_bounds__(256) token_mask_fuse_ln_kernel(const void* __restrict__ src_, const void* __restrict__ add_,
+                                                                 const float* __restrict__ grid, float a, float b,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                 int L1, int M, int D, void* __restrict__ out_x, void* __restrict__ out_ln) {
+  const int L = L1 - 1, dv = D / 8, lane = threadIdx.x & 31;
+  const size_t rows = (size_t)M * L1;
+  const float inv_d = 1.f / (float)D;
+  for (size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (size_t)gridDim.x * 8) {
+    const int m = (int)(row / L1), l = (int)(row - (size_t)m * L1);
+    float w = a;
+    if (grid != nullptr && l > 0) w = a * grid[(size_t)m * L + (l - 1)];
+    float o[kLnMaxV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < kLnMaxV; ++u) {
+      const int vi = lane + 32 * u;
+      if (vi >= dv) break;
+      const size_t v = row * dv + vi;
+      float x[8], y[8];
+      if (kBF16) {
+        const uint4 s4 = reinterpret_cast<const uint4*>(src_)[v];
+        const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x[2 * q] = bf16_bits_to_float(sw[q] & 0xffffu); x[2 * q + 1] = bf16_bits_to_float(sw[q] >> 16); }
+        if (add_) {
+          const uint4 t4 = reinterpret_cast<const uint4*>(add_)[v];
+          const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { y[2 * q] = bf16_bits_to_float(tw[q] & 0xffffu); y[2 * q + 1] = bf16_bits_to_float(tw[q] >> 16); }
+        }
+      } else {
+        const float4 s0 = reinterpret_cast<const float4*>(src_)[2 * v], s1 = reinterpret_cast<const float4*>(src_)[2 * v + 1];
+        x[0] = s0.x; x[1] = s0.y; x[2] = s0.z; x[3] = s0.w; x[4] = s1.x; x[5] = s1.y; x[6] = s1.z; x[7] = s1.w;
+        if (add_) {
+          const float4 t0 = reinterpret_cast<const float4*>(add_)[2 * v], t1 = reinterpret_cast<const float4*>(add_)[2 * v + 1];
+          y[0] = t0.x; y[1] = t0.y; y[2] = t0.z; y[3] = t0.w; y[4] = t1.x; y[5] = t1.y; y[6] = t1.z; y[7] = t1.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float t = __fmul_rn(x[q], w);
+        float r = add_ ? __fadd_rn(t, __fmul_rn(y[q], b)) : t;
+        if (kBF16) r = bf16_bits_to_float(pack_bf16x2(r, 0.f) & 0xffffu);          // the value the stream stores
+        o[u][q] = r;
+        sum += r;
+      }
+      if (out_x) {
+        if (kBF16) {
+          uint4 r4;
+          r4.x = pack_bf16x2(o[u][0], o[u][1]); r4.y = pack_bf16x2(o[u][2], o[u][3]);
+          r4.z = pack_bf16x2(o[u][4], o[u][5]); r4.w = pack_bf16x2(o[u][6], o[u][7]);
+          reinterpret_cast<uint4*>(out_x)[v] = r4;
+        } else {
+          reinterpret_cast<float4*>(out_x)[2 * v] = make_float4(o[u][0], o[u][1], o[u][2], o[u][3]);
+          reinterpret_cast<float4*>(out_x)[2 * v + 1] = make_float4(o[u][4], o[u][5], o[u][6], o[u][7]);
+        }
+      }
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int u = 0; u < kLnMaxV; ++u) {
+      if (lane + 32 * u >= dv) break;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const float d = o[u][q] - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+#pragma unroll
+    for (int u = 0; u < kLnMaxV; ++u) {
+      const int vi = lane + 32 * u;
+      if (vi >= dv) break;
+      const size_t v = row * dv + vi;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y[q] = (o[u][q] - mean) * rstd * gg[q] + bb[q];
+      if (kBF16) {
+        uint4 r4;
+        r4.x = pack_bf16x2(y[0], y[1]); r4.y = pack_bf16x2(y[2], y[3]); r4.z = pack_bf16x2(y[4], y[5]); r4.w = pack_bf16x2(y[6], y[7]);
+        reinterpret_cast<uint4*>(out_ln)[v] = r4;
+      } else {
+        reinterpret_cast<float4*>(out_ln)[2 * v] = make_float4(y[0], y[1], y[2], y[3]);
+        reinterpret_cast<float4*>(out_ln)[2 * v + 1] = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    }
+  }
+}
+
 }  // namespace hgl
+
+extern "C" int hgl_token_mask_fuse_ln(const void* src, const void* add, const float* grid, float a, float b, const float* gamma,
+                                      const float* beta, float eps, int L1, int M, int D, int dtype, void* out_x, void* out_ln, void* stream) {
+  using namespace hgl;
+  HGL_REQUIRE(src && out_ln && gamma && beta, "hgl_token_mask_fuse_ln: null pointer");
+  HGL_REQUIRE(L1 >= 2 && M >= 0 && D >= 8 && D % 8 == 0 && D <= 256 * kLnMaxV, "hgl_token_mask_fuse_ln: bad shape L1=%d M=%d D=%d (D %% 8, D <= %d)",
+              L1, M, D, 256 * kLnMaxV);
+  HGL_REQUIRE(dtype == HGL_F32 || dtype == HGL_BF16, "hgl_token_mask_fuse_ln: dtype %d", dtype);
+  HGL_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out_x) | reinterpret_cast<uintptr_t>(out_ln) |
+                reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+              "hgl_token_mask_fuse_ln: tensors must be 16-byte aligned");
+  if (M == 0) return HGL_OK;
+  const size_t rows = (size_t)M * L1;
+  const int blocks = (int)std::min<size_t>((rows + 7) / 8, (size_t)sm_count() * 8);
+  if (dtype == HGL_BF16)
+    token_mask_fuse_ln_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, gamma, beta, eps, L1, M, D, out_x, out_ln);
+  else
+    token_mask_fuse_ln_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, add, grid, a, b, gamma, beta, eps, L1, M, D, out_x, out_ln);
+  return launch_status("hgl_token_mask_fuse_ln");
+}
 
 extern "C" int hgl_attn_mask(const float* grid, int M, int L, int heads, uint8_t* out, void* stream) {
   using namespace hgl;

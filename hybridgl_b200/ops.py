@@ -342,6 +342,41 @@ def token_mask_fuse(src: torch.Tensor, add: Optional[torch.Tensor], grid: Option
     return out
 
 
+def token_mask_fuse_ln(src: torch.Tensor, add: Optional[torch.Tensor], grid: Optional[torch.Tensor], a: float, b: float,
+                       gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, out_x: Optional[torch.Tensor] = None,
+                       out_ln: Optional[torch.Tensor] = None, want_x: bool = True):
+    """token_mask_fuse (NLD layout) + the LayerNorm that follows it, one pass (hgl_token_mask_fuse_ln).  src / add [M, L+1, D];
+    gamma / beta f32 [D].  Returns (out_x, out_ln); out_x is None with want_x=False.  out_x / out_ln may be slices along dim 0 of
+    larger tensors (the block's concatenated batch)."""
+    _req(src, (torch.float32, torch.bfloat16), "src", 3)
+    M, L1, D = src.shape
+    if add is not None:
+        _req(add, src.dtype, "add", 3)
+        if add.shape != src.shape:
+            raise ValueError("add must have the shape of src")
+    if grid is not None:
+        _req(grid, torch.float32, "grid")
+        if grid.shape[0] != M or grid[0].numel() != L1 - 1:
+            raise ValueError(f"grid {tuple(grid.shape)} does not match streams {tuple(src.shape)}")
+    _req(gamma, torch.float32, "gamma", 1)
+    _req(beta, torch.float32, "beta", 1)
+    if gamma.numel() != D or beta.numel() != D:
+        raise ValueError("gamma / beta must be [D]")
+    if out_ln is None:
+        out_ln = torch.empty_like(src)
+    if want_x and out_x is None:
+        out_x = torch.empty_like(src)
+    for t, name in ((out_ln, "out_ln"), (out_x, "out_x")):
+        if t is not None:
+            _req(t, src.dtype, name, 3)
+            if t.shape != src.shape:
+                raise ValueError(f"{name} must have the shape of src")
+    check(_lib.load().hgl_token_mask_fuse_ln(src.data_ptr(), _ptr(add), _ptr(grid), float(a), float(b), gamma.data_ptr(), beta.data_ptr(),
+                                             float(eps), L1, M, D, _dt(src.dtype), _ptr(out_x if want_x else None), out_ln.data_ptr(),
+                                             _stream()), "hgl_token_mask_fuse_ln")
+    return (out_x if want_x else None), out_ln
+
+
 def cls_attention(qkv: torch.Tensor, bias: Optional[torch.Tensor], heads: int) -> torch.Tensor:
     """Attention output of the CLS query alone under the key bias (hgl_cls_attention).  qkv [M, L1, 3*D] (the packed in_proj output,
     f32 / bf16), bias f32 [M, L1] or None.  Returns [M, heads, hd] of qkv's dtype."""

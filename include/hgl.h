@@ -165,6 +165,14 @@ HGL_API int hgl_cls_head(const void* x, int64_t row_stride, const void* gamma, c
  * src/add/out [L+1, M, D] (layout HGL_LND) or [M, L+1, D] (HGL_NLD) of dtype; grid f32 [M,L]. out may alias src or add. */
 HGL_API int hgl_token_mask_fuse(const void* src, const void* add, const float* grid, float a, float b,
                         int L1, int M, int D, int dtype, int layout, void* out, void* stream);
+/* (f1) The same fuse and the LayerNorm that follows it in the masked block (ln_1, third_party/modified_CLIP/clip/model.py:244-257,
+ * computed in fp32 like CLIP's LayerNorm, :188-195) in one pass over the tokens, NLD layout [M, L+1, D]:
+ *   out_x  = a * tokenmask(src, grid) + b * add      rounded to `dtype` (may be NULL when the stream is not needed again)
+ *   out_ln = LayerNorm(out_x) * gamma + beta          f32 arithmetic on the stored out_x; gamma, beta f32 [D]
+ * add / grid may be NULL (a = 1: plain copy + LayerNorm).  D % 8 == 0, D <= 2048.  out_x / out_ln may be slices of larger tensors
+ * (contiguous [M, L+1, D] blocks): the hybrid forward writes its streams straight into the block's concatenated batch. */
+HGL_API int hgl_token_mask_fuse_ln(const void* src, const void* add, const float* grid, float a, float b, const float* gamma,
+                                   const float* beta, float eps, int L1, int M, int D, int dtype, void* out_x, void* out_ln, void* stream);
 
 /* ---- (a10)+(a11) heat-map conditioning and mask pooling ---------------------------------------------
  * Replaces Hybridgl_main.py:204-223 and gen_dir_mask utils.py:135-161:

@@ -183,3 +183,48 @@ def test_cls_head_kernel_vs_torch(M, L1, Dv, De, dtype):
     torch.testing.assert_close(got, ref, rtol=tol, atol=tol)
     ops.cls_head(x, gamma, beta, proj, 1e-5, out=got, accumulate=True)
     torch.testing.assert_close(got, 2 * ref, rtol=tol, atol=2 * tol)
+
+
+@pytest.mark.parametrize("M,L1,D,dtype", [(5, 17, 64, torch.float32), (3, 197, 768, torch.bfloat16), (2, 577, 1024, torch.bfloat16),
+                                          (4, 50, 768, torch.float32), (1, 2, 2048, torch.float32)])
+def test_token_mask_fuse_ln_equals_fuse_then_layernorm(M, L1, D, dtype):
+    """hgl_token_mask_fuse_ln (f1): the fused stream is bit-identical to hgl_token_mask_fuse, its LayerNorm equals CLIP's fp32
+    LayerNorm (clip/model.py:188-195) of the STORED stream; also the plain copy + LayerNorm form and slice outputs."""
+    from hybridgl_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(M * 1000 + D)
+    src = torch.randn((M, L1, D), generator=gen, device=DEV).to(dtype)
+    add = torch.randn((M, L1, D), generator=gen, device=DEV).to(dtype)
+    grid = torch.rand((M, L1 - 1), generator=gen, device=DEV)
+    grid[:, ::3] = 0.0
+    gam = 1 + 0.1 * torch.randn(D, generator=gen, device=DEV); bet = 0.1 * torch.randn(D, generator=gen, device=DEV)
+    tol = dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=1.6e-2, atol=1.6e-2)
+    for a_, g_, a, b in ((add, grid, 2.0, 1.0), (add, None, 2.0, 1.0), (None, grid, 1.0, 0.0), (None, None, 1.0, 0.0)):
+        ref_x = ops.token_mask_fuse(src, a_, g_, a, b, layout="NLD")
+        ref_h = torch.nn.functional.layer_norm(ref_x.float(), (D,), gam, bet, 1e-5)
+        big_x = torch.zeros((M + 2, L1, D), dtype=dtype, device=DEV); big_h = torch.zeros_like(big_x)
+        x, h = ops.token_mask_fuse_ln(src, a_, g_, a, b, gam, bet, 1e-5, out_x=big_x[1:M + 1], out_ln=big_h[1:M + 1])
+        assert torch.equal(x, ref_x)
+        torch.testing.assert_close(h.float(), ref_h, **tol)
+        if dtype == torch.bfloat16:                                  # off by at most one bf16 step from the rounded fp32 LayerNorm
+            assert (h.float() - ref_h.to(dtype).float()).abs().max() <= 2.0 ** -6 * max(1.0, float(ref_h.abs().max()))
+        assert not big_x[0].any() and not big_x[M + 1].any() and not big_h[0].any() and not big_h[M + 1].any()
+        x2, h2 = ops.token_mask_fuse_ln(src, a_, g_, a, b, gam, bet, 1e-5, want_x=False)
+        assert x2 is None and torch.equal(h2, h)
+
+
+def test_fused_and_unfused_ln_forward_agree(model, golden):
+    """The hybrid forward with hgl_token_mask_fuse_ln (default) against the same forward with hgl_token_mask_fuse + torch.cat +
+    the block's own LayerNorm, every fusion mode of the toy model."""
+    g = golden("forward")
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    loc, glo, masks = cu(g["local"]), cu(g["global"]), cu(g["masks"])
+    for mode in ("G2L", "L2G", "G2L&L2G", "token_masking"):
+        with torch.no_grad():
+            model.fused_ln = True
+            a = model(loc, glo, masks, masking_block=1, fusion_mode=mode)
+            model.fused_ln = False
+            try:
+                b = model(loc, glo, masks, masking_block=1, fusion_mode=mode)
+            finally:
+                model.fused_ln = True
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
