@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(256) pack_masks_rows_kernel(const uint8_t* __r
 // setup: per-image FG / BG answer planes + tap bytes
 // ---------------------------------------------------------------------------------------------------------------------
 // planes: [B][12][S*S] in the output dtype; plane k = 3*kind + channel, kind 0 = FG local, 1 = FG global, 2 = BG local, 3 = BG global
-// taps:   [B][6][S*S] u32; words 0-2 image bytes, 3-5 background bytes, byte index inside the 12 = tap*3 + channel
+// taps:   [B][S*S][8] u32 (one 32-byte sector per output pixel); words 0-2 image bytes, 3-5 background bytes (6-7 unused), byte
+//         index inside the 12 = tap*3 + channel.  One sector = one prefetch when an outline pixel is filed, two 16-byte loads when
+//         it is evaluated (six planar words cost six sectors per pixel: 154 MB instead of 26 MB of sector traffic per pass).
 template <bool kBF16>
 __global__ void __launch_bounds__(256) prep_setup_kernel(const uint8_t* __restrict__ image, const uint8_t* __restrict__ blur, int H, int W, int S,
                                                          void* __restrict__ planes, uint32_t* __restrict__ taps, float* __restrict__ lut) {
@@ -158,11 +160,9 @@ __global__ void __launch_bounds__(256) prep_setup_kernel(const uint8_t* __restri
     if (kBF16) reinterpret_cast<__nv_bfloat16*>(planes)[o] = __float2bfloat16_rn(v[k]);
     else reinterpret_cast<float*>(planes)[o] = v[k];
   }
-#pragma unroll
-  for (int w = 0; w < 3; ++w) {
-    taps[((size_t)b * 6 + w) * SS + px] = iw[w];
-    taps[((size_t)b * 6 + 3 + w) * SS + px] = bw[w];
-  }
+  uint4* tp = reinterpret_cast<uint4*>(taps + ((size_t)b * SS + px) * 8);
+  tp[0] = make_uint4(iw[0], iw[1], iw[2], bw[0]);
+  tp[1] = make_uint4(bw[1], bw[2], 0u, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -172,7 +172,7 @@ struct PrepParams {
   const uint32_t* bits;       // [M,H,WW]
   const int32_t* mask_off;
   const void* planes;         // [B,12,S*S]
-  const uint32_t* taps;       // [B,6,S*S]
+  const uint32_t* taps;       // [B,S*S,8]
   const float* lut;           // [1024] byte -> unit / normalised value
   void* local_out;
   void* global_out;
@@ -217,15 +217,12 @@ struct Pack {
 // Only pixels whose taps straddle the mask outline come here, through the dense per-warp resolve step of prep_main_kernel.
 // lut: tables (built by prep_setup_kernel, L1-resident) of the two per-byte maps, [0..255] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255)
 // -- the same correctly-rounded divisions as to_unit / to_norm, evaluated once per image batch instead of 27 times per pixel.
-__device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__ taps, size_t tap0, int SS, uint32_t code,
+__device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__ taps, size_t tap0, uint32_t code,
                                                     float wx0, float wx1, float wy0, float wy1, const float* __restrict__ lut,
                                                     float* __restrict__ out6) {
-  uint32_t iw[3], bw[3];
-#pragma unroll
-  for (int w = 0; w < 3; ++w) {
-    iw[w] = __ldg(taps + tap0 + (size_t)w * SS);
-    bw[w] = __ldg(taps + tap0 + (size_t)(3 + w) * SS);
-  }
+  // tap0 = (image * S*S + pixel) * 8: the pixel's 32-byte record (brought into L1 by the prefetch issued when it was filed)
+  const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(taps + tap0)), t1 = __ldg(reinterpret_cast<const uint4*>(taps + tap0) + 1);
+  const uint32_t iw[3] = {t0.x, t0.y, t0.z}, bw[3] = {t0.w, t1.x, t1.y};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float gv[4], lv[4];
@@ -243,7 +240,12 @@ __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__
   }
 }
 
-constexpr int kPrepStages = 3;      // shared-memory ring of bit-row stages
+#ifndef HGL_PREP_STAGES
+#define HGL_PREP_STAGES 3
+#endif
+constexpr int kPrepStages = HGL_PREP_STAGES;      // shared-memory ring of bit-row stages (<= 8: the barrier block below)
+constexpr int kPrepBarBytes = 128;  // full[kPrepStages] | empty[kPrepStages] mbarriers
+static_assert(2 * kPrepStages * 8 <= kPrepBarBytes, "barrier block");
 constexpr int kPrepSubDefault = 4;  // masks per stage (PrepParams::sub; HGL_PREP_SUB overrides for tuning)
 constexpr int kPrepWq = 512;        // per-warp list of outline pixels waiting for their exact value (>= 32 lanes x 8 pixels)
 constexpr int kPrepMaxSub = 16;     // masks per stage, at most
@@ -288,7 +290,7 @@ __device__ __forceinline__ void prep_pixel_of(const PrepGeom& gm, int bxi, int b
 template <bool kBF16, int PX, bool kTMA, bool kNarrow>
 __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepParams p) {
   extern __shared__ __align__(128) uint8_t sm_prep[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages]  (64 bytes reserved for both)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages]  (kPrepBarBytes reserved for both)
   uint64_t* empty = full + kPrepStages;                                        // [kPrepStages]
   const float* lut = p.lut;
 
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const int SS = S * S;
   const PrepGeom gm = {p.gw, p.gh, p.cw, p.nbx, p.strip};
   const int ncons = 32 * gm.cw;                                                // consumer threads (the producer warp comes after them)
-  uint32_t* stage_base = reinterpret_cast<uint32_t*>(sm_prep + 64 + (size_t)gm.cw * kPrepWarpBytes);   // [kPrepStages][kPrepSub][rows * WW] + 16 B
+  uint32_t* stage_base = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + (size_t)gm.cw * kPrepWarpBytes);   // [kPrepStages][kPrepSub][rows * WW] + 16 B
   // blockIdx.x = band tile * gz + z: the gz CTAs that share a band tile's answer planes (and the CTAs of one image) are dispatched
   // back to back, so the planes are fetched from HBM once per image and served from L2 to the rest (with z as a grid dimension the
   // z-slices of an image ran a wave apart and every one of them re-fetched the planes: 2.3x read amplification in ncu)
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   }
 
   // ---- consumers
-  uint32_t* wq = reinterpret_cast<uint32_t*>(sm_prep + 64 + (size_t)warp * kPrepWarpBytes);   // [kPrepWq] mask << 16 | owner pixel << 4 | tap code
+  uint32_t* wq = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + (size_t)warp * kPrepWarpBytes);   // [kPrepWq] mask << 16 | owner pixel << 4 | tap code
   int i, j0;
   prep_pixel_of(gm, bxi, byi, tid, PX, i, j0);
   const bool live = i <= row_last && j0 < S;                         // partial last band / idle lanes of the last warp (strip mode)
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   uint8_t* lp0 = reinterpret_cast<uint8_t*>(p.local_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;    // planes of mask n_lo
   uint8_t* gp0 = reinterpret_cast<uint8_t*>(p.global_out) + ((size_t)n_lo * 3 * SS + px0) * kElem;
   const int row_off0 = lead + (ty.i0 - ylo) * WW, row_off1 = row_off0 + ty.d * WW;
-  const size_t tap_base = (size_t)b * 6 * SS;
+  const uint32_t tap_base = (uint32_t)b * (uint32_t)SS * 8u;          // word offset of the image's tap records (< 2^32: host check)
+  const uint32_t tap_px0 = tap_base + (uint32_t)px0 * 8u;
 
   // exact values of the listed outline pixels (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel), one lane
   // per pixel; overwrites the placeholders this warp stored earlier (ordered by the __syncwarp)
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
       const int pj = pj0 + oq, gpx = pi * S + pj;
       const Taps tyy = make_taps(pi, H, S, sc_y), txx = make_taps(pj, W, S, sc_x);
       float o6[6];
-      prep_boundary_pixel(p.taps, tap_base + gpx, SS, ent & 15u, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
+      prep_boundary_pixel(p.taps, tap_base + (uint32_t)gpx * 8u, ent & 15u, txx.w0, txx.w1, tyy.w0, tyy.w1, lut, o6);
       const size_t o = ((size_t)(n_lo + (int)(ent >> 16)) * 3) * SS + gpx;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
             code = (codes >> (4 * q)) & 15u;
           }
           wq[slot_w++] = ((uint32_t)(c0 + k) << 16) | ((uint32_t)(lane * PX + q) << 4) | code;
+          prefetch_l1(p.taps + tap_px0 + q * 8);              // the record is in L1 by the time the list is flushed
         }
         wcount += total;
       }
@@ -604,7 +608,7 @@ static PrepWs prep_carve(void* ws, int B, int S, int out_dtype) {
   auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~size_t(255); return o; };
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   w.planes = base + take((size_t)B * 12 * SS * elem);
-  w.taps = reinterpret_cast<uint32_t*>(base + take((size_t)B * 6 * SS * 4));
+  w.taps = reinterpret_cast<uint32_t*>(base + take((size_t)B * 8 * SS * 4));
   w.lut = reinterpret_cast<float*>(base + take(1024 * 4));
   w.bytes = off;
   return w;
@@ -691,6 +695,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   using namespace hgl;
   if (M == 0 && B >= 1) return HGL_OK;
   HGL_REQUIRE(bits && local_out && global_out && workspace, "hgl_prep: null pointer");
+  HGL_REQUIRE((uint64_t)B * (uint64_t)S * S * 8 < (1ull << 32), "hgl_prep: B=%d images of %dx%d outputs exceed the 32-bit tap-record offsets", B, S, S);
   HGL_REQUIRE(out_dtype == HGL_F32 || out_dtype == HGL_BF16, "hgl_prep: out_dtype %d", out_dtype);
   HGL_REQUIRE(B >= 1 && M >= 0 && H >= 1 && W >= 1 && max_n >= 1, "hgl_prep: bad shape B=%d M=%d H=%d W=%d max_n=%d", B, M, H, W, max_n);
   HGL_REQUIRE(S >= 4 && S % 4 == 0 && S <= 1024, "hgl_prep: S=%d must be a multiple of 4 in [4,1024]", S);
@@ -740,7 +745,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   const int stage_rows = std::min(H, (int)(gh_ * sy) + 3);                    // source rows behind a band
   const size_t per_mask_bytes = (size_t)((stage_rows * p.WW + 3 + 3) & ~3) * 4;   // slot of one mask: rows + lead words, whole 16-byte units
   // barriers | per-warp scratch | stages (+ the word after the last row)
-  const size_t fixed_smem = 64 + (size_t)cw * kPrepWarpBytes + 16;
+  const size_t fixed_smem = kPrepBarBytes + (size_t)cw * kPrepWarpBytes + 16;
   const size_t stage_budget = fixed_smem + 24 * 1024 <= 112 * 1024 ? 112 * 1024 - fixed_smem      // two CTAs per SM
                                                                      : (fixed_smem < 200 * 1024 ? 224 * 1024 - fixed_smem : 0);
   int kPrepSub = std::max(1, std::min(kPrepMaxSub, tuning_int("HGL_PREP_SUB", kPrepSubDefault)));
