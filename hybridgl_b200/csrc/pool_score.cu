@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_arrive();                                              // "this CTA runs": waited for before the first push into rank 0
+  bool peers_started = false;
   const uint32_t tmem_base = *tmem_slot;
   PS_TRACE(1);
 
@@ -442,6 +444,8 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
   PS_TRACE(7);
   mbar_wait(bar_acc, 0u);
   tc_fence_after();
+  __syncthreads();      // everything before the epilogue (text rows, ring contents) is also ordered by a CTA barrier, not only through the
+                        // mbarrier chain stores -> bar_afull -> MMA -> tcgen05.commit -> bar_acc (which compute-sanitizer cannot follow)
   PS_TRACE(8);
   const int quarter = warp >> 2;                                 // which 32-column groups of a row this thread reads
   const int my_row = (warp & 3) * 32 + lane;
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) pool_score_kernel(const __grid_
           }
         }
       }
+      if (!peers_started) { cluster_wait(); peers_started = true; }   // uniform: once per CTA, before its first remote store
       if (quarter) {
         float* pq = part1 + (size_t)(quarter - 1) * kNP * kPsM + my_row;
         pq[0] = ss;

@@ -215,7 +215,7 @@ struct Pack {
 
 // boundary pixel: exact per-tap evaluation (Hybridgl_main.py:106-121 restricted to the 4 taps of one output pixel).
 // Only pixels whose taps straddle the mask outline come here, through the dense per-warp resolve step of prep_main_kernel.
-// lut: tables (built by prep_setup_kernel, L1-resident) of the two per-byte maps, [0..255] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255)
+// lut: tables (built by prep_setup_kernel, copied into shared memory by every CTA) of the two per-byte maps, [0..255] = v/255 (T.ToTensor), [256 + 256*c + v] = Normalize_c(v/255)
 // -- the same correctly-rounded divisions as to_unit / to_norm, evaluated once per image batch instead of 27 times per pixel.
 __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__ taps, size_t tap0, uint32_t code,
                                                     float wx0, float wx1, float wy0, float wy1, const float* __restrict__ lut,
@@ -232,8 +232,8 @@ __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__
       const uint32_t vi = (iw[kk >> 2] >> ((kk & 3) * 8)) & 0xffu;
       const uint32_t vb = (bw[kk >> 2] >> ((kk & 3) * 8)) & 0xffu;
       const bool in = (code >> t) & 1u;
-      gv[t] = __ldg(lut + (in ? vi : vb));
-      lv[t] = in ? __ldg(lut + 256 + 256 * c + vi) : c_clip_mean[c];
+      gv[t] = lut[in ? vi : vb];
+      lv[t] = in ? lut[256 + 256 * c + vi] : c_clip_mean[c];
     }
     out6[3 + c] = __fdiv_rn(__fsub_rn(bilerp(gv[0], gv[1], gv[2], gv[3], wx0, wx1, wy0, wy1), c_in_mean[c]), c_in_std[c]);
     out6[c] = bilerp(lv[0], lv[1], lv[2], lv[3], wx0, wx1, wy0, wy1);
@@ -245,6 +245,8 @@ __device__ __forceinline__ void prep_boundary_pixel(const uint32_t* __restrict__
 #endif
 constexpr int kPrepStages = HGL_PREP_STAGES;      // shared-memory ring of bit-row stages (<= 8: the barrier block below)
 constexpr int kPrepBarBytes = 128;  // full[kPrepStages] | empty[kPrepStages] mbarriers
+constexpr int kPrepLutBytes = 4096; // the two per-byte maps (1024 floats) of the exact outline evaluation, copied in per CTA:
+                                    // data-dependent lookups hit 32 banks at once instead of up to 32 L1 sectors one after the other
 static_assert(2 * kPrepStages * 8 <= kPrepBarBytes, "barrier block");
 constexpr int kPrepSubDefault = 4;  // masks per stage (PrepParams::sub; HGL_PREP_SUB overrides for tuning)
 constexpr int kPrepWq = 512;        // per-warp list of outline pixels waiting for their exact value (>= 32 lanes x 8 pixels)
@@ -292,13 +294,13 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   extern __shared__ __align__(128) uint8_t sm_prep[];
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_prep);                       // [kPrepStages]  (kPrepBarBytes reserved for both)
   uint64_t* empty = full + kPrepStages;                                        // [kPrepStages]
-  const float* lut = p.lut;
+  float* lut = reinterpret_cast<float*>(sm_prep + kPrepBarBytes);              // [1024]
 
   const int H = p.H, W = p.W, S = p.S, WW = p.WW;
   const int SS = S * S;
   const PrepGeom gm = {p.gw, p.gh, p.cw, p.nbx, p.strip};
   const int ncons = 32 * gm.cw;                                                // consumer threads (the producer warp comes after them)
-  uint32_t* stage_base = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + (size_t)gm.cw * kPrepWarpBytes);   // [kPrepStages][kPrepSub][rows * WW] + 16 B
+  uint32_t* stage_base = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + kPrepLutBytes + (size_t)gm.cw * kPrepWarpBytes);   // [kPrepStages][kPrepSub][rows * WW] + 16 B
   // blockIdx.x = band tile * gz + z: the gz CTAs that share a band tile's answer planes (and the CTAs of one image) are dispatched
   // back to back, so the planes are fetched from HBM once per image and served from L2 to the rest (with z as a grid dimension the
   // z-slices of an image ran a wave apart and every one of them re-fetched the planes: 2.3x read amplification in ncu)
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   const int stage_words = p.stage_words;                             // ring pitch (host: kPrepSub * max slot words)
   const uint32_t* src0 = p.bits + (size_t)n_lo * mask_words + (size_t)ylo * WW - lead;
 
+  for (int t = tid; t < 1024; t += blockDim.x) lut[t] = __ldg(p.lut + t);
   if (kTMA) {
     if (tid == 0) {
       for (int s = 0; s < kPrepStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (uint32_t)gm.cw); }
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
   }
 
   // ---- consumers
-  uint32_t* wq = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + (size_t)warp * kPrepWarpBytes);   // [kPrepWq] mask << 16 | owner pixel << 4 | tap code
+  uint32_t* wq = reinterpret_cast<uint32_t*>(sm_prep + kPrepBarBytes + kPrepLutBytes + (size_t)warp * kPrepWarpBytes);   // [kPrepWq] mask << 16 | owner pixel << 4 | tap code
   int i, j0;
   prep_pixel_of(gm, bxi, byi, tid, PX, i, j0);
   const bool live = i <= row_last && j0 < S;                         // partial last band / idle lanes of the last warp (strip mode)
@@ -745,7 +748,7 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   const int stage_rows = std::min(H, (int)(gh_ * sy) + 3);                    // source rows behind a band
   const size_t per_mask_bytes = (size_t)((stage_rows * p.WW + 3 + 3) & ~3) * 4;   // slot of one mask: rows + lead words, whole 16-byte units
   // barriers | per-warp scratch | stages (+ the word after the last row)
-  const size_t fixed_smem = kPrepBarBytes + (size_t)cw * kPrepWarpBytes + 16;
+  const size_t fixed_smem = kPrepBarBytes + kPrepLutBytes + (size_t)cw * kPrepWarpBytes + 16;
   const size_t stage_budget = fixed_smem + 24 * 1024 <= 112 * 1024 ? 112 * 1024 - fixed_smem      // two CTAs per SM
                                                                      : (fixed_smem < 200 * 1024 ? 224 * 1024 - fixed_smem : 0);
   int kPrepSub = std::max(1, std::min(kPrepMaxSub, tuning_int("HGL_PREP_SUB", kPrepSubDefault)));

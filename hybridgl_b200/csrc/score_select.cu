@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_select_kernel(const Score
       }
   };
 
+  cluster_arrive();                                               // "this CTA runs": waited for before the first store into rank 0
+  bool peers_started = false;
   for (int eg = e_lo; eg < e_hi; eg += kEG) {
     const int ne = min(kEG, e_hi - eg);
     if (rank == 0) prefetch_tail(eg, ne);
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_select_kernel(const Score
       }
     }
     __syncthreads();
+    if (!peers_started) { cluster_wait(); peers_started = true; }
     // ---- cosine scores of this CTA's mask rows (model/backbone.py:79-85); lane owns features 4*lane + 128*i
     for (int m = row_lo + warp; m < row_hi; m += kScoreWarps) {
       const size_t row = (size_t)(n_lo + m) * De;

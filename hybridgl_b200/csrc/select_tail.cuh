@@ -238,6 +238,11 @@ __device__ __forceinline__ void select_tail_block(const TailArgs& t, int e_first
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Split form.  Every kernel that writes into a peer's shared memory arrives right after its own set-up and waits just before its
+// first remote access: a peer CTA must have STARTED before its shared memory may be touched (compute-sanitizer racecheck: "block
+// that might not have entered yet"), and by then every CTA has long arrived, so the wait costs nothing.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
