@@ -726,7 +726,10 @@ __global__ void __launch_bounds__(256) mask_area_kernel(const uint32_t* __restri
 static int launch_rows(RowsParams p, bool want_grid, bool want_heat, void* scratch, cudaStream_t st) {
   HGL_REQUIRE(p.WW <= 63, "mask rows pass: W=%d wider than 2016", p.W);
   p.sc = rows_carve(scratch, p.M, want_grid ? p.g : 0, want_heat ? p.E : 0, want_heat ? p.max_n : 0);
-  cudaError_t e = cudaMemsetAsync(p.sc.tickets, 0, (size_t)(p.M + 1) * 4, st);
+  // one memset: the tickets, and (grid passes) the tap-table block in front of them, whose unused slots and alignment gaps the CTAs
+  // copy along with the tables -- zero rather than uninitialised (compute-sanitizer initcheck)
+  uint8_t* z0 = want_grid ? p.sc.aatab : reinterpret_cast<uint8_t*>(p.sc.tickets);
+  cudaError_t e = cudaMemsetAsync(z0, 0, (size_t)(reinterpret_cast<uint8_t*>(p.sc.tickets) - z0) + (size_t)(p.M + 1) * 4, st);
   if (e != cudaSuccess) { set_error("mask rows pass: cudaMemsetAsync: %s", cudaGetErrorString(e)); return HGL_ECUDA; }
   size_t off = (size_t)4 * kMaxG * 4;
   auto take = [&](size_t n, size_t align) { off = (off + align - 1) & ~(align - 1); size_t o = off; off += n; return (int)o; };
