@@ -59,6 +59,8 @@ def test_sass_is_sm100(lib):
     assert "UTCHMMA" in out.stdout         # tcgen05.mma (mask pooling on the 5th-generation tensor cores)
     assert "LDTM" in out.stdout            # tcgen05.ld (TMEM accumulator read-back in the epilogue)
     assert "UBLKCP" in out.stdout          # cp.async.bulk (TMA bulk copies: bit-row stages of prep_main)
+    assert "UTMALDG.3D" in out.stdout      # cp.async.bulk.tensor.3d through a CUtensorMap (token tiles of the pooling kernel)
+    assert "UTCBAR" in out.stdout          # tcgen05.commit (MMA completion onto an mbarrier)
     assert "SYNCS.ARRIVE.TRANS64" in out.stdout   # mbarrier expect_tx / arrive (full / empty barriers of the stage ring)
 
 
