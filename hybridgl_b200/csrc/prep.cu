@@ -180,7 +180,7 @@ struct PrepParams {
   int stage_words;            // ring pitch of the shared-memory bit-row stages (words)
   int sub;                    // masks per stage
   int gw, gh, cw, nbx, strip; // thread -> pixel map (PrepGeom)
-  int flush_every;            // masks between two flushes of a warp's outline list (<= sub)
+  int flush_every;            // masks between two flushes of a warp's outline list; > sub: only when the list is full and at the CTA's end
   int debug;                  // profiling only (HGL_PREP_DEBUG): 1 = skip the exact outline pixels, 2 = skip the stores
   int narrow;                 // 1 if the 8 taps of 4 adjacent pixels always fit one 32-bit window
   int gz;                     // mask-span splits per (image, band tile)
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) prep_main_kernel(const PrepPa
         }
         wcount += total;
       }
-      if (wcount && ((k + 1) % p.flush_every) == 0) flush();          // early enough for the patched lines to be in L2 still
+      if (wcount && ((k + 1) % p.flush_every) == 0) flush();          // (only for flush_every <= sub)
     }
     if (wcount && (p.flush_every <= kPrepSub || c == nst - 1)) flush();
     if (kTMA) {                                                       // this warp is done with the slot
@@ -772,7 +772,10 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   }
   gz = std::max(1, tuning_int("HGL_PREP_GZ", gz));
   p.debug = 0;
-  p.flush_every = std::max(1, tuning_int("HGL_PREP_FLUSH", kPrepSub));
+  // outline lists are flushed as rarely as possible: when a warp's list is full, and after the CTA's last mask (a CTA lives ~15 us,
+  // so the lines it patches are still in L2).  Dense flushes cost less than frequent ones: every 1 / 2 / 4 masks 224 / 210 / 204 us
+  // alone, once per CTA 203 us and 0.466 instead of 0.474 ms per pass (profiles/r2_variants.md)
+  p.flush_every = std::max(1, tuning_int("HGL_PREP_FLUSH", 16 * kPrepMaxSub));
 #ifdef HGL_TUNING
   p.debug = tuning_int("HGL_PREP_DEBUG", 0);       // profiling builds only (results are wrong when set): never in the shipped library
 #endif
