@@ -757,7 +757,8 @@ extern "C" int hgl_prep_main(const uint32_t* bits, const int32_t* mask_off, int 
   HGL_REQUIRE((size_t)kPrepStages * kPrepSub * per_mask_bytes <= stage_budget, "hgl_prep: frame %dx%d (S=%d) too large for the shared-memory stages",
               H, W, S);
   p.stage_words = (int)(kPrepSub * per_mask_bytes / 4);
-  const size_t smem = fixed_smem + (size_t)kPrepStages * kPrepSub * per_mask_bytes;
+  // (HGL_PREP_SMEM_PAD_KB, profiling build: extra dynamic shared memory, e.g. 80 -> one CTA per SM, to measure prep at half residency)
+  const size_t smem = fixed_smem + (size_t)kPrepStages * kPrepSub * per_mask_bytes + (size_t)tuning_int("HGL_PREP_SMEM_PAD_KB", 0) * 1024;
   const int resident = std::max(1, std::min(std::min(2 * kPrepThreads / threads, (int)((220 * 1024) / (smem + 1024))), 65536 / (threads * 128)));
   const long slots = (long)sm_count() * resident;
   int gz = 1;

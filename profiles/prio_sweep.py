@@ -13,8 +13,8 @@ B = 16
 H, W, N, E, S, g, De = cfg["h"], cfg["w"], cfg["n_masks"], cfg["n_expr"], cfg["S"], cfg["g"], cfg["De"]
 batches = [synth.make_batch_device(1234 + i, B, H, W, N, E, De, device="cuda", grid=g, raw_heat=True) for i in range(2)]
 print("priority range", torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else "?")
-cands = {"tab -1 side -1 pre -1 (round 1)": (-1, -1, -1), "tab -3 side -2 pre -1 (HEAD)": (-2, -1, -3), "tab -3 side -1 pre 0": (-1, 0, -3),
-         "tab -3 side -3 pre -1": (-3, -1, -3), "tab -3 side -2 pre -3": (-2, -3, -3), "tab -1 side -1 pre -3": (-1, -3, -1), "all 0": (0, 0, 0)}
+cands = {"tab -3 side -2 pre -1 (HEAD)": (-2, -1, -3), "tab -3 side -2 pre -3": (-2, -3, -3), "tab -2 side -2 pre -3": (-2, -3, -2), "tab -3 side -1 pre -3": (-1, -3, -3),
+         "all -1": (-1, -1, -1), "tab -3 side -3 pre -3": (-3, -3, -3)}
 paths = {}
 for name, (ps, pp, pt) in cands.items():
     path = ScoringPath(size=S, grid=g, feature_source="tokens", overlap=True)
