@@ -648,6 +648,33 @@ def test_pool_score_select_empty_image_and_no_expressions(ops):
     np.testing.assert_allclose(res["features"][5:].cpu().numpy(), O.mask_pool_tokens(w[5:], tok[2]), rtol=1e-3, atol=1e-5)
 
 
+def test_pool_score_select_capacity(ops):
+    """The largest image the pooling kernel takes (512 proposals: four 128-row tiles in TMEM) against the oracle, and the explicit
+    error one proposal beyond it (no silent truncation)."""
+    rng = np.random.default_rng(6)
+    L, D, n = 49, 128, 512
+    w = rng.random((n, L)).astype(np.float32); w[rng.random((n, L)) < 0.5] = 0.0
+    tok = synth.bf16_round(rng.standard_normal((1, L, D)).astype(np.float32))
+    sent = rng.standard_normal((1, D)).astype(np.float32); noun = rng.standard_normal((1, D)).astype(np.float32)
+    boxes = np.ones((n, 4), np.int64)
+
+    def call(k):
+        return ops.pool_score_select(cu(w[:k]), cu(tok, torch.bfloat16), cu(sent), cu(noun), cu(np.zeros((0, D), np.float32)), cu(np.zeros(2, np.int32)),
+                                     cu(boxes[:k]), cu(np.zeros(1, np.int32)), None, cu(np.array([0, k], np.int32)), cu(np.array([0, 1], np.int32)), k,
+                                     100.0, 0.5, 0.6, want_features=True, dtype=torch.float32)
+    res = call(n)
+    torch.cuda.synchronize()
+    f_ref = O.mask_pool_tokens(w, tok[0])
+    np.testing.assert_allclose(res["features"].cpu().numpy(), f_ref, rtol=1e-3, atol=1e-5)
+    r = O.score_and_select(f_ref, sent[0], noun[0], np.zeros((0, D), np.float32), boxes, "none")
+    np.testing.assert_allclose(res["score_clip"][0].cpu().numpy(), r["score_clip"], rtol=1e-3, atol=1e-3)
+    if _selection_margin_ok(r):
+        assert int(res["idx_hybrid"][0]) == r["idx_hybrid"]
+    w = np.concatenate([w, w[:1]]); boxes = np.concatenate([boxes, boxes[:1]])
+    with pytest.raises(RuntimeError, match="TMEM accumulator budget"):
+        call(n + 1)
+
+
 def test_pipeline_token_features_vs_oracle(ops):
     """ScoringPath(feature_source="tokens"): grid masks -> tcgen05 pooling + scoring in one kernel, against the oracle chain."""
     from hybridgl_b200.pipeline import ScoringPath
